@@ -1,0 +1,108 @@
+"""ctypes binding of libatlj.so (include/atlj.h).  No CPU fallback: if the library is missing or no
+CUDA device is usable, every compute call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatlj.so")
+
+OK, ERR_DIM, ERR_SMALL, ERR_INDEX, ERR_MISMATCH, ERR_CUDA, ERR_ARG = 0, -1, -2, -3, -4, -100, -101
+MODEL_LJ, MODEL_WCA = 0, 1
+NREC = 12
+
+# the reference's assertion messages (SURVEY.md 8b "Errors")
+_ASSERTS = {
+    ERR_DIM: "Dimension error in force",            # md_lj_module.py:77
+    ERR_SMALL: "System is too small for cells",     # md_lj_ll_module.py:107
+    ERR_INDEX: "Index error",                       # md_lj_ll_module.py:109
+    ERR_MISMATCH: "Dimension mismatch in hessian",  # md_lj_module.py:163
+}
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_lib = None
+
+
+class AtljError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libatlj.so (built by __graft_entry__.build() / make -C examples_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AtljError("%s not found: build it with `make -C examples_b200/csrc` (nvcc, sm_100a). "
+                        "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.atlj_version.restype = C.c_int
+    L.atlj_last_error.restype = C.c_char_p
+    L.atlj_device_count.restype = C.c_int
+    L.atlj_set_device.argtypes = [C.c_int]
+    L.atlj_kernel_launches.restype = C.c_int64
+    L.atlj_force_lj.argtypes = [_dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    L.atlj_force_le.argtypes = [_dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                C.c_int, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    L.atlj_hessian_lj.argtypes = [_dp, _dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                  C.POINTER(C.c_double)]
+    L.atlj_cells.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, C.c_double, _i64p, _i32p, _i32p]
+    L.atlj_neighbour_cells.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p]
+    L.atlj_sim_create.restype = _vp
+    L.atlj_sim_create.argtypes = [C.c_int64, _vp]
+    L.atlj_sim_destroy.restype = None
+    L.atlj_sim_destroy.argtypes = [_vp]
+    L.atlj_sim_configure.argtypes = [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                     C.c_int]
+    L.atlj_sim_upload.argtypes = [_vp, _vp, _vp, _vp, C.c_int64]
+    L.atlj_sim_download.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]
+    L.atlj_sim_natoms.restype = C.c_int64
+    L.atlj_sim_natoms.argtypes = [_vp]
+    L.atlj_sim_force.argtypes = [_vp, C.c_double, C.c_int, _vp]
+    L.atlj_sim_run_nve.argtypes = [_vp, C.c_double, C.c_int, C.c_int, _vp]
+    L.atlj_sim_run_baoab.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp]
+    L.atlj_sim_run_baoab_noise.argtypes = [_vp, C.c_double, C.c_double, C.c_double, _vp, C.c_int, _vp]
+    L.atlj_sim_run_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
+    L.atlj_sim_run_sllod.argtypes = [_vp, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, _vp]
+    L.atlj_sim_mg_drift_pack.argtypes = [_vp, C.c_double, _vp, _vp, C.c_int64]
+    L.atlj_sim_mg_bin_pack.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64]
+    L.atlj_sim_mg_force_kick.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_double, _vp]
+    L.atlj_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
+    L.atlj_sim_enable_timing.argtypes = [_vp, C.c_int]
+    L.atlj_sim_timing.argtypes = [_vp, _dp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    """Map a library status to the reference's behaviour: AssertionError with the reference's text for its
+    own assertion conditions, AtljError otherwise."""
+    if rc == OK:
+        return
+    if rc in _ASSERTS:
+        raise AssertionError(_ASSERTS[rc])
+    msg = lib().atlj_last_error().decode("utf-8", "replace")
+    raise AtljError("libatlj error %d: %s" % (rc, msg))
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    return lib().atlj_device_count()
+
+
+def kernel_launches():
+    return int(lib().atlj_kernel_launches())
+
+
+def measure_fp64_peak():
+    v = C.c_double(0.0)
+    check(lib().atlj_measure_fp64_peak(C.byref(v)))
+    return v.value

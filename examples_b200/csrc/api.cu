@@ -1,0 +1,555 @@
+// C ABI of libatlj.so (include/atlj.h): device-resident simulation object + stateless host-array entry points.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "integrate.cuh"
+#include "sim.cuh"
+
+namespace atlj {
+
+static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int device_ok() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no usable CUDA device (%s); libatlj has no CPU path", e == cudaSuccess ? "device count 0"
+                                                                                       : cudaGetErrorString(e));
+    return ATLJ_ERR_CUDA;
+  }
+  return ATLJ_OK;
+}
+
+// ---- timing -------------------------------------------------------------------------------------------------------
+void Timer::begin(atlj_sim *s, int cat) {
+  if (!s->timing) return;
+  cudaEvent_t e0, e1;
+  if (s->ev_free.size() >= 2) {
+    e0 = s->ev_free.back(), s->ev_free.pop_back();
+    e1 = s->ev_free.back(), s->ev_free.pop_back();
+  } else {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+  }
+  cudaEventRecord(e0, s->st);
+  s->ev_open.push_back({e0, e1, cat});
+}
+void Timer::end(atlj_sim *s) {
+  if (!s->timing) return;
+  auto &t = s->ev_open.back();
+  cudaEventRecord(t.e1, s->st);
+  s->ev_done.push_back(t);
+  s->ev_open.pop_back();
+}
+
+// ---- allocation ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+  ATLJ_CUDA(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+  return ATLJ_OK;
+}
+
+static int ensure_cells(atlj_sim *s, int ncell) {
+  if (ncell <= s->ncell_alloc) return ATLJ_OK;
+  cudaFree(s->cb.cell_count);
+  cudaFree(s->cb.cell_start);
+  s->cb.cell_count = s->cb.cell_start = nullptr;
+  int rc;
+  if ((rc = dev_alloc(&s->cb.cell_count, (size_t)ncell))) return rc;
+  if ((rc = dev_alloc(&s->cb.cell_start, (size_t)ncell + 1))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)ncell, s->st));
+  ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_start, 0, sizeof(int) * ((size_t)ncell + 1), s->st));
+  s->ncell_alloc = ncell;
+  return ATLJ_OK;
+}
+
+static int ensure_rec(atlj_sim *s, int64_t nrec) {
+  if (nrec <= s->rec_cap) return ATLJ_OK;
+  cudaFree(s->rec_dev);
+  s->rec_dev = nullptr;
+  int rc = dev_alloc(&s->rec_dev, (size_t)nrec * ATLJ_NREC);
+  if (rc) return rc;
+  s->rec_cap = nrec;
+  return ATLJ_OK;
+}
+
+// ---- one force evaluation on the current positions ----------------------------------------------------------------------
+// Cell route: wrap+assign -> scan -> scatter/sort/gather (atoms re-ordered into cell order, buffers swapped) -> pair
+// kernel -> finalize.  All-pairs route (sc < 4): pair_all on the current order.
+int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs) {
+  int rc;
+  const int n = (int)s->n;
+  Phys p = s->p;
+  p.strain = strain;
+  p.shift = (p.model == ATLJ_MODEL_WCA) ? (int)floor(strain * s->g.sc) : 0;  // md_lj_llle_module.py:112
+  ATLJ_CUDA(cudaMemsetAsync(rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if (s->use_cells) {
+    const int cur = s->cur, alt = 1 - s->cur;
+    Timer::begin(s, 1);
+    // the Lees-Edwards x pre-correction (md_lj_llle_module.py:94) is applied by the caller (shim / A propagator)
+    if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], n, false, strain, s->cb, nullptr))) return rc;
+    if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
+    if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
+                                      s->id[alt])))
+      return rc;
+    Timer::end(s);
+    s->cur = alt;
+    PairArgs a;
+    a.r = s->r[alt];
+    a.fin = nullptr;
+    a.cell_start = s->cb.cell_start;
+    a.cell_count = s->cb.cell_count;
+    a.f = s->f;
+    a.partials = s->partials;
+    a.g = s->g;
+    a.p = p;
+    Timer::begin(s, 0);
+    int nb = launch_pair_cells(s->st, a, false, n);
+    Timer::end(s);
+    if (nb < 0) return nb;
+    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev))) return rc;
+    if (with_hessian) {
+      a.fin = s->f;
+      a.f = nullptr;
+      Timer::begin(s, 3);
+      nb = launch_pair_cells(s->st, a, true, n);
+      Timer::end(s);
+      if (nb < 0) return nb;
+      if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
+    }
+  } else {
+    if (check_index_allpairs) {  // honour md_lj_ll_module.py:107-109 even though sc < 4 is served by all pairs
+      Geom g = s->g;
+      if ((rc = launch_cell_assign(s->st, g, s->r[s->cur], nullptr, n, false, strain, s->cb, nullptr))) return rc;
+    }
+    int nb = 0;
+    Timer::begin(s, 0);
+    if ((rc = launch_pair_all(s->st, s->r[s->cur], nullptr, n, p, s->f, s->partials, false, &nb))) return rc;
+    Timer::end(s);
+    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev))) return rc;
+    if (with_hessian) {
+      if ((rc = launch_pair_all(s->st, s->r[s->cur], s->f, n, p, nullptr, s->partials, true, &nb))) return rc;
+      if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
+    }
+  }
+  return ATLJ_OK;
+}
+
+// read back and clear the device error flags; maps to the reference's assertion codes
+int sim_check_flags(atlj_sim *s) {
+  int h[4] = {0, 0, 0, 0};
+  ATLJ_CUDA(cudaMemcpyAsync(h, s->cb.err, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  if (h[0] || h[1]) ATLJ_CUDA(cudaMemsetAsync(s->cb.err, 0, sizeof(h), s->st));
+  if (h[0]) {
+    set_error("Index error");
+    return ATLJ_ERR_INDEX;
+  }
+  if (h[1]) {
+    set_error("buffer capacity exceeded (migration / halo)");
+    return ATLJ_ERR_ARG;
+  }
+  return ATLJ_OK;
+}
+
+int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps) {
+  if (rec_host)
+    ATLJ_CUDA(cudaMemcpyAsync(rec_host, s->rec_dev, sizeof(double) * ATLJ_NREC * (size_t)nsteps,
+                              cudaMemcpyDeviceToHost, s->st));
+  return sim_check_flags(s);
+}
+
+}  // namespace atlj
+
+using namespace atlj;
+
+// =====================================================================================================================
+extern "C" {
+
+int atlj_version(void) { return 100; }
+const char *atlj_last_error(void) { return g_err; }
+int64_t atlj_kernel_launches(void) { return g_launches; }
+
+int atlj_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int atlj_set_device(int device) {
+  int rc = device_ok();
+  if (rc) return rc;
+  ATLJ_CUDA(cudaSetDevice(device));
+  return ATLJ_OK;
+}
+
+atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
+  if (device_ok() != ATLJ_OK) return nullptr;
+  if (capacity < 1) capacity = 1;
+  if (capacity > (1ll << 30)) {
+    set_error("capacity too large");
+    return nullptr;
+  }
+  atlj_sim *s = new atlj_sim();
+  s->st = (cudaStream_t)stream;
+  s->cap = capacity;
+  size_t c = (size_t)capacity;
+  bool ok = true;
+  for (int k = 0; k < 2 && ok; k++) {
+    ok = ok && dev_alloc(&s->r[k], 3 * c) == ATLJ_OK && dev_alloc(&s->v[k], 3 * c) == ATLJ_OK &&
+         dev_alloc(&s->id[k], c) == ATLJ_OK;
+  }
+  ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
+       dev_alloc(&s->cb.rank, c) == ATLJ_OK && dev_alloc(&s->cb.keys, c) == ATLJ_OK &&
+       dev_alloc(&s->cb.block_sums, 8192) == ATLJ_OK && dev_alloc(&s->cb.err, 4) == ATLJ_OK &&
+       dev_alloc(&s->partials, (size_t)pair_grid_blocks() * 8) == ATLJ_OK && dev_alloc(&s->scal, 64) == ATLJ_OK;
+  if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 4 * sizeof(int), s->st) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(s->scal, 0, 64 * sizeof(double), s->st) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(s->f, 0, 3 * c * sizeof(double), s->st) == cudaSuccess;
+  if (ok) ok = ensure_rec(s, 64) == ATLJ_OK;
+  if (!ok) {
+    atlj_sim_destroy(s);
+    return nullptr;
+  }
+  return s;
+}
+
+void atlj_sim_destroy(atlj_sim *s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->st);
+  for (int k = 0; k < 2; k++) cudaFree(s->r[k]), cudaFree(s->v[k]), cudaFree(s->id[k]);
+  cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
+  cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
+  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev);
+  for (auto e : s->ev_free) cudaEventDestroy(e);
+  for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+  for (auto &t : s->ev_open) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+  delete s;
+}
+
+int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, double box_sq, double pot_cut, int sc,
+                       int x_lo, int x_hi) {
+  if (!s) return ATLJ_ERR_ARG;
+  if (model != ATLJ_MODEL_LJ && model != ATLJ_MODEL_WCA) {
+    set_error("unknown model %d", model);
+    return ATLJ_ERR_ARG;
+  }
+  s->p.model = model;
+  s->p.box = box;
+  s->p.box_sq = box_sq;
+  s->p.r_cut_box_sq = r_cut_box_sq;
+  s->p.pot_cut = pot_cut;
+  s->p.strain = 0.0;
+  s->p.shift = 0;
+  s->use_cells = sc >= 4;
+  if (sc < 1) sc = 1;
+  if (sc > 1024) {
+    set_error("sc = %d exceeds 1024 cells per edge", sc);
+    return ATLJ_ERR_ARG;
+  }
+  if (x_lo < 0 || x_hi > sc || x_hi <= x_lo) {
+    set_error("bad slab [%d,%d) for sc=%d", x_lo, x_hi, sc);
+    return ATLJ_ERR_ARG;
+  }
+  Geom g;
+  g.sc = sc;
+  g.x_lo = x_lo;
+  g.nx_own = x_hi - x_lo;
+  g.h = (g.nx_own == sc) ? 0 : 1;
+  g.nxl = g.nx_own + 2 * g.h;
+  s->g = g;
+  // prefilter threshold in cell units with a 1e-4 relative margin (error bound of the fp32 path ~1.5e-6)
+  double rc_cell = sqrt(r_cut_box_sq) * sc;
+  s->p.rc2_cell = (float)(rc_cell * rc_cell * (1.0 + 1e-4));
+  s->configured = true;
+  return ensure_cells(s, g.ncell());
+}
+
+int atlj_sim_upload(atlj_sim *s, const double *r_host, const double *v_host, const int32_t *id_host, int64_t n) {
+  if (!s || !r_host || n < 0 || n > s->cap) {
+    set_error("upload: bad arguments (n=%lld, capacity=%lld)", (long long)n, s ? (long long)s->cap : -1ll);
+    return ATLJ_ERR_ARG;
+  }
+  s->n = n;
+  s->cur = 0;
+  size_t b = sizeof(double) * 3 * (size_t)n;
+  ATLJ_CUDA(cudaMemcpyAsync(s->r[0], r_host, b, cudaMemcpyHostToDevice, s->st));
+  if (v_host)
+    ATLJ_CUDA(cudaMemcpyAsync(s->v[0], v_host, b, cudaMemcpyHostToDevice, s->st));
+  else
+    ATLJ_CUDA(cudaMemsetAsync(s->v[0], 0, b, s->st));
+  if (id_host)
+    ATLJ_CUDA(cudaMemcpyAsync(s->id[0], id_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->st));
+  else {
+    int rc = launch_iota(s->st, (int)n, s->id[0]);
+    if (rc) return rc;
+  }
+  ATLJ_CUDA(cudaMemsetAsync(s->f, 0, b, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));  // the host arrays may be reused by the caller
+  return ATLJ_OK;
+}
+
+int64_t atlj_sim_natoms(atlj_sim *s) { return s ? s->n : -1; }
+
+int atlj_sim_download(atlj_sim *s, double *r_host, double *v_host, double *f_host, int32_t *id_host, int64_t *n_out) {
+  if (!s) return ATLJ_ERR_ARG;
+  size_t b = sizeof(double) * 3 * (size_t)s->n;
+  if (r_host) ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  if (v_host) ATLJ_CUDA(cudaMemcpyAsync(v_host, s->v[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  if (f_host) ATLJ_CUDA(cudaMemcpyAsync(f_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
+  if (id_host)
+    ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  if (n_out) *n_out = s->n;
+  return ATLJ_OK;
+}
+
+int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_host) {
+  if (!s || !s->configured) return ATLJ_ERR_ARG;
+  int rc = sim_force(s, strain, with_hessian != 0, s->rec_dev, true);
+  if (rc) return rc;
+  if ((rc = launch_vf_sums(s->st, 3 * s->n, s->v[s->cur], s->f, s->partials, s->rec_dev + 4))) return rc;
+  return sim_copy_rec(s, rec_host, 1);
+}
+
+int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host) {
+  if (!s || !s->configured || nsteps < 0) return ATLJ_ERR_ARG;
+  int rc = ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc) return rc;
+  const long long n3 = 3 * s->n;
+  const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    Timer::begin(s, 2);
+    if ((rc = launch_kick_drift(s->st, n3, s->r[s->cur], s->v[s->cur], s->f, half_dt, dt, s->p.box, nullptr)))
+      return rc;
+    Timer::end(s);
+    if ((rc = sim_force(s, 0.0, with_hessian != 0, rec, false))) return rc;
+    Timer::begin(s, 2);
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4))) return rc;
+    Timer::end(s);
+  }
+  return sim_copy_rec(s, rec_host, nsteps);
+}
+
+int atlj_sim_enable_timing(atlj_sim *s, int on) {
+  if (!s) return ATLJ_ERR_ARG;
+  s->timing = on != 0;
+  return ATLJ_OK;
+}
+
+int atlj_sim_timing(atlj_sim *s, double ms[4]) {
+  if (!s) return ATLJ_ERR_ARG;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  for (int k = 0; k < 4; k++) ms[k] = 0.0;
+  for (auto &t : s->ev_done) {
+    float m = 0.f;
+    if (cudaEventElapsedTime(&m, t.e0, t.e1) == cudaSuccess) ms[t.cat & 3] += m;
+    s->ev_free.push_back(t.e0);
+    s->ev_free.push_back(t.e1);
+  }
+  s->ev_done.clear();
+  return ATLJ_OK;
+}
+
+int atlj_measure_fp64_peak(double *flops_per_s) {
+  int rc = device_ok();
+  if (rc) return rc;
+  double *scratch = nullptr;
+  ATLJ_CUDA(cudaMalloc((void **)&scratch, 64));
+  rc = measure_fp64_peak(0, scratch, flops_per_s);
+  cudaFree(scratch);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stateless drop-in entry points: a cached simulation object sized to the largest n seen so far
+// ---------------------------------------------------------------------------------------------------------------------
+static atlj_sim *g_host_sim = nullptr;
+
+static atlj_sim *host_sim(int64_t n) {
+  if (g_host_sim && g_host_sim->cap >= n) return g_host_sim;
+  if (g_host_sim) atlj_sim_destroy(g_host_sim);
+  g_host_sim = atlj_sim_create(n + n / 8 + 1024, nullptr);
+  return g_host_sim;
+}
+
+static int force_host(int model, const double *r_host, int64_t n, double box, double rcbsq, double bsq, double pot_cut,
+                      double strain, int sc, int check_index, double *f_host, double totals[4], int *ovr,
+                      int64_t *npair) {
+  int rc = device_ok();
+  if (rc) return rc;
+  if (!r_host || !f_host || !totals || !ovr || n < 1) {
+    set_error("force: bad arguments");
+    return ATLJ_ERR_ARG;
+  }
+  if (check_index && sc < 3) return ATLJ_ERR_SMALL;  // md_lj_ll_module.py:107
+  atlj_sim *s = host_sim(n);
+  if (!s) return ATLJ_ERR_CUDA;
+  if ((rc = atlj_sim_configure(s, model, box, rcbsq, bsq, pot_cut, sc > 0 ? sc : 1, 0, sc > 0 ? sc : 1))) return rc;
+  if ((rc = atlj_sim_upload(s, r_host, nullptr, nullptr, n))) return rc;
+  if ((rc = sim_force(s, strain, false, s->rec_dev, check_index != 0))) return rc;
+  double *src = s->f;
+  if (s->use_cells) {  // back to the caller's atom order
+    src = s->r[1 - s->cur];
+    if ((rc = launch_unsort(s->st, (int)n, s->id[s->cur], s->f, src))) return rc;
+  }
+  ATLJ_CUDA(cudaMemcpyAsync(f_host, src, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->st));
+  double rec[ATLJ_NREC];
+  if ((rc = sim_copy_rec(s, rec, 1))) return rc;
+  for (int k = 0; k < 4; k++) totals[k] = rec[k];
+  *ovr = rec[7] != 0.0;
+  if (npair) *npair = (int64_t)rec[8];
+  return ATLJ_OK;
+}
+
+int atlj_force_lj(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double pot_cut,
+                  int sc, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair) {
+  return force_host(ATLJ_MODEL_LJ, r_host, n, box, r_cut_box_sq, box_sq, pot_cut, 0.0, sc, check_index, f_host, totals,
+                    ovr, npair);
+}
+
+int atlj_force_le(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double strain,
+                  int sc, int shift, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair) {
+  (void)shift;  // recomputed as floor(strain*sc) on the host side of the library; the argument documents the contract
+  return force_host(ATLJ_MODEL_WCA, r_host, n, box, r_cut_box_sq, box_sq, 0.0, strain, sc, check_index, f_host, totals,
+                    ovr, npair);
+}
+
+int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, double box, double r_cut_box_sq,
+                    double box_sq, int sc, int check_index, double *hes) {
+  int rc = device_ok();
+  if (rc) return rc;
+  if (!r_host || !f_host || !hes || n < 1) {
+    set_error("hessian: bad arguments");
+    return ATLJ_ERR_ARG;
+  }
+  if (check_index && sc < 3) return ATLJ_ERR_SMALL;
+  atlj_sim *s = host_sim(n);
+  if (!s) return ATLJ_ERR_CUDA;
+  if ((rc = atlj_sim_configure(s, ATLJ_MODEL_LJ, box, r_cut_box_sq, box_sq, 0.0, sc > 0 ? sc : 1, 0, sc > 0 ? sc : 1)))
+    return rc;
+  // the caller's forces ride through the sort in the velocity slot
+  if ((rc = atlj_sim_upload(s, r_host, f_host, nullptr, n))) return rc;
+  Phys p = s->p;
+  int nb = 0;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if (s->use_cells) {
+    const int cur = s->cur, alt = 1 - cur;
+    if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], (int)n, false, 0.0, s->cb, nullptr))) return rc;
+    if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
+    if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, (int)n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
+                                      s->v[alt], s->id[alt])))
+      return rc;
+    s->cur = alt;
+    PairArgs a;
+    a.r = s->r[alt];
+    a.fin = s->v[alt];
+    a.cell_start = s->cb.cell_start;
+    a.cell_count = s->cb.cell_count;
+    a.f = nullptr;
+    a.partials = s->partials;
+    a.g = s->g;
+    a.p = p;
+    nb = launch_pair_cells(s->st, a, true, (int)n);
+    if (nb < 0) return nb;
+  } else {
+    if (check_index)
+      if ((rc = launch_cell_assign(s->st, s->g, s->r[s->cur], nullptr, (int)n, false, 0.0, s->cb, nullptr))) return rc;
+    if ((rc = launch_pair_all(s->st, s->r[s->cur], s->v[s->cur], (int)n, p, nullptr, s->partials, true, &nb)))
+      return rc;
+  }
+  if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, s->rec_dev))) return rc;
+  double rec[ATLJ_NREC];
+  if ((rc = sim_copy_rec(s, rec, 1))) return rc;
+  *hes = rec[6];
+  return ATLJ_OK;
+}
+
+int atlj_cells(const double *r_host, int64_t n, int sc, int le, double strain, int64_t *c_host, int32_t *perm_host,
+               int32_t *cell_start_host) {
+  int rc = device_ok();
+  if (rc) return rc;
+  if (!r_host || n < 1) return ATLJ_ERR_ARG;
+  if (sc < 3) return ATLJ_ERR_SMALL;
+  atlj_sim *s = host_sim(n);
+  if (!s) return ATLJ_ERR_CUDA;
+  if ((rc = atlj_sim_configure(s, le ? ATLJ_MODEL_WCA : ATLJ_MODEL_LJ, 1.0, 1.0, 1.0, 0.0, sc, 0, sc))) return rc;
+  if ((rc = atlj_sim_upload(s, r_host, nullptr, nullptr, n))) return rc;
+  long long *c_dev = nullptr;
+  ATLJ_CUDA(cudaMalloc((void **)&c_dev, sizeof(long long) * 3 * (size_t)n));
+  const int cur = s->cur, alt = 1 - cur;
+  rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], (int)n, le != 0, strain, s->cb, c_dev);
+  if (!rc) rc = launch_cell_scan(s->st, s->g, s->cb, 0);
+  if (!rc)
+    rc = launch_cell_sort_gather(s->st, s->g, s->cb, (int)n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
+                                 s->id[alt]);
+  if (!rc) {
+    s->cur = alt;
+    cudaError_t e = cudaSuccess;
+    if (c_host)
+      e = cudaMemcpyAsync(c_host, c_dev, sizeof(long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess && perm_host)
+      e = cudaMemcpyAsync(perm_host, s->id[alt], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess && cell_start_host)
+      e = cudaMemcpyAsync(cell_start_host, s->cb.cell_start, sizeof(int) * ((size_t)s->g.ncell() + 1),
+                          cudaMemcpyDeviceToHost, s->st);
+    if (e != cudaSuccess) {
+      set_error("atlj_cells copy: %s", cudaGetErrorString(e));
+      rc = ATLJ_ERR_CUDA;
+    }
+  }
+  int rc2 = sim_check_flags(s);  // synchronises
+  cudaFree(c_dev);
+  return rc ? rc : rc2;
+}
+
+__global__ void neighbour_table_kernel(Geom g, int le, int shift, int *__restrict__ nb, int *__restrict__ cnt) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell()) return;
+  int sc = g.sc;
+  int lx = c / (sc * sc), cy = (c / sc) % sc, cz = c % sc;
+  int m = 0;
+  for (int k = 0; k < MAX_NB; k++) {
+    int nc = neighbour_cell(g, le != 0, shift, lx, cy, cz, k);
+    nb[(size_t)c * MAX_NB + k] = nc;
+    if (nc >= 0) m++;
+  }
+  cnt[c] = m;
+}
+
+int atlj_neighbour_cells(int sc, int le, int shift, int32_t *nb_host, int32_t *count_host) {
+  int rc = device_ok();
+  if (rc) return rc;
+  if (sc < 3 || sc > 256 || !nb_host || !count_host) return ATLJ_ERR_ARG;
+  Geom g;
+  g.sc = sc, g.x_lo = 0, g.nx_own = sc, g.h = 0, g.nxl = sc;
+  int nc = g.ncell();
+  int *nb = nullptr, *cnt = nullptr;
+  ATLJ_CUDA(cudaMalloc((void **)&nb, sizeof(int) * (size_t)nc * MAX_NB));
+  ATLJ_CUDA(cudaMalloc((void **)&cnt, sizeof(int) * (size_t)nc));
+  neighbour_table_kernel<<<(nc + 127) / 128, 128>>>(g, le, shift, nb, cnt);
+  ATLJ_LAUNCHED();
+  ATLJ_CUDA(cudaMemcpy(nb_host, nb, sizeof(int) * (size_t)nc * MAX_NB, cudaMemcpyDeviceToHost));
+  ATLJ_CUDA(cudaMemcpy(count_host, cnt, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost));
+  cudaFree(nb);
+  cudaFree(cnt);
+  return ATLJ_OK;
+}
+
+}  // extern "C"

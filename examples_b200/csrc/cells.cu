@@ -1,0 +1,275 @@
+// Link-cell construction as a counting sort.
+//
+// Reference: python_examples/md_lj_ll_module.py:88,106-120 (wrap, cell triplets, per-cell atom lists in C order of
+// cells and ascending atom index) and link_list_module.f90:103-161 (make_list / c_index / create_in_list).
+// The integer results (triplets, per-cell membership and order) are bit-identical to the reference's; the
+// algorithm is not the reference's O(N * cells) mask sweep nor the Fortran head/list chain:
+//   1. cell_assign : wrap, triplet, local cell id; one atomicAdd per atom gives the per-cell histogram and an
+//                    arrival rank inside the cell                                  (reads 24 B, writes 8 B / atom)
+//   2. cell_scan   : exclusive scan of the histogram -> cell_start                 (4 B / cell, three small kernels)
+//   3. cell_scatter: key = (atom id << 32 | source index) -> slot cell_start + rank
+//   4. cell_sort   : one thread per cell orders its <= ~30 keys by atom id (the arrival rank of step 1 is
+//                    scheduling dependent, the sorted result is not) -> "ascending atom index" of the reference
+//   5. gather      : r (and v, id) copied into cell order
+// All HBM-bound; see DESIGN.md for bytes per atom.
+#include "common.cuh"
+
+namespace atlj {
+
+// ---- 1. wrap + assign ---------------------------------------------------------------------------------------
+// The triplet must be floor((w+0.5)*sc) with the add and the multiply rounded separately (NumPy evaluates
+// (r+0.5)*sc as two ufunc passes), so the intrinsics below forbid FMA contraction.
+__global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *__restrict__ r_in,
+                                                          double *__restrict__ r_wr, int n, int le, double strain,
+                                                          int *__restrict__ cellid, int *__restrict__ rank,
+                                                          int *__restrict__ cell_count, int *__restrict__ err,
+                                                          long long *__restrict__ c_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = r_in[3 * i], y = r_in[3 * i + 1], z = r_in[3 * i + 2];
+  if (le) x = __dsub_rn(x, __dmul_rn(rint(y), strain));  // md_lj_llle_module.py:94
+  x = __dsub_rn(x, rint(x));                              // md_lj_ll_module.py:88
+  y = __dsub_rn(y, rint(y));
+  z = __dsub_rn(z, rint(z));
+  if (r_wr) {
+    r_wr[3 * i] = x;
+    r_wr[3 * i + 1] = y;
+    r_wr[3 * i + 2] = z;
+  }
+  double scd = (double)g.sc;
+  long long c0 = (long long)floor(__dmul_rn(__dadd_rn(x, 0.5), scd));  // md_lj_ll_module.py:108
+  long long c1 = (long long)floor(__dmul_rn(__dadd_rn(y, 0.5), scd));
+  long long c2 = (long long)floor(__dmul_rn(__dadd_rn(z, 0.5), scd));
+  if (c_out) {
+    c_out[3 * i] = c0;
+    c_out[3 * i + 1] = c1;
+    c_out[3 * i + 2] = c2;
+  }
+  bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc;  // md_lj_ll_module.py:109
+  int lx = (int)c0 - g.x_lo + g.h;
+  if (!bad && (lx < g.h || lx >= g.h + g.nx_own)) bad = true;  // not an owned layer (caller migrates first)
+  if (bad) {
+    atomicOr(&err[0], 1);
+    cellid[i] = -1;
+    rank[i] = 0;
+    return;
+  }
+  int cid = (lx * g.sc + (int)c1) * g.sc + (int)c2;
+  cellid[i] = cid;
+  rank[i] = atomicAdd(&cell_count[cid], 1);
+}
+
+int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
+                       double strain, const CellBufs &b, long long *c_out) {
+  ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+  if (n > 0) {
+    cell_assign_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, r_in, r_wrapped, n, le ? 1 : 0, strain, b.cellid, b.rank,
+                                                         b.cell_count, b.err, c_out);
+    ATLJ_LAUNCHED();
+  }
+  return ATLJ_OK;
+}
+
+// ---- 2. exclusive scan over the owned cells ------------------------------------------------------------------
+constexpr int SCAN_T = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_T * SCAN_ITEMS;  // 4096 cells per block
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem /*[SCAN_T/32]*/, int *total) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < SCAN_T / 32 ? smem[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) si += t;
+    }
+    if (lane < SCAN_T / 32) smem[lane] = si - s;  // exclusive warp offsets
+    if (lane == 31) *total = si;
+  }
+  __syncthreads();
+  return incl - v + smem[w];
+}
+
+// phase A: per-tile sums
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums_kernel(const int *__restrict__ cnt, int n,
+                                                                int *__restrict__ tile_sums) {
+  __shared__ int sm[SCAN_T / 32];
+  __shared__ int total;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += cnt[base + k];
+  block_exclusive_scan(s, sm, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// phase B: scan the tile sums in place (one block; ntiles <= SCAN_TILE)
+__global__ void __launch_bounds__(SCAN_T) scan_tile_offsets_kernel(int *__restrict__ tile_sums, int ntiles) {
+  __shared__ int sm[SCAN_T / 32];
+  __shared__ int total;
+  int base = threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < ntiles ? tile_sums[base + k] : 0;
+    s += v[k];
+  }
+  int off = block_exclusive_scan(s, sm, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < ntiles) tile_sums[base + k] = off;
+    off += v[k];
+  }
+}
+
+// phase C: final exclusive scan, cell_start[first + c] = base + prefix; also writes the end sentinel
+__global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restrict__ cnt, int n,
+                                                            const int *__restrict__ tile_off, int base_off,
+                                                            int *__restrict__ start) {
+  __shared__ int sm[SCAN_T / 32];
+  __shared__ int total;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? cnt[base + k] : 0;
+    s += v[k];
+  }
+  int off = block_exclusive_scan(s, sm, &total) + tile_off[blockIdx.x] + base_off;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) start[base + k] = off;
+    off += v[k];
+    if (base + k == n - 1) start[n] = off;
+  }
+}
+
+int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base) {
+  int n = g.n_own_cells();
+  int first = g.first_own_cell();
+  int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (ntiles > SCAN_TILE) {
+    set_error("cell grid too large for the two-level scan (%d cells)", n);
+    return ATLJ_ERR_ARG;
+  }
+  scan_tile_sums_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums);
+  ATLJ_LAUNCHED();
+  scan_tile_offsets_kernel<<<1, SCAN_T, 0, st>>>(b.block_sums, ntiles);
+  ATLJ_LAUNCHED();
+  scan_final_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums, base, b.cell_start + first);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+
+// ---- 3. scatter keys into their cells ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cell_scatter_kernel(int n, int base, const int *__restrict__ cellid,
+                                                           const int *__restrict__ rank,
+                                                           const int *__restrict__ cell_start,
+                                                           const int *__restrict__ id_in,
+                                                           unsigned long long *__restrict__ keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cid = cellid[i];
+  if (cid < 0) return;
+  unsigned id = id_in ? (unsigned)id_in[i] : (unsigned)i;
+  int slot = cell_start[cid] - base + rank[i];
+  keys[slot] = ((unsigned long long)id << 32) | (unsigned)i;
+}
+
+// ---- 4. order each cell by atom id -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const int *__restrict__ cell_start,
+                                                        const int *__restrict__ cell_count,
+                                                        unsigned long long *__restrict__ keys) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.n_own_cells()) return;
+  c += g.first_own_cell();
+  int n = cell_count[c];
+  if (n < 2) return;
+  unsigned long long *k = keys + (cell_start[c] - base);
+  if (n <= 32) {  // insertion sort; keys arrive nearly ordered when the atoms were in cell order already
+    for (int a = 1; a < n; a++) {
+      unsigned long long x = k[a];
+      int b = a - 1;
+      while (b >= 0 && k[b] > x) {
+        k[b + 1] = k[b];
+        b--;
+      }
+      k[b + 1] = x;
+    }
+  } else {  // heap sort for crowded cells (dense blobs); O(n log n), in place
+    for (int start = n / 2 - 1; start >= 0; start--) {
+      int root = start;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= n) break;
+        if (child + 1 < n && k[child] < k[child + 1]) child++;
+        if (k[root] >= k[child]) break;
+        unsigned long long t = k[root];
+        k[root] = k[child];
+        k[child] = t;
+        root = child;
+      }
+    }
+    for (int end = n - 1; end > 0; end--) {
+      unsigned long long t = k[0];
+      k[0] = k[end];
+      k[end] = t;
+      int root = 0;
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= end) break;
+        if (child + 1 < end && k[child] < k[child + 1]) child++;
+        if (k[root] >= k[child]) break;
+        unsigned long long u = k[root];
+        k[root] = k[child];
+        k[child] = u;
+        root = child;
+      }
+    }
+  }
+}
+
+// ---- 5. gather into cell order ---------------------------------------------------------------------------------
+// One thread per (atom, component) so that the writes are perfectly coalesced; the reads hit 24-byte records
+// whose three components are fetched by neighbouring threads.
+__global__ void __launch_bounds__(256) cell_gather_kernel(int n, const unsigned long long *__restrict__ keys,
+                                                          const double *__restrict__ r_in,
+                                                          const double *__restrict__ v_in, double *__restrict__ r_out,
+                                                          double *__restrict__ v_out, int *__restrict__ id_out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  int s = t / 3, k = t - 3 * s;
+  unsigned long long key = keys[s];
+  unsigned src = (unsigned)(key & 0xffffffffull);
+  r_out[t] = r_in[3 * (size_t)src + k];
+  if (v_in) v_out[t] = v_in[3 * (size_t)src + k];
+  if (k == 0 && id_out) id_out[s] = (int)(key >> 32);
+}
+
+int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
+                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out) {
+  if (n <= 0) return ATLJ_OK;
+  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, base, b.cellid, b.rank, b.cell_start, id_in, b.keys);
+  ATLJ_LAUNCHED();
+  int nc = g.n_own_cells();
+  cell_sort_kernel<<<(nc + 127) / 128, 128, 0, st>>>(g, base, b.cell_start, b.cell_count, b.keys);
+  ATLJ_LAUNCHED();
+  cell_gather_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, b.keys, r_in, v_in, r_out, v_out, id_out);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+
+}  // namespace atlj

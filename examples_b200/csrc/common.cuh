@@ -1,0 +1,152 @@
+// Shared declarations of libatlj's translation units (internal; the public ABI is include/atlj.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/atlj.h"
+
+namespace atlj {
+
+// ---- error plumbing -----------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern int64_t g_launches;  // kernels launched by this library (atlj_kernel_launches)
+
+#define ATLJ_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      atlj::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return ATLJ_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+#define ATLJ_LAUNCHED()                                                                          \
+  do {                                                                                           \
+    atlj::g_launches++;                                                                          \
+    cudaError_t e_ = cudaPeekAtLastError();                                                      \
+    if (e_ != cudaSuccess) {                                                                     \
+      atlj::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_));  \
+      return ATLJ_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+// ---- local cell grid of one rank ------------------------------------------------------------------------------
+// Global grid: sc x sc x sc cells, id = (c0*sc + c1)*sc + c2 (C order, md_lj_ll_module.py:116).
+// A rank owns global x-layers [x_lo, x_lo+nx_own); its local grid has nxl = nx_own + 2h layers where h = 1
+// when the slab has halo layers (multi-GPU) and 0 when x wraps inside the array (single GPU).
+struct Geom {
+  int sc;      // cells per box edge (global)
+  int x_lo;    // first owned global x layer
+  int nx_own;  // owned layers
+  int h;       // halo layers on each side (0 or 1)
+  int nxl;     // nx_own + 2h
+  __host__ __device__ int ncell() const { return nxl * sc * sc; }
+  __host__ __device__ int n_own_cells() const { return nx_own * sc * sc; }
+  __host__ __device__ int first_own_cell() const { return h * sc * sc; }
+};
+
+constexpr int MAX_NB = 30;  // 27 (LJ) or up to 9+12+9 (Lees-Edwards top/bottom layer)
+
+// Full-stencil neighbour cell k of local cell (lx,cy,cz); returns local cell id or -1 if slot k is unused.
+// LJ: the 14 offsets of md_lj_ll_module.py:84-86 and their mirror images = all 27 offsets.
+// LE: md_lj_llle_module.py:88-92,131-135: i-cells in the top y layer look up (dy=+1) at dx in {1,0,-1,-2}-shift;
+//     the mirror relation makes bottom-layer cells look down (dy=-1) at dx in {-1,0,1,2}+shift.
+__host__ __device__ inline int neighbour_cell(const Geom &g, bool le, int shift, int lx, int cy, int cz, int k) {
+  int dx, dy, dz;
+  if (!le) {
+    if (k >= 27) return -1;
+    dx = k / 9 - 1;
+    dy = (k / 3) % 3 - 1;
+    dz = k % 3 - 1;
+  } else {
+    if (k < 9) {  // dy = 0
+      dy = 0;
+      dx = k / 3 - 1;
+      dz = k % 3 - 1;
+    } else if (k < 21) {  // dy = +1, up to 4 x-offsets
+      int m = k - 9;
+      dy = 1;
+      dz = m % 3 - 1;
+      int q = m / 3;  // 0..3
+      if (cy == g.sc - 1) {
+        dx = (1 - q) - shift;  // 1,0,-1,-2 minus shift
+      } else {
+        if (q == 3) return -1;
+        dx = 1 - q;
+      }
+    } else {  // dy = -1
+      int m = k - 21;
+      if (m >= 12) return -1;
+      dy = -1;
+      dz = m % 3 - 1;
+      int q = m / 3;
+      if (cy == 0) {
+        dx = (q - 1) + shift;  // -1,0,1,2 plus shift
+      } else {
+        if (q == 3) return -1;
+        dx = q - 1;
+      }
+    }
+  }
+  int sc = g.sc;
+  int ny = cy + dy;
+  ny = ny < 0 ? ny + sc : (ny >= sc ? ny - sc : ny);
+  int nz = cz + dz;
+  nz = nz < 0 ? nz + sc : (nz >= sc ? nz - sc : nz);
+  int nx = lx + dx;
+  if (g.h == 0) {
+    nx %= sc;
+    if (nx < 0) nx += sc;
+  } else if (nx < 0 || nx >= g.nxl) {
+    return -1;  // cannot happen for LJ with one halo layer
+  }
+  return (nx * sc + ny) * sc + nz;
+}
+
+// ---- physics constants of one force evaluation -------------------------------------------------------------------
+struct Phys {
+  double box, box_sq, r_cut_box_sq, pot_cut, strain;
+  float rc2_cell;  // prefilter threshold: (r_cut/box*sc)^2 * (1+margin), cell units
+  int shift;       // floor(strain*sc), md_lj_llle_module.py:112
+  int model;       // ATLJ_MODEL_*
+};
+
+// ---- launchers implemented in cells.cu / pair.cu / integrate.cu -------------------------------------------------
+struct CellBufs {
+  int *cellid;          // [cap] local cell id of each atom (current order)
+  int *rank;            // [cap] arrival rank inside its cell
+  unsigned long long *keys;  // [cap] (id << 32 | source index), sorted per cell
+  int *cell_count;      // [ncell]
+  int *cell_start;      // [ncell+1]
+  int *block_sums;      // scan scratch
+  int *err;             // [4] device flags: [0] index error, [1] capacity overflow
+};
+
+// wrap + cell assignment + per-cell counts (+ optional int64 triplets out)
+int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
+                       double strain, const CellBufs &b, long long *c_out);
+// exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
+int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
+// scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
+int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
+                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out);
+
+struct PairArgs {
+  const double *r;       // sorted positions (owned + halo), AoS
+  const double *fin;     // sorted forces (hessian) or nullptr
+  const int *cell_start;
+  const int *cell_count;
+  double *f;             // sorted forces out (force mode)
+  double *partials;      // [grid][8]
+  Geom g;
+  Phys p;
+};
+int pair_grid_blocks();  // blocks of the persistent pair kernel (partials has this many rows)
+int launch_pair_cells(cudaStream_t st, const PairArgs &a, bool hessian, int natoms_hint);
+int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
+                    double *partials, bool hessian, int *nblocks_out);
+// fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)
+int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec);
+
+}  // namespace atlj

@@ -1,0 +1,49 @@
+// The device-resident simulation object behind atlj_sim (internal).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct atlj_sim {
+  cudaStream_t st = nullptr;
+  int64_t cap = 0;  // atom capacity of every per-atom buffer
+  int64_t n = 0;    // owned atoms
+  bool configured = false;
+  bool use_cells = false;  // sc >= 4: link-cell route; otherwise all pairs
+  atlj::Geom g{};
+  atlj::Phys p{};
+  // state, double-buffered because the cell sort re-orders atoms every force evaluation
+  double *r[2] = {nullptr, nullptr};
+  double *v[2] = {nullptr, nullptr};
+  int *id[2] = {nullptr, nullptr};
+  int cur = 0;
+  double *f = nullptr;  // forces in the order of r[cur]
+  atlj::CellBufs cb{};
+  int ncell_alloc = 0;
+  double *partials = nullptr;  // [pair_grid_blocks()][8]
+  double *scal = nullptr;      // 64 device scalars (thermostat state, reduction results)
+  double *rec_dev = nullptr;   // per-step records
+  int64_t rec_cap = 0;
+  double *noise_dev = nullptr;  // injected noise (tests)
+  int64_t noise_cap = 0;
+  // multi-GPU slab bookkeeping
+  int n_halo_left = 0, n_halo_right = 0;
+  // timing
+  bool timing = false;
+  struct Ev {
+    cudaEvent_t e0, e1;
+    int cat;
+  };
+  std::vector<cudaEvent_t> ev_free;
+  std::vector<Ev> ev_open, ev_done;
+};
+
+namespace atlj {
+struct Timer {
+  static void begin(atlj_sim *s, int cat);  // cat: 0 pair, 1 cells, 2 integrate, 3 other
+  static void end(atlj_sim *s);
+};
+int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs);
+int sim_check_flags(atlj_sim *s);
+int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
+}  // namespace atlj

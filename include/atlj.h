@@ -1,0 +1,162 @@
+/*
+ * atlj.h -- C ABI of libatlj.so: the B200 (sm_100a) Lennard-Jones pair-force hot path of
+ * Allen-Tildesley/examples.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative to the
+ * reference tree).  The Python shim in examples_b200/ binds these with ctypes and presents
+ * the reference's module API (force/hessian/PotentialType/introduction/conclusion).
+ *
+ * Conventions
+ *   - positions r are (n,3) C-order fp64 in box = 1 units, as in the reference
+ *     (python_examples/md_nve_lj.py:162-163); forces/energies in sigma = epsilon = 1 units.
+ *   - "host" pointers are ordinary CPU memory (pageable or pinned); "dev" pointers are CUDA
+ *     device memory on the library's current device.
+ *   - return value: ATLJ_OK, one of the reference's assertion conditions (the shim raises
+ *     AssertionError with the reference's message), or ATLJ_ERR_CUDA / ATLJ_ERR_ARG with the
+ *     text available from atlj_last_error().
+ *   - the library NEVER computes on the CPU: without a usable CUDA device every compute entry
+ *     point returns ATLJ_ERR_CUDA.
+ */
+#ifndef ATLJ_H
+#define ATLJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATLJ_OK 0
+#define ATLJ_ERR_DIM -1      /* 'Dimension error in force'        md_lj_module.py:77        */
+#define ATLJ_ERR_SMALL -2    /* 'System is too small for cells'   md_lj_ll_module.py:107    */
+#define ATLJ_ERR_INDEX -3    /* 'Index error'                     md_lj_ll_module.py:109    */
+#define ATLJ_ERR_MISMATCH -4 /* 'Dimension mismatch in hessian'   md_lj_module.py:163       */
+#define ATLJ_ERR_CUDA -100   /* CUDA runtime failure or no device */
+#define ATLJ_ERR_ARG -101    /* invalid argument                  */
+
+/* models */
+#define ATLJ_MODEL_LJ 0  /* cut-and-shifted LJ, totals = {cut,pot,vir,lap}   md_lj_module.py    */
+#define ATLJ_MODEL_WCA 1 /* WCA + Lees-Edwards, totals = {pot,vir,lap,pyx}   md_lj_le_module.py */
+
+/* number of doubles in one per-step record written by the device-resident integrators */
+#define ATLJ_NREC 12
+/* record layout: [0..3] totals as above, [4] sum v^2, [5] sum f^2, [6] hessian (NVE, optional),
+ * [7] ovr flag (0/1), [8] in-range pair count, [9] sum vx*vy (SLLOD), [10] strain (SLLOD) or
+ * conserved-energy thermostat term (NHC), [11] number of owned atoms (multi-GPU)            */
+
+/* ---------------------------------------------------------------------------------------------
+ * library / device
+ * ------------------------------------------------------------------------------------------- */
+int atlj_version(void);
+const char *atlj_last_error(void);
+int atlj_device_count(void);      /* number of CUDA devices, 0 if none          */
+int atlj_set_device(int device);  /* all later calls of this thread use device  */
+int64_t atlj_kernel_launches(void); /* kernels launched by this library so far (bench: gpu_launches) */
+
+/* ---------------------------------------------------------------------------------------------
+ * stateless drop-in path: host arrays in, host arrays out (H2D + kernels + D2H per call)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces md_lj_module.force (md_lj_module.py:68-149) when sc <= 0 or sc < 4 (all pairs) and
+ * md_lj_ll_module.force (md_lj_ll_module.py:69-224) when sc >= 4 (link cells, sc =
+ * floor(box/r_cut) computed by the caller with the reference's expression, :106).
+ * r_cut_box_sq, box_sq, pot_cut are the host scalars of md_lj_module.py:80-88, passed in so the
+ * in-range predicate uses bit-identical thresholds.  check_index != 0 enforces the cell-index
+ * assertion of md_lj_ll_module.py:109 even on the all-pairs route.
+ * totals = {cut, pot, vir, lap} after the scaling of md_lj_module.py:143-147; f is (n,3). */
+int atlj_force_lj(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double pot_cut,
+                  int sc, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair);
+
+/* Replaces md_lj_le_module.force (md_lj_le_module.py:69-150; sc < 4) and md_lj_llle_module.force
+ * (md_lj_llle_module.py:70-245; sc >= 4, shift = floor(strain*sc) of :112).  WCA potential,
+ * Lees-Edwards image.  totals = {pot, vir, lap, pyx}. */
+int atlj_force_le(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double strain,
+                  int sc, int shift, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair);
+
+/* Replaces md_lj_module.hessian (md_lj_module.py:151-213) / md_lj_ll_module.hessian
+ * (md_lj_ll_module.py:227-357). */
+int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, double box, double r_cut_box_sq,
+                    double box_sq, int sc, int check_index, double *hes);
+
+/* The integer work on its own, for bit-exact tests: wrap (md_lj_ll_module.py:88; le != 0 adds the
+ * pre-wrap of md_lj_llle_module.py:94), cell triplets c (int64, :108), and the per-cell atom lists
+ * of :116-120 in CSR form: perm (atoms in C order of cells, ascending index inside a cell) and
+ * cell_start (sc^3+1).  link_list_module.f90:103-161 is the Fortran twin. */
+int atlj_cells(const double *r_host, int64_t n, int sc, int le, double strain, int64_t *c_host, int32_t *perm_host,
+               int32_t *cell_start_host);
+
+/* Neighbour-cell enumeration used by the pair kernel (full stencil = the reference's half stencil
+ * md_lj_ll_module.py:84-86,128-129 / md_lj_llle_module.py:88-92,131-141 plus its mirror image).
+ * nb_host is (sc^3, 30) int32, unused slots -1; count_host (sc^3). */
+int atlj_neighbour_cells(int sc, int le, int shift, int32_t *nb_host, int32_t *count_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * device-resident path: state stays in HBM between steps
+ * (replaces the loop bodies md_nve_lj.py:178-192, bd_nvt_lj.py:221-233, md_nvt_lj.py:270-288,
+ *  md_nvt_lj_le.py:226-240 together with the force call inside them)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct atlj_sim atlj_sim;
+
+/* capacity = maximum number of atoms this rank will ever hold (owned + halo).
+ * stream = a cudaStream_t (0 = legacy default stream); all work is enqueued on it. */
+atlj_sim *atlj_sim_create(int64_t capacity, void *stream);
+void atlj_sim_destroy(atlj_sim *s);
+
+/* Model and geometry.  sc = floor(box/r_cut) (md_lj_ll_module.py:106); r_cut_box_sq, box_sq, pot_cut as
+ * above.  Slab decomposition: this rank owns global cell layers [x_lo, x_hi) along axis 0; for a
+ * single GPU x_lo = 0, x_hi = sc. */
+int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, double box_sq, double pot_cut, int sc,
+                       int x_lo, int x_hi);
+
+/* Upload owned atoms: r (box units, wrapped), v, global ids (NULL = 0..n-1). */
+int atlj_sim_upload(atlj_sim *s, const double *r_host, const double *v_host, const int32_t *id_host, int64_t n);
+/* Download owned atoms in the order they are held (sorted by cell); ids tell which is which.
+ * Any pointer may be NULL.  Returns the number of owned atoms through n_out. */
+int atlj_sim_download(atlj_sim *s, double *r_host, double *v_host, double *f_host, int32_t *id_host, int64_t *n_out);
+int64_t atlj_sim_natoms(atlj_sim *s);
+
+/* One force evaluation on the current positions (cell build + pair kernel); rec[ATLJ_NREC]. */
+int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_host);
+
+/* nsteps velocity-Verlet steps (md_nve_lj.py:178-192); rec_host (nsteps, ATLJ_NREC) or NULL. */
+int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host);
+/* BAOAB Langevin steps (bd_nvt_lj.py:91-127,221-233) with a counter-based device Gaussian RNG. */
+int atlj_sim_run_baoab(atlj_sim *s, double dt, double gamma, double temperature, uint64_t seed, int nsteps,
+                       double *rec_host);
+/* Nose-Hoover chain steps (md_nvt_lj.py:101-159,270-288), chain length m <= 8; eta, p_eta, q host in/out. */
+int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, int m, double *eta, double *p_eta, const double *q,
+                     int nsteps, double *rec_host);
+/* Isokinetic SLLOD steps (md_nvt_lj_le.py:84-129,226-240); *strain host in/out. */
+int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strain, int nsteps, double *rec_host);
+
+/* BAOAB with an injected noise array (nsteps, n, 3) indexed by GLOBAL atom id -- deterministic parity
+ * tests against bd_nvt_lj.py:127 with the same numbers. */
+int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double gamma, double temperature, const double *noise_host,
+                             int nsteps, double *rec_host);
+
+/* ---- phases of one multi-GPU NVE step (the exchange between them is done by the caller with
+ * NCCL send/recv on the same stream; see examples_b200/slab.py) ------------------------------ */
+/* kick(dt/2) + drift(dt) + wrap, then split owned atoms into stay / go-left / go-right.  Leavers are packed
+ * into the two send buffers: [0] = count, then per atom 7 doubles (r, v, id). */
+int atlj_sim_mg_drift_pack(atlj_sim *s, double dt, double *send_left_dev, double *send_right_dev, int64_t cap);
+/* append arrivals from the two receive buffers, bin + sort owned atoms, pack the boundary layers:
+ * halo send buffers: [0] = count, [1..sc*sc] = per-cell counts, then 3 doubles per atom. */
+int atlj_sim_mg_bin_pack(atlj_sim *s, const double *recv_left_dev, const double *recv_right_dev, int64_t cap,
+                         double *halo_left_dev, double *halo_right_dev, int64_t halo_cap);
+/* unpack halos, pair kernel, kick(dt/2), local partial sums -> rec_dev[ATLJ_NREC] (device; caller all-reduces). */
+int atlj_sim_mg_force_kick(atlj_sim *s, const double *halo_from_left_dev, const double *halo_from_right_dev,
+                           int64_t halo_cap, double dt, double *rec_dev);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Register-resident DFMA loop on every SM: returns achieved fp64 FLOP/s (2 flop per DFMA) -- the
+ * roofline denominator for the pair kernel (no fp64 figure in MEASURED_PEAKS.json). */
+int atlj_measure_fp64_peak(double *flops_per_s);
+/* Device time (ms) of the most recent pair-kernel / cell-build / integration launches, by CUDA events
+ * recorded on the sim's stream when timing is enabled. */
+int atlj_sim_enable_timing(atlj_sim *s, int on);
+int atlj_sim_timing(atlj_sim *s, double ms[4]); /* accumulated {pair, cells, integrate, other} ms; resets */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLJ_H */

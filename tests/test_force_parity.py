@@ -1,0 +1,218 @@
+"""GPU: the CUDA path (through the drop-in modules -> ctypes -> C ABI) against the golden vectors generated
+from the reference Python modules, and against the C oracle at sizes the reference cannot reach.
+
+Bars (BASELINE.json north_star): integer cell / neighbour work bit-exact; in-range pair count and overlap flag
+exact; energies, virials, Laplacian, forces <= 1e-10 relative (fp64, summation order differs)."""
+import numpy as np
+import pytest
+
+from conftest import WCA_R_CUT, liquid_like, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+LJ_TAGS = ["lj_n256_a0", "lj_n256_a0.1", "lj_n864_a0", "lj_n864_a0.1", "lj_n4000_a0", "lj_n4000_a0.1"]
+
+
+def check_lj(total, f, gt, gf, govr):
+    t = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(t - gt) / np.abs(gt)) < TOL
+    if np.max(np.abs(gf)) > 1e-6:
+        assert rel_err(f, gf) < TOL
+    else:  # perfect lattice: forces cancel
+        assert np.max(np.abs(f - gf)) < 1e-9
+    assert total.ovr == govr
+
+
+@pytest.mark.parametrize("tag", LJ_TAGS)
+def test_lj_force_golden(golden, tag):
+    from examples_b200 import md_lj_ll_module, md_lj_module
+    r, box = golden[tag + "_r"], float(golden[tag + "_box"])
+    for kind, mod in (("ap", md_lj_module), ("ll", md_lj_ll_module)):
+        if tag + "_" + kind + "_totals" not in golden:
+            continue
+        r_in = r.copy()
+        total, f = mod.force(box, 2.5, r_in)
+        assert np.array_equal(r_in, r), "caller's r must not be modified (SURVEY.md 8b)"
+        assert f.shape == r.shape and f.dtype == np.float64
+        check_lj(total, f, golden[tag + "_" + kind + "_totals"], golden[tag + "_" + kind + "_f"],
+                 bool(golden[tag + "_" + kind + "_ovr"]))
+        hes = mod.hessian(box, 2.5, r, golden[tag + "_" + kind + "_f"])
+        gh = float(golden[tag + "_" + kind + "_hes"])
+        assert abs(hes - gh) <= TOL * abs(gh)
+    # the all-pairs module on a system large enough for cells goes through the cell kernel: same answer
+    if "n4000" in tag:
+        total, f = md_lj_module.force(box, 2.5, r)
+        check_lj(total, f, golden[tag + "_ll_totals"], golden[tag + "_ll_f"], bool(golden[tag + "_ll_ovr"]))
+
+
+@pytest.mark.parametrize("tag", [t for t in LJ_TAGS if "n256" not in t])
+def test_cells_bit_exact_golden(golden, tag):
+    from examples_b200 import md_lj_ll_module
+    r, box = golden[tag + "_r"], float(golden[tag + "_box"])
+    c, perm, cell_start = md_lj_ll_module.cells(box, 2.5, r)
+    assert np.array_equal(c, golden[tag + "_c"])
+    assert np.array_equal(perm, golden[tag + "_perm"])
+    assert np.array_equal(cell_start, golden[tag + "_cell_start"])
+
+
+@pytest.mark.parametrize("n", [256, 864])
+@pytest.mark.parametrize("strain", [0.0, 0.13, -0.37, 0.499])
+def test_le_force_golden(golden, n, strain):
+    from examples_b200 import md_lj_le_module, md_lj_llle_module
+    tag = "le_n%d_s%g" % (n, strain)
+    r, box = golden[tag + "_r"], float(golden[tag + "_box"])
+    for kind, mod in (("ap", md_lj_le_module), ("ll", md_lj_llle_module)):
+        total, f = mod.force(box, strain, r.copy())
+        t = np.array([total.pot, total.vir, total.lap, total.pyx])
+        gt = golden[tag + "_" + kind + "_totals"]
+        assert np.max(np.abs(t - gt) / np.abs(gt)) < TOL, (kind, t, gt)
+        assert rel_err(f, golden[tag + "_" + kind + "_f"]) < TOL
+        assert total.ovr == bool(golden[tag + "_" + kind + "_ovr"])
+
+
+def test_neighbour_cells_match_reference_stencils(golden):
+    """Full stencil of the kernel == reference half stencil (golden) plus its mirror image, as sets, per cell."""
+    from examples_b200 import _lib
+    L = _lib.lib()
+    cases = [(sc, 0, 0, golden["nb14_sc%d" % sc]) for sc in (4, 7)]
+    cases += [(sc, 1, shift, golden["nb17_sc%d_shift%d" % (sc, shift)]) for sc, shift in ((5, 0), (5, 2), (8, -3), (8, 3))]
+    for sc, le, shift, half in cases:
+        nb = np.empty((sc ** 3, 30), dtype=np.int32)
+        cnt = np.empty(sc ** 3, dtype=np.int32)
+        _lib.check(L.atlj_neighbour_cells(sc, le, shift, nb, cnt))
+        want = [set() for _ in range(sc ** 3)]
+        for ci in range(sc ** 3):
+            for cj in half[ci]:
+                if cj >= 0:
+                    want[ci].add(int(cj))
+                    want[int(cj)].add(ci)
+        for ci in range(sc ** 3):
+            got = [int(x) for x in nb[ci] if x >= 0]
+            assert len(got) == len(set(got)) == cnt[ci], "duplicate neighbour cell"
+            assert set(got) == want[ci], (sc, le, shift, ci)
+
+
+@pytest.mark.parametrize("nc,sigma", [(20, 0.02), (20, 0.08), (13, 0.05)])
+def test_lj_cells_vs_oracle_32k(oracle, nc, sigma):
+    """BASELINE config 2 size (N=32,000, sc=13) and a non-commensurate size, against the C oracle."""
+    from examples_b200 import md_lj_ll_module
+    n, box, r = liquid_like(nc, 0.75, sigma)
+    t, f, ovr, npair = oracle.force(r, box, 2.5, cells=True)
+    total, fg = md_lj_ll_module.force(box, 2.5, r)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL
+    assert rel_err(fg, f) < TOL
+    assert total.ovr == ovr
+    from examples_b200.md_lj_module import _force
+    import math
+    rc, _, _, _, npair_g = _force(box, 2.5, r, math.floor(box / 2.5), 1)
+    assert rc == 0 and npair_g == npair, "in-range pair count must be exact"
+    hes = md_lj_ll_module.hessian(box, 2.5, r, f)
+    ho = oracle.hessian(r, f, box, 2.5, cells=True)
+    assert abs(hes - ho) <= TOL * abs(ho)
+    c, perm, cs = md_lj_ll_module.cells(box, 2.5, r)
+    rw, co, permo, cso = oracle.cells(r, math.floor(box / 2.5))
+    assert np.array_equal(c, co) and np.array_equal(perm, permo) and np.array_equal(cs, cso)
+
+
+@pytest.mark.parametrize("strain", [0.0, 0.2501, -0.4999])
+def test_le_cells_vs_oracle_tiny_cells(oracle, strain):
+    """WCA cells hold ~1 atom each (BASELINE config 3 geometry, smaller N)."""
+    from examples_b200 import md_lj_llle_module
+    n, box, r = liquid_like(16, 0.8442, 0.05)  # N=16,384, sc=23
+    r[:, 0] = r[:, 0] - np.rint(r[:, 1]) * strain
+    r = r - np.rint(r)
+    t, f, ovr, npair = oracle.force(r, box, WCA_R_CUT, cells=True, le=True, strain=strain)
+    total, fg = md_lj_llle_module.force(box, strain, r.copy())
+    tg = np.array([total.pot, total.vir, total.lap, total.pyx])
+    assert np.max(np.abs(tg - t) / np.maximum(np.abs(t), 1e-300)) < TOL
+    assert rel_err(fg, f) < TOL
+    assert total.ovr == ovr
+
+
+def test_overlap_flag_and_crowded_cell(oracle):
+    """Two atoms nearly on top of each other set ovr; a crowded cell exceeds the per-cell fast paths."""
+    from examples_b200 import md_lj_ll_module
+    n, box, r = liquid_like(6, 0.75, 0.02)
+    r[1] = r[0] + np.array([0.7 / box, 0.0, 0.0])
+    r = r - np.rint(r)
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    t, fo, ovr, _ = oracle.force(r, box, 2.5, cells=True)
+    assert ovr and total.ovr
+    assert rel_err(f, fo) < TOL
+    # 700 extra atoms on a tiny lattice inside one cell: per-cell sort uses the heap path, the pair kernel's
+    # candidate set exceeds its shared-memory chunk
+    rng = np.random.default_rng(3)
+    g = np.stack(np.meshgrid(*[np.arange(9)] * 3, indexing="ij"), -1).reshape(-1, 3)[:700]
+    extra = (g * 0.9 + 0.3) / box - 0.5 + rng.normal(0, 1e-3, (700, 3))
+    r2 = np.ascontiguousarray(np.concatenate([r[2:], extra]))
+    rng.shuffle(r2)
+    total, f = md_lj_ll_module.force(box, 2.5, r2)
+    t, fo, ovr, npair = oracle.force(r2, box, 2.5, cells=True)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL
+    assert rel_err(f, fo) < TOL
+    c, perm, cs = md_lj_ll_module.cells(box, 2.5, r2)
+    _, co, permo, cso = oracle.cells(r2, 4)
+    assert np.array_equal(perm, permo) and np.array_equal(cs, cso)
+
+
+def test_reference_assertions():
+    from examples_b200 import md_lj_ll_module, md_lj_llle_module, md_lj_module
+    from examples_b200.lattice import fcc_positions
+    n, box, r = fcc_positions(4)  # N=256: sc=2
+    with pytest.raises(AssertionError, match="System is too small for cells"):
+        md_lj_ll_module.force(box, 2.5, r)
+    with pytest.raises(AssertionError, match="Dimension error in force"):
+        md_lj_module.force(box, 2.5, np.zeros((10, 2)))
+    n, box, r = fcc_positions(6)
+    total, f = md_lj_module.force(box, 2.5, r)
+    with pytest.raises(AssertionError, match="Dimension mismatch in hessian"):
+        md_lj_module.hessian(box, 2.5, r, f[:-1])
+    r2 = r.copy()
+    r2[0, 0] = 0.5  # rint(0.5)=0 keeps it at +0.5 -> cell index sc
+    with pytest.raises(AssertionError, match="Index error"):
+        md_lj_ll_module.force(box, 2.5, r2)
+    r2[0, 0] = -0.5
+    md_lj_ll_module.force(box, 2.5, r2)
+    # the all-pairs module has no such restriction
+    r2[0, 0] = 0.5
+    n, box, r = fcc_positions(10)
+    r[0, 0] = 0.5
+    md_lj_module.force(box, 2.5, r)
+    with pytest.raises(AssertionError, match="System is too small for cells"):
+        md_lj_llle_module.force(2.0, 0.0, np.zeros((4, 3)))
+
+
+def test_sc3_served_by_all_pairs(oracle):
+    """sc == 3 (N=500): every cell's stencil is the whole box; the cell module must still agree."""
+    from examples_b200 import md_lj_ll_module
+    from examples_b200.lattice import fcc_positions, perturb
+    n, box, r = fcc_positions(5)
+    r = perturb(r, box, 0.1)
+    assert int(np.floor(box / 2.5)) == 3
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    t, fo, ovr, _ = oracle.force(r, box, 2.5, cells=True)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL and rel_err(f, fo) < TOL
+
+
+def test_size_independent_properties_large():
+    """N = 256,000: Newton's third law (sum f = 0), invariance of the totals under a rigid translation and under
+    a permutation of the atom order, and determinism (bitwise identical repeat)."""
+    from examples_b200 import md_lj_ll_module
+    n, box, r = liquid_like(40, 0.75, 0.06)
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    assert not total.ovr
+    assert np.max(np.abs(f.sum(axis=0))) < 1e-8 * np.max(np.abs(f))
+    total2, f2 = md_lj_ll_module.force(box, 2.5, r)
+    assert np.array_equal(f, f2) and total.pot == total2.pot and total.lap == total2.lap
+    perm = np.random.default_rng(0).permutation(n)
+    total3, f3 = md_lj_ll_module.force(box, 2.5, np.ascontiguousarray(r[perm]))
+    assert abs(total3.pot - total.pot) < 1e-11 * abs(total.pot)
+    assert rel_err(f3, f[perm]) < 1e-11
+    rs = r + np.array([0.123, -0.377, 0.25])
+    rs = rs - np.rint(rs)
+    total4, f4 = md_lj_ll_module.force(box, 2.5, rs)
+    for a, b in ((total4.pot, total.pot), (total4.vir, total.vir), (total4.lap, total.lap)):
+        assert abs(a - b) < 1e-9 * abs(b)  # translation changes rounding of r, hence a few borderline pairs
