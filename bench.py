@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- LJ atom-steps/s of the device-resident NVE loop (cell build + pair force + velocity Verlet).
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            our arm (libatlj.so, sm_100a CUDA)
+  python bench.py --impl reference --gpus N --steps K ...  the CPU restatement of the reference path on host cores
+
+Workloads (BASELINE.json configs; --workload):
+  c5 (default)  NVE LJ weak scaling, fcc nc=80 -> 2,048,000 atoms per GPU (nc=101/127/160 at 2/4/8 GPUs), rho=0.75,
+                r_cut=2.5, dt=0.005, melted before timing.  This is the configuration the metric
+                ("atom-steps/s at 1/2/4/8 B200") is quoted on; its state (~350 MB) exceeds the 126 MB L2.
+  c2            md_nve_lj + md_lj_ll_module, N=32,000 (launch-latency bound on a B200; reported under "other").
+  c4            N=1,000,188.
+A "step" is one velocity-Verlet step of md_nve_lj.py:178-192: kick, drift+wrap, cell build, pair force, kick, sums.
+
+`value`    atoms * steps / device time of the device-resident loop (CUDA events on the launching stream, max over
+           ranks, barrier + synchronize on both sides).
+`e2e`      same step, but the state (r, v, f, id) lives in pinned HOST memory as it does in the reference driver:
+           every step copies it to the device, steps, and copies r, v, f, id + the per-step record back.
+`roofline` pair kernel: algorithmic flops (45 per in-range pair) / its CUDA-event time, against the
+           fp64 DFMA peak measured in the same run (MEASURED_PEAKS.json has no fp64 figure).
+           `roofline_hbm`: cell build + integration kernels, 152 B/atom-step, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline`  the C restatement of the reference (oracle/, "port": gfortran is not in the image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R_CUT, DT, DENSITY = 2.5, 0.005, 0.75
+FLOP_PER_PAIR = 45.0
+HBM_BYTES_NON_PAIR = 152.0       # 200 B/atom-step minus the pair kernel's 48
+NC_WEAK = {1: 80, 2: 101, 4: 127, 8: 160}
+T_INIT = 2.0                     # lattice start temperature: melts to a T ~ 1 liquid (reported in config)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower() == "active":
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_system(nc, seed=20170101):
+    from examples_b200.lattice import fcc_positions, ran_velocities
+    n, box, r = fcc_positions(nc, DENSITY)
+    v = ran_velocities(n, T_INIT, seed)
+    return n, box, r, v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the C restatement of md_nve_lj.py + md_lj_ll_module on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_nve(nc, steps, warmup, melt_state=None):
+    """-> atom-steps/s, threads, n.  Liquid-like input: melt_state (r, v) if given, else a perturbed lattice."""
+    from oracle import oracle as O
+    O.build()
+    n, box, r, v = make_system(nc)
+    if melt_state is not None:
+        r, v = melt_state
+        n = r.shape[0]
+    else:
+        rng = np.random.default_rng(1)
+        r = r + rng.normal(0.0, 0.08 / box, size=r.shape)
+        r = np.ascontiguousarray(r - np.rint(r))
+        v = v * np.sqrt(1.0 / T_INIT)
+    r, v = np.ascontiguousarray(r.copy()), np.ascontiguousarray(v.copy())
+    _, f, _, _ = O.force(r, box, R_CUT, cells=True, omp=True)
+    if warmup > 0:
+        O.nve_steps(r, v, f, box, R_CUT, DT, warmup, cells=True, omp=True, record=False)
+    t0 = time.perf_counter()
+    O.nve_steps(r, v, f, box, R_CUT, DT, steps, cells=True, omp=True, record=False)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, O.num_threads(True), n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: nc=40 (256,000 atoms, same density / cutoff / dt) keeps K+W steps within minutes; the
+    # algorithm is O(N) so atom-steps/s does not depend on the sample size
+    nc = 40
+    value, threads, n, dt = cpu_nve(nc, args.steps, args.warmup)
+    nc_w = NC_WEAK.get(world, 80)
+    line = {
+        "impl": "reference", "metric": "LJ atom-steps/sec (rho=0.75, r_cut=2.5)", "value": value,
+        "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic fcc lattice + Gaussian displacement (sigma 0.08), T=1 velocities",
+        "config": {"workload": "c5: NVE LJ weak scaling, 2,048,000 atoms/GPU (fcc nc=%d), rho=0.75, r_cut=2.5, "
+                               "dt=0.005" % nc_w, "sample_atoms": n},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of N=%d (fcc nc=%d) velocity Verlet + link-cell force, C restatement "
+                                   "of md_nve_lj.py/md_lj_ll_module.py (gcc -O2 -fopenmp); gfortran absent so the "
+                                   "Fortran twin cannot be built" % (args.steps, n, nc)},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    from examples_b200 import _lib
+    from examples_b200.device import REC_NPAIR, REC_T1, REC_VSQ, Simulation
+    if _lib.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libatlj has no CPU path")
+    _lib.check(_lib.lib().atlj_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = args.workload
+    if wl == "c5":
+        nc = NC_WEAK[world]
+    elif wl == "c2":
+        nc = 20
+    elif wl == "c4":
+        nc = 63
+    else:
+        raise SystemExit("unknown workload " + wl)
+    n, box, r, v = make_system(nc)
+
+    if world > 1:
+        from examples_b200.slab import SlabSimulation
+        sim = SlabSimulation(box, R_CUT, r, v, rank, world)
+    else:
+        sim = Simulation(box, R_CUT, r, v)
+    del r, v
+    sim.force()
+    t_melt0 = time.perf_counter()
+    done = 0
+    while done < args.melt:  # un-timed: melt the lattice so the pair count is liquid-like
+        k = min(500, args.melt - done)
+        sim.run_nve(DT, k, record=False)
+        done += k
+    sim.sync()
+    t_melt = time.perf_counter() - t_melt0
+
+    def barrier():
+        sim.sync()
+        if dist is not None:
+            dist.barrier()
+        sim.sync()
+
+    # ---- device-resident loop ---------------------------------------------------------------------------------------
+    sim.run_nve(DT, args.warmup, record=False)
+    sampler = ClockSampler(local_rank)
+    fp64_peak = _lib.measure_fp64_peak() if rank == 0 else 0.0
+    sim.enable_timing(True)
+    sim.timing()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.kernel_launches()
+    sim.timer_start()
+    rec = sim.run_nve(DT, args.steps, record=True)
+    ms = sim.timer_stop()
+    l1 = _lib.kernel_launches()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    cat = sim.timing()
+    sim.enable_timing(False)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_total = n
+    value = n_total * args.steps / (ms * 1e-3)
+    pairs_per_step = float(np.mean(rec[:, REC_NPAIR]))
+    temp = float(np.mean(rec[:, REC_VSQ])) / (3 * n_total - 3)
+    epot = float(np.mean(rec[:, REC_T1])) / n_total
+    ovr = bool(rec[:, 7].any())
+
+    # ---- end to end through host buffers (rank-local; single GPU only: the slab path keeps state on the device) --
+    e2e = None
+    if world == 1:
+        from examples_b200._lib import PinnedArray
+        rs, vs, fs, ids = sim.download_sorted()
+        pr, pv, pf = PinnedArray((n, 3)), PinnedArray((n, 3)), PinnedArray((n, 3))
+        pi = PinnedArray((n,), np.int32)
+        pr.array[:], pv.array[:], pf.array[:], pi.array[:] = rs, vs, fs, ids
+        ke = max(3, min(args.steps, 50))
+        for _ in range(3):
+            sim.nve_step_host(DT, pr.array, pv.array, pf.array, pi.array)
+        sim.sync()
+        t0 = time.perf_counter()
+        sim.timer_start()
+        for _ in range(ke):
+            sim.nve_step_host(DT, pr.array, pv.array, pf.array, pi.array)
+        ms_e = sim.timer_stop()
+        wall_e = time.perf_counter() - t0
+        ms_e = max(ms_e, wall_e * 1e3)  # host-side time counts too
+        e2e = {"value": n * ke / (ms_e * 1e-3), "unit": "atom-steps/s", "steps": ke,
+               "h2d_bytes_per_step": 3 * 24 * n + 4 * n, "d2h_bytes_per_step": 3 * 24 * n + 4 * n + 8 * _lib.NREC,
+               "api": "atlj_sim_nve_step_host: r,v,f,id in pinned host memory each step"}
+        # the drop-in force(box, r_cut, r) call with NumPy (pageable) arrays
+        from examples_b200 import md_lj_ll_module
+        rr = np.ascontiguousarray(pr.array.copy())
+        md_lj_ll_module.force(box, R_CUT, rr)
+        t0 = time.perf_counter()
+        kf = 5
+        for _ in range(kf):
+            md_lj_ll_module.force(box, R_CUT, rr)
+        e2e["force_call_atoms_per_s"] = n * kf / (time.perf_counter() - t0)
+        for a in (pr, pv, pf, pi):
+            a.free()
+
+    if rank != 0:
+        return
+    hbm_peak, hbm_src = peaks()
+    pair_ms = cat["pair"] / args.steps
+    other_ms = (cat["cells"] + cat["integrate"]) / args.steps
+    n_rank = n_total / world
+    flops = FLOP_PER_PAIR * pairs_per_step / world
+    ach = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
+    roofline = {"kernel": "pair_cells_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12,
+                "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
+                "peak_source": "register-resident DFMA probe (atlj_measure_fp64_peak) in this run; "
+                               "MEASURED_PEAKS.json has no fp64 figure",
+                "ms_per_launch": pair_ms, "flop_per_launch": flops,
+                "share_of_step": pair_ms / (ms / args.steps)}
+    ach_h = HBM_BYTES_NON_PAIR * n_rank / (other_ms * 1e-3) / 1e9 if other_ms > 0 else 0.0
+    roofline_hbm = {"kernel": "cell build (5 kernels) + kick_drift + kick_sums", "bound": "hbm", "achieved": ach_h,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach_h / hbm_peak, "traffic": None,
+                    "peak_source": hbm_src, "ms_per_step": other_ms, "bytes_per_step": HBM_BYTES_NON_PAIR * n_rank}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        # bounded sample: nc=40 (256,000 atoms) of the same fluid; O(N) algorithm
+        t0 = time.perf_counter()
+        cv, threads, cn, cdt = cpu_nve(40, 3, 1)
+        cpu = {"value": cv, "unit": "atom-steps/s", "cores": threads, "kind": "port",
+               "sample": "3 velocity-Verlet steps of N=%d (fcc nc=40 + Gaussian displacement), C restatement of the "
+                         "reference with OpenMP over cells, %.1f s" % (cn, time.perf_counter() - t0)}
+
+    line = {
+        "metric": "LJ atom-steps/sec (rho=0.75, r_cut=2.5)", "value": value, "unit": "atom-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic: fcc lattice (initialize.py formula), Gaussian velocities seed 20170101 at T=%.1f, "
+                "melted %d steps before timing" % (T_INIT, args.melt),
+        "config": {"workload": "%s: NVE LJ, N=%d (fcc nc=%d), rho=0.75, r_cut=2.5, dt=0.005, link cells sc=%d"
+                               % (wl, n_total, nc, int(np.floor(box / R_CUT))),
+                   "atoms_per_gpu": n_rank, "l2": "state %.0f MB per GPU exceeds the 126 MB L2"
+                   % (n_rank * 24 * 7 / 1e6) if n_rank * 24 * 7 > 126e6 else "state fits in L2 (device-resident loop)",
+                   "temperature": temp, "pot_per_atom": epot, "pairs_per_atom": pairs_per_step / n_total,
+                   "overlap": ovr, "melt_s": t_melt, "parallelism": "slab%d" % world if world > 1 else "single"},
+        "e2e": e2e, "gpu_launches": int(l1 - l0), "clocks": clocks, "roofline": roofline,
+        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+        "kernel_ms_per_step": {k: cat[k] / args.steps for k in cat},
+    }
+    print(json.dumps(line), flush=True)
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c4"])
+    ap.add_argument("--melt", type=int, default=2000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

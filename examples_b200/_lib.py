@@ -72,6 +72,14 @@ def lib():
     L.atlj_sim_mg_drift_pack.argtypes = [_vp, C.c_double, _vp, _vp, C.c_int64]
     L.atlj_sim_mg_bin_pack.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64]
     L.atlj_sim_mg_force_kick.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_double, _vp]
+    L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
+    L.atlj_host_alloc.restype = _vp
+    L.atlj_host_alloc.argtypes = [C.c_int64]
+    L.atlj_host_free.restype = None
+    L.atlj_host_free.argtypes = [_vp]
+    L.atlj_sim_timer_start.argtypes = [_vp]
+    L.atlj_sim_timer_stop.argtypes = [_vp, C.POINTER(C.c_double)]
+    L.atlj_sim_sync.argtypes = [_vp]
     L.atlj_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     L.atlj_sim_enable_timing.argtypes = [_vp, C.c_int]
     L.atlj_sim_timing.argtypes = [_vp, _dp]
@@ -106,3 +114,21 @@ def measure_fp64_peak():
     v = C.c_double(0.0)
     check(lib().atlj_measure_fp64_peak(C.byref(v)))
     return v.value
+
+
+class PinnedArray:
+    """A NumPy view of page-locked host memory (cudaHostAlloc) so that H2D/D2H copies are asynchronous DMA."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().atlj_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise AtljError("pinned allocation failed: " + lib().atlj_last_error().decode())
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().atlj_host_free(self.ptr)
+            self.ptr = None

@@ -236,6 +236,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
   cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev);
+  if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
   for (auto &t : s->ev_open) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
@@ -345,6 +346,70 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     Timer::end(s);
   }
   return sim_copy_rec(s, rec_host, nsteps);
+}
+
+int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_host, double *f_host, int32_t *id_host,
+                           int64_t n, double *rec_host) {
+  if (!s || !s->configured || !r_host || !v_host || !f_host || !id_host || n < 1 || n > s->cap) {
+    set_error("nve_step_host: bad arguments");
+    return ATLJ_ERR_ARG;
+  }
+  int rc;
+  s->n = n;
+  s->cur = 0;
+  const size_t b = sizeof(double) * 3 * (size_t)n;
+  ATLJ_CUDA(cudaMemcpyAsync(s->r[0], r_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->v[0], v_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->f, f_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->id[0], id_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->st));
+  const long long n3 = 3 * n;
+  const double half_dt = 0.5 * dt;
+  if ((rc = launch_kick_drift(s->st, n3, s->r[0], s->v[0], s->f, half_dt, dt, s->p.box, nullptr))) return rc;
+  if ((rc = sim_force(s, 0.0, false, s->rec_dev, false))) return rc;
+  if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, s->rec_dev + 4))) return rc;
+  ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(v_host, s->v[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(f_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st));
+  return sim_copy_rec(s, rec_host, 1);  // synchronises
+}
+
+void *atlj_host_alloc(int64_t bytes) {
+  if (device_ok() != ATLJ_OK || bytes < 0) return nullptr;
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    set_error("cudaHostAlloc(%lld) -> %s", (long long)bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void atlj_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int atlj_sim_timer_start(atlj_sim *s) {
+  if (!s) return ATLJ_ERR_ARG;
+  if (!s->sw0) {
+    ATLJ_CUDA(cudaEventCreate(&s->sw0));
+    ATLJ_CUDA(cudaEventCreate(&s->sw1));
+  }
+  ATLJ_CUDA(cudaEventRecord(s->sw0, s->st));
+  return ATLJ_OK;
+}
+int atlj_sim_timer_stop(atlj_sim *s, double *ms) {
+  if (!s || !s->sw0 || !ms) return ATLJ_ERR_ARG;
+  ATLJ_CUDA(cudaEventRecord(s->sw1, s->st));
+  ATLJ_CUDA(cudaEventSynchronize(s->sw1));
+  float m = 0.f;
+  ATLJ_CUDA(cudaEventElapsedTime(&m, s->sw0, s->sw1));
+  *ms = m;
+  return ATLJ_OK;
+}
+int atlj_sim_sync(atlj_sim *s) {
+  if (!s) return ATLJ_ERR_ARG;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  return ATLJ_OK;
 }
 
 int atlj_sim_enable_timing(atlj_sim *s, int on) {

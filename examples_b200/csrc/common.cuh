@@ -60,33 +60,34 @@ __host__ __device__ inline int neighbour_cell(const Geom &g, bool le, int shift,
     dy = (k / 3) % 3 - 1;
     dz = k % 3 - 1;
   } else {
-    if (k < 9) {  // dy = 0
+    // slots 0..8: dy = 0; slots 9..20: the "wide" row (4 x-offsets: top layer looking up / bottom layer looking
+    // down through the sheared boundary; interior cells use 3 of the 4); slots 21..29: the opposite plain row.
+    if (k >= 30) return -1;
+    const bool bottom = (cy == 0), top = (cy == g.sc - 1);
+    if (k < 9) {
       dy = 0;
       dx = k / 3 - 1;
       dz = k % 3 - 1;
-    } else if (k < 21) {  // dy = +1, up to 4 x-offsets
+    } else if (k < 21) {
       int m = k - 9;
-      dy = 1;
       dz = m % 3 - 1;
       int q = m / 3;  // 0..3
-      if (cy == g.sc - 1) {
-        dx = (1 - q) - shift;  // 1,0,-1,-2 minus shift
+      if (top) {
+        dy = 1;
+        dx = (1 - q) - shift;  // 1,0,-1,-2 minus shift   (md_lj_llle_module.py:88-92,133)
+      } else if (bottom) {
+        dy = -1;
+        dx = (q - 1) + shift;  // mirror image: -1,0,1,2 plus shift
       } else {
         if (q == 3) return -1;
+        dy = 1;
         dx = 1 - q;
       }
-    } else {  // dy = -1
-      int m = k - 21;
-      if (m >= 12) return -1;
-      dy = -1;
+    } else {
+      int m = k - 21;  // 0..8
       dz = m % 3 - 1;
-      int q = m / 3;
-      if (cy == 0) {
-        dx = (q - 1) + shift;  // -1,0,1,2 plus shift
-      } else {
-        if (q == 3) return -1;
-        dx = q - 1;
-      }
+      dx = m / 3 - 1;
+      dy = (bottom && !top) ? 1 : -1;
     }
   }
   int sc = g.sc;

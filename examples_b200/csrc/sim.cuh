@@ -29,6 +29,7 @@ struct atlj_sim {
   // multi-GPU slab bookkeeping
   int n_halo_left = 0, n_halo_right = 0;
   // timing
+  cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // stopwatch (atlj_sim_timer_*)
   bool timing = false;
   struct Ev {
     cudaEvent_t e0, e1;

@@ -131,6 +131,24 @@ class Simulation:
                                                  _ptr(rec)))
         return rec, s.value
 
+    def nve_step_host(self, dt, r, v, f, ids):
+        """One velocity-Verlet step with the state in HOST arrays (updated in place, cell order on return)."""
+        rec = np.zeros(NREC)
+        _lib.check(_lib.lib().atlj_sim_nve_step_host(self._h, float(dt), _ptr(r), _ptr(v), _ptr(f), _ptr(ids),
+                                                     r.shape[0], _ptr(rec)))
+        return rec
+
+    def timer_start(self):
+        _lib.check(_lib.lib().atlj_sim_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        _lib.check(_lib.lib().atlj_sim_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        _lib.check(_lib.lib().atlj_sim_sync(self._h))
+
     # ---- measurement ------------------------------------------------------------------------------------------
     def enable_timing(self, on=True):
         _lib.check(_lib.lib().atlj_sim_enable_timing(self._h, int(on)))

@@ -147,7 +147,22 @@ int atlj_sim_mg_bin_pack(atlj_sim *s, const double *recv_left_dev, const double 
 int atlj_sim_mg_force_kick(atlj_sim *s, const double *halo_from_left_dev, const double *halo_from_right_dev,
                            int64_t halo_cap, double dt, double *rec_dev);
 
+/* ---- host-buffer step (the end-to-end path of bench.py) --------------------------------------
+ * One velocity-Verlet step (md_nve_lj.py:178-192) whose state lives in HOST memory, as it does in the
+ * reference driver: r, v, f, id (n atoms, any order, f = forces of r) are copied to the device, the step
+ * runs there, and r, v, f, id come back (in cell order; id says which atom is which) with rec[ATLJ_NREC].
+ * Pinned buffers from atlj_host_alloc make the copies asynchronous DMA. */
+int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_host, double *f_host, int32_t *id_host,
+                           int64_t n, double *rec_host);
+void *atlj_host_alloc(int64_t bytes); /* page-locked host memory (cudaHostAlloc); NULL on failure */
+void atlj_host_free(void *p);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
+/* CUDA-event stopwatch on the sim's stream: start records an event, stop records a second one, waits for it
+ * and returns the elapsed device milliseconds. */
+int atlj_sim_timer_start(atlj_sim *s);
+int atlj_sim_timer_stop(atlj_sim *s, double *ms);
+int atlj_sim_sync(atlj_sim *s); /* cudaStreamSynchronize on the sim's stream */
 /* Register-resident DFMA loop on every SM: returns achieved fp64 FLOP/s (2 flop per DFMA) -- the
  * roofline denominator for the pair kernel (no fp64 figure in MEASURED_PEAKS.json). */
 int atlj_measure_fp64_peak(double *flops_per_s);
