@@ -1,6 +1,7 @@
 // C ABI of libatlj.so (include/atlj.h): device-resident simulation object + stateless host-array entry points.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -75,6 +76,16 @@ static int ensure_cells(atlj_sim *s, int ncell) {
   return ATLJ_OK;
 }
 
+static int ensure_partials(atlj_sim *s, int rows) {
+  if (rows <= s->partials_rows) return ATLJ_OK;
+  cudaFree(s->partials);
+  s->partials = nullptr;
+  int rc = dev_alloc(&s->partials, (size_t)rows * 8);
+  if (rc) return rc;
+  s->partials_rows = rows;
+  return ATLJ_OK;
+}
+
 static int ensure_rec(atlj_sim *s, int64_t nrec) {
   if (nrec <= s->rec_cap) return ATLJ_OK;
   cudaFree(s->rec_dev);
@@ -116,15 +127,19 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.g = s->g;
     a.p = p;
     Timer::begin(s, 0);
-    int nb = launch_pair_cells(s->st, a, false, n);
+    int nb;
+    if (s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ)
+      nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
+    else
+      nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, false, n) : launch_pair_tile(s->st, a, false);
     Timer::end(s);
     if (nb < 0) return nb;
-    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev))) return rc;
+    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2))) return rc;
     if (with_hessian) {
       a.fin = s->f;
       a.f = nullptr;
       Timer::begin(s, 3);
-      nb = launch_pair_cells(s->st, a, true, n);
+      nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
       Timer::end(s);
       if (nb < 0) return nb;
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
@@ -207,6 +222,9 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   }
   atlj_sim *s = new atlj_sim();
   s->st = (cudaStream_t)stream;
+  // A/B runs: "tile1" = first tiled kernel for every model, "warp" = first-generation warp-per-atom kernel
+  const char *op = getenv("ATLJ_PAIR_KERNEL");
+  s->pair_kernel = !op ? 0 : (strcmp(op, "warp") == 0 ? 2 : (strcmp(op, "tile1") == 0 ? 1 : 0));
   s->cap = capacity;
   size_t c = (size_t)capacity;
   bool ok = true;
@@ -217,7 +235,8 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
        dev_alloc(&s->cb.rank, c) == ATLJ_OK && dev_alloc(&s->cb.keys, c) == ATLJ_OK &&
        dev_alloc(&s->cb.block_sums, 8192) == ATLJ_OK && dev_alloc(&s->cb.err, 4) == ATLJ_OK &&
-       dev_alloc(&s->partials, (size_t)pair_grid_blocks() * 8) == ATLJ_OK && dev_alloc(&s->scal, 64) == ATLJ_OK;
+       dev_alloc(&s->scal, 64) == ATLJ_OK;
+  if (ok) ok = ensure_partials(s, pair_grid_blocks()) == ATLJ_OK;
   if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 4 * sizeof(int), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->scal, 0, 64 * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->f, 0, 3 * c * sizeof(double), s->st) == cudaSuccess;
@@ -278,6 +297,11 @@ int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, 
   double rc_cell = sqrt(r_cut_box_sq) * sc;
   s->p.rc2_cell = (float)(rc_cell * rc_cell * (1.0 + 1e-4));
   s->configured = true;
+  int rows = pair_grid_blocks();
+  if (pair_tile_grid(g) > rows) rows = pair_tile_grid(g);
+  if (pair_tile2_items(g) > rows) rows = pair_tile2_items(g);
+  int rc = ensure_partials(s, rows);
+  if (rc) return rc;
   return ensure_cells(s, g.ncell());
 }
 
@@ -531,7 +555,7 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.partials = s->partials;
     a.g = s->g;
     a.p = p;
-    nb = launch_pair_cells(s->st, a, true, (int)n);
+    nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true);
     if (nb < 0) return nb;
   } else {
     if (check_index)

@@ -145,9 +145,15 @@ struct PairArgs {
 };
 int pair_grid_blocks();  // blocks of the persistent pair kernel (partials has this many rows)
 int launch_pair_cells(cudaStream_t st, const PairArgs &a, bool hessian, int natoms_hint);
+int pair_tile_grid(const Geom &g);  // CTAs of the tiled kernel (rows of partials it writes)
+int launch_pair_tile(cudaStream_t st, const PairArgs &a, bool hessian);  // -> CTAs launched or a negative status
+int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the second-generation LJ kernel
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);  // -> items or a negative status
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)
-int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec);
+// (also zeroes *reset_counter, the work counter of the tiled kernel, when it is not null)
+int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
+                    int *reset_counter = nullptr);
 
 }  // namespace atlj

@@ -18,112 +18,14 @@
 // exact fp64 test accepts; the exact test then decides.  Per-atom forces are finished with a warp-shuffle
 // reduction, totals accumulate per lane in fp64 and are reduced per CTA, then by launch_finalize in fixed order.
 #include "common.cuh"
+#include "pair_math.cuh"
 
 namespace atlj {
 
 constexpr int PW = 4;      // warps per CTA
 constexpr int CAP = 512;   // staged candidates per chunk (27 cells x ~12-15 atoms fits; larger sets loop)
-constexpr unsigned FULL = 0xffffffffu;
 
 int pair_grid_blocks() { return 148 * 16; }
-
-struct Acc {
-  double a, pot, vir, lap, hes;
-  unsigned long long np;
-  int ovr;
-};
-
-// separation with the reference's exact operation order; returns the in-range predicate
-template <bool LE>
-__device__ __forceinline__ bool pair_sep(double rix, double riy, double riz, double xj, double yj, double zj,
-                                         double strain, double rcbsq, double &dx, double &dy, double &dz, double &s) {
-  dx = __dsub_rn(rix, xj);
-  dy = __dsub_rn(riy, yj);
-  dz = __dsub_rn(riz, zj);
-  if (LE) dx = __dsub_rn(dx, __dmul_rn(rint(dy), strain));  // md_lj_le_module.py:94
-  dx = __dsub_rn(dx, rint(dx));
-  dy = __dsub_rn(dy, rint(dy));
-  dz = __dsub_rn(dz, rint(dz));
-  s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));  // ((x^2+y^2)+z^2), no FMA
-  return s < rcbsq;
-}
-
-template <int MODEL>
-__device__ __forceinline__ void pair_force_term(const Phys &p, double dx, double dy, double dz, double s, double &fx,
-                                                double &fy, double &fz, Acc &acc) {
-  double s2 = __dmul_rn(s, p.box_sq);
-  dx *= p.box;
-  dy *= p.box;
-  dz *= p.box;
-  double sr2 = __drcp_rn(s2);  // == 1.0/s2, correctly rounded (feeds the overlap predicate)
-  acc.ovr |= (sr2 > 1.77) ? 1 : 0;
-  double sr6 = sr2 * sr2 * sr2;
-  double sr12 = sr6 * sr6;
-  double cut = sr12 - sr6;
-  double vir = cut + sr12;
-  acc.lap += (22.0 * sr12 - 5.0 * sr6) * sr2;
-  double fs = vir * sr2;
-  double fxi = dx * fs;
-  fx += fxi;
-  fy += dy * fs;
-  fz += dz * fs;
-  acc.vir += vir;
-  if (MODEL == ATLJ_MODEL_LJ) {
-    acc.pot += cut - p.pot_cut;
-    acc.a += cut;
-  } else {
-    acc.pot += cut + 0.25;  // md_lj_le_module.py:106
-    acc.a += dy * fxi;      // pyx, md_lj_le_module.py:110
-  }
-  acc.np++;
-}
-
-// md_lj_module.py:176-191
-__device__ __forceinline__ void pair_hess_term(const Phys &p, double dx, double dy, double dz, double s, double gx,
-                                               double gy, double gz, Acc &acc) {
-  double s2 = __dmul_rn(s, p.box_sq);
-  dx *= p.box;
-  dy *= p.box;
-  dz *= p.box;
-  double ff = gx * gx + gy * gy + gz * gz;
-  double rf = dx * gx + dy * gy + dz * gz;
-  double sr2 = __drcp_rn(s2);
-  double sr6 = sr2 * sr2 * sr2;
-  double sr8 = sr6 * sr2;
-  double sr10 = sr8 * sr2;
-  double v1 = 24.0 * (1.0 - 2.0 * sr6) * sr8;
-  double v2 = 96.0 * (7.0 * sr6 - 2.0) * sr10;
-  acc.hes += v1 * ff + v2 * (rf * rf);
-  acc.np++;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
-
-// CTA-level reduction of the accumulators into one row of partials (fixed order: lanes by butterfly, warps 0..NW-1)
-template <int NW>
-__device__ __forceinline__ void block_store_partials(Acc acc, double *__restrict__ row) {
-  __shared__ double red[NW][8];
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[7] = {acc.a, acc.pot, acc.vir, acc.lap, acc.hes, (double)acc.np, (double)acc.ovr};
-#pragma unroll
-  for (int k = 0; k < 7; k++) v[k] = warp_sum(v[k]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 7; k++) red[warp][k] = v[k];
-  }
-  __syncthreads();
-  if (threadIdx.x < 7) {
-    double s = 0.0;
-    for (int w = 0; w < NW; w++) s += red[w][threadIdx.x];
-    row[threadIdx.x] = s;
-  }
-  if (threadIdx.x == 7) row[7] = 0.0;
-}
 
 // ---- link-cell kernel --------------------------------------------------------------------------------------------
 template <int MODEL, bool HESS>
@@ -372,7 +274,9 @@ int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, 
 
 // ---- fixed-order reduction of the CTA partials + the reference's final scaling ------------------------------------
 __global__ void __launch_bounds__(256) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,
-                                                       int hessian, double *__restrict__ rec) {
+                                                       int hessian, double *__restrict__ rec,
+                                                       int *__restrict__ reset_counter) {
+  if (threadIdx.x == 0 && reset_counter) *reset_counter = 0;
   __shared__ double sm[256][7];
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int b = threadIdx.x; b < nblocks; b += 256) {
@@ -412,8 +316,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double *__restrict_
   }
 }
 
-int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec) {
-  finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec);
+int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
+                    int *reset_counter) {
+  finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -1,0 +1,479 @@
+// Second-generation tiled LJ pair-force kernel: the hot kernel of the device-resident loop.
+//
+// Reference arithmetic: python_examples/md_lj_ll_module.py:134-165; scaling md_lj_module.py:143-147.
+// Same exactness scheme as pair_tile.cu (fp32 filter that never drops an in-range pair -> fp64 evaluation, the
+// reference's exact operation sequence for every pair within 1e-8 of the cutoff or near the overlap threshold),
+// with the structure chosen from the ncu profile of the first tiled kernel (profiles/r1_pair_tile_v1.md):
+//   * a CTA owns TWO adjacent y rows of cells, so the staged cross-section is 3 x 4 = 12 rows for two i rows
+//     (6 per i row instead of 9): a third less shared memory per atom -> 4 CTAs (16 warps) per SM, and a third
+//     less staging work;
+//   * staged candidates are laid out CELL-major (for each z cell: 4 y-offsets x 3 x-offsets), so the candidates of
+//     one thread are ONE contiguous run per z cell (3 runs, ~111 candidates each) instead of 9 short windows;
+//   * the fp32 filter runs on packed pairs of candidates with FFMA2/FADD2 (sm_100 f32x2): 2 LDS.128 + 1 FADD2 +
+//     3 FFMA2 + 2 funnel shifts per TWO candidates; the sign bit of (|qj|^2 - 2 qi.qj) - (thr - |qi|^2) is shifted
+//     straight into left-aligned 32-bit mask words;
+//   * work items (x layer, y row pair, z part) are handed out through an atomic counter so the tail of the grid
+//     stays busy; every item writes its own row of partial sums, so totals stay bitwise reproducible.
+#include "common.cuh"
+#include "pair_math.cuh"
+
+namespace atlj {
+
+constexpr int U_NT = 128;               // threads per CTA = i atoms per batch
+constexpr int U_CAP = 1280;             // staged candidates per chunk
+constexpr int U_MAXC = 24;              // logical cells per chunk, including one halo cell at each end
+constexpr int U_K = 12;                 // staged rows per z cell: 4 y-offsets (outer) x 3 x-offsets (inner)
+constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
+constexpr int U_WW = 6;                 // mask words per window (<= 191 candidates per window)
+constexpr int U_NWORDS = 3 * U_WW;
+
+static inline size_t tile2_smem_bytes() {
+  return sizeof(double) * 3 * U_CAP + sizeof(float4) * (U_CAP + 2) + sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
+}
+
+int pair_tile2_parts(const Geom &g) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("ATLJ_TILE_PARTS");
+    forced = e ? atoi(e) : 0;
+  }
+  int maxp = g.sc / 4 < 1 ? 1 : g.sc / 4;
+  if (forced > 0) return forced > maxp ? maxp : forced;
+  int rows2 = g.nx_own * ((g.sc + 1) / 2);
+  int want = (148 * 4 * 5 + rows2 - 1) / rows2;  // ~5 items per resident CTA
+  return want < 1 ? 1 : (want > maxp ? maxp : want);
+}
+int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * pair_tile2_parts(g); }
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// A pair the fast fp64 path could not classify safely (within 1e-8 of the cutoff, or close to the overlap
+// threshold): the reference's exact operation sequence on the original coordinates decides, then it is accumulated
+// like md_lj_module.py:100-115.  Rare (probability ~1e-8 per pair in a fluid), hence out of line.
+struct ExactOut {
+  double dx, dy, dz, s;  // separation and its square in sigma units (reference operation order)
+  int in, ovr;           // in range (md_lj_module.py:99), overlap (md_lj_module.py:103)
+};
+__device__ __noinline__ ExactOut exact_pair(const double *__restrict__ r, Phys p, const int *S, const int *egl, int NE,
+                                            int i, int j) {
+  ExactOut o;
+  int en = 0;
+  for (int step = 256; step >= 1; step >>= 1)
+    if (en + step < NE && S[en + step] <= j) en += step;
+  const size_t jg = (size_t)(egl[en] + (j - S[en]));
+  double dx, dy, dz, s;
+  o.in = pair_sep<false>(r[3 * (size_t)i], r[3 * (size_t)i + 1], r[3 * (size_t)i + 2], r[3 * jg], r[3 * jg + 1],
+                         r[3 * jg + 2], 0.0, p.r_cut_box_sq, dx, dy, dz, s);
+  o.s = __dmul_rn(s, p.box_sq);
+  o.ovr = o.in && (__drcp_rn(o.s) > 1.77);
+  o.dx = dx * p.box, o.dy = dy * p.box, o.dz = dz * p.box;
+  return o;
+}
+
+// sr^2 = 1/s: MUFU.RCP64H seed (relative error <= 2^-23) + one Newton step -> <= 2^-46
+__device__ __forceinline__ double rcp46(double s) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  return fma(y, fma(-s, y, 1.0), y);
+}
+
+// one in-range pair into the running sums: forces (md_lj_module.py:109,113) and sr^6, sr^12, sr^8, sr^14
+#define U_ACCUM(dx_, dy_, dz_, s_)                                                     \
+  do {                                                                                 \
+    const double sr2_ = rcp46(s_);                                                     \
+    const double sr6_ = sr2_ * sr2_ * sr2_, sr12_ = sr6_ * sr6_;                       \
+    const double sr8_ = sr6_ * sr2_, sr14_ = sr12_ * sr2_;                             \
+    const double fs_ = fma(2.0, sr14_, -sr8_); /* (cut + sr12) * sr2 */                \
+    fx = fma(dx_, fs_, fx), fy = fma(dy_, fs_, fy), fz = fma(dz_, fs_, fz);            \
+    a6 += sr6_, a12 += sr12_, a8 += sr8_, a14 += sr14_;                                \
+  } while (0)
+#define U_EXACT(jj)                                                                    \
+  do {                                                                                 \
+    const ExactOut o_ = exact_pair(a.r, p, S, egl, NE, i, (jj));                       \
+    ovr |= o_.ovr;                                                                     \
+    if (o_.in) {                                                                       \
+      U_ACCUM(o_.dx, o_.dy, o_.dz, o_.s);                                              \
+      npf++;                                                                           \
+    }                                                                                  \
+  } while (0)
+
+__global__ void __launch_bounds__(U_NT, 4)
+    pair_tile2_kernel(PairArgs a, int parts, int nyb, int nitems, int *__restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *ux = reinterpret_cast<double *>(smem_raw);
+  double *uy = ux + U_CAP;
+  double *uz = uy + U_CAP;
+  float4 *qp = reinterpret_cast<float4 *>(uz + U_CAP);  // pair p: qp[2p] = (x0,x1,y0,y1), qp[2p+1] = (z0,z1,n0,n1)
+  int *S = reinterpret_cast<int *>(qp + U_CAP + 2);      // [U_NE + 4] staged offset of entry e = cell*12 + row
+  int *egl = S + U_NE + 4;                               // [U_NE] global index of the first atom of entry e
+  __shared__ int rowcell0[U_K];
+  __shared__ int wsum[U_NT / 32];
+  __shared__ unsigned s_q2max;
+  __shared__ int s_maxwin, s_item;
+
+  const Geom g = a.g;
+  const Phys p = a.p;
+  const int sc = g.sc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *__restrict__ cs = a.cell_start;
+  const double box = p.box;
+  const double rc2s = p.r_cut_box_sq * p.box_sq;
+  const double band = 1e-8 * rc2s;
+  const double sovr = (1.0 / 1.77) * (1.0 + 1e-6);
+  const int band_hi = __double2hiint(band), sovr_hi = __double2hiint(sovr);
+  const double sci = 1.0 / (double)sc;
+  const float *qf = reinterpret_cast<const float *>(qp);
+  const unsigned ux_s = (unsigned)__cvta_generic_to_shared(ux);
+
+  for (;;) {
+    // ---- next work item ----------------------------------------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u, s_maxwin = 0;
+    __syncthreads();
+    const int item = s_item;
+    if (item >= nitems) break;
+    const int part = item % parts, t2 = item / parts;
+    const int yb = t2 % nyb, xo = t2 / nyb;
+    const int lx = g.h + xo, y0 = 2 * yb;
+    const bool two = (y0 + 1 < sc);
+    const int zA = (int)((long long)sc * part / parts), zB = (int)((long long)sc * (part + 1) / parts);
+    const int ownA0 = (lx * sc + y0) * sc, ownB0 = ownA0 + sc;
+    if (tid < U_K) {
+      // row k = yi*3 + xi holds cells (lx-1+xi, y0-1+yi); yi = 0..2 are the dy = -1,0,1 neighbours of row y0 and
+      // yi = 1..3 those of row y0+1; the ids come from the stencil function the bit-exact tests cover
+      const int yi = tid / 3, xi = tid - 3 * yi;
+      int c;
+      if (yi < 3)
+        c = neighbour_cell(g, false, 0, lx, y0, 0, xi * 9 + yi * 3 + 1);
+      else
+        c = two ? neighbour_cell(g, false, 0, lx, y0 + 1, 0, xi * 9 + 2 * 3 + 1) : -1;
+      rowcell0[tid] = c;
+    }
+    const double ctrx = ((lx - g.h + g.x_lo) + 0.5) * sci - 0.5;
+    const double ctry = (y0 + (two ? 1.0 : 0.5)) * sci - 0.5;
+
+    // sums of sr^6, sr^12, sr^8, sr^14 over this thread's pairs; cut, vir, lap follow at the end of the item
+    double a6 = 0.0, a12 = 0.0, a8 = 0.0, a14 = 0.0;
+    unsigned npf = 0u;
+    int ovr = 0;
+
+    for (int z = zA; z < zB;) {
+      // ---- chunk extent: whole cells of both rows holding <= U_NT atoms ---------------------------------------
+      const int sA = cs[ownA0 + z], sB = two ? cs[ownB0 + z] : 0;
+      int ok = 0;
+      if (tid < U_MAXC - 2 && z + tid < zB)
+        ok = ((cs[ownA0 + z + tid + 1] - sA) + (two ? cs[ownB0 + z + tid + 1] - sB : 0)) <= U_NT;
+      int ncz = __syncthreads_count(ok);  // barrier: previous chunk is done with shared memory
+      if (ncz == 0) ncz = 1;
+
+      int total, NE;
+      for (;;) {
+        // ---- entry table: counts -> exclusive scan (3 entries per thread) -------------------------------------
+        NE = (ncz + 2) * U_K;
+        int cnt[3], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int e = 3 * tid + u;
+          cnt[u] = 0;
+          if (e < NE) {
+            const int c = e / U_K, k = e - c * U_K, rc0 = rowcell0[k];
+            int zc = z - 1 + c;
+            zc = zc < 0 ? zc + sc : (zc >= sc ? zc - sc : zc);
+            if (rc0 >= 0) {
+              const int g0 = cs[rc0 + zc];
+              cnt[u] = cs[rc0 + zc + 1] - g0;
+              egl[e] = g0;
+            } else {
+              egl[e] = 0;
+            }
+          }
+          sum += cnt[u];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int off = incl - sum;
+#pragma unroll
+        for (int w = 0; w < U_NT / 32; w++)
+          if (w < warp) off += wsum[w];
+        total = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int e = 3 * tid + u;
+          if (e <= NE) S[e] = off;
+          off += cnt[u];
+        }
+        __syncthreads();
+        if (total <= U_CAP || ncz == 1) break;
+        ncz = max(1, min(ncz - 1, (int)((long long)ncz * U_CAP / total)));
+      }
+      const int nA = cs[ownA0 + z + ncz] - sA, nB = two ? cs[ownB0 + z + ncz] - sB : 0;
+      const int ni = nA + nB;
+      if (ni == 0) {
+        z += ncz;
+        continue;
+      }
+      // longest window (9 consecutive entries of 3 consecutive cells are three windows; check each)
+      {
+        int mw = 0;
+        for (int e = tid; e < (ncz + 2) * 2; e += U_NT) {
+          const int c = e >> 1, k0 = (e & 1) * 3;
+          mw = max(mw, S[c * U_K + k0 + 9] - S[c * U_K + k0]);
+        }
+        mw = __reduce_max_sync(FULL, mw);
+        if (lane == 0) atomicMax(&s_maxwin, mw);
+      }
+      __syncthreads();
+      const bool slow = total > U_CAP || s_maxwin > 32 * U_WW - 2;
+
+      if (slow) {
+        // ---- crowded neighbourhood (does not occur in a fluid): exact arithmetic straight from global memory ----
+        for (int il = tid; il < ni; il += U_NT) {
+          const bool inA = il < nA;
+          const int own0 = inA ? ownA0 : ownB0;
+          const int i = inA ? sA + il : sB + (il - nA);
+          const int k0 = inA ? 0 : 3;
+          int c = 0;
+          for (int step = 16; step >= 1; step >>= 1)
+            if (c + step < ncz && cs[own0 + z + c + step] <= i) c += step;
+          const int zi = z + c;
+          const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
+          double fx = 0, fy = 0, fz = 0;
+          for (int k = k0; k < k0 + 9; k++) {
+            const int rc0 = rowcell0[k];
+            if (rc0 < 0) continue;
+            for (int dz = -1; dz <= 1; dz++) {
+              int zj = zi + dz;
+              zj = zj < 0 ? zj + sc : (zj >= sc ? zj - sc : zj);
+              for (int j = cs[rc0 + zj]; j < cs[rc0 + zj + 1]; j++) {
+                if (j == i) continue;
+                double dx, dy, dzz, s;
+                if (pair_sep<false>(rix, riy, riz, a.r[3 * (size_t)j], a.r[3 * (size_t)j + 1],
+                                    a.r[3 * (size_t)j + 2], 0.0, p.r_cut_box_sq, dx, dy, dzz, s)) {
+                  const double s2 = __dmul_rn(s, p.box_sq);
+                  if (__drcp_rn(s2) > 1.77) ovr = 1;  // md_lj_module.py:103
+                  U_ACCUM(dx * box, dy * box, dzz * box, s2);
+                  npf++;
+                }
+              }
+            }
+          }
+          a.f[3 * (size_t)i] = 24.0 * fx;
+          a.f[3 * (size_t)i + 1] = 24.0 * fy;
+          a.f[3 * (size_t)i + 2] = 24.0 * fz;
+        }
+        __syncthreads();
+        if (tid == 0) s_maxwin = 0;
+        z += ncz;
+        continue;
+      }
+
+      // ---- stage the candidates: half a warp per (cell,row) entry ----------------------------------------------
+      {
+        const double ctrz = (z + 0.5 * ncz) * sci - 0.5;
+        const int hw = tid >> 4, hl = tid & 15;
+        float q2m = 0.f;
+        for (int e = hw; e < NE; e += U_NT / 16) {
+          const int s0 = S[e], cnt = S[e + 1] - s0;
+          if (cnt == 0) continue;
+          const int c = e / U_K;
+          const int lc = z - 1 + c;
+          const double wz = lc < 0 ? -1.0 : (lc >= sc ? 1.0 : 0.0);
+          const int g0 = egl[e];
+          for (int k = hl; k < cnt; k += 16) {
+            const size_t j = (size_t)(g0 + k);
+            const int s = s0 + k;
+            double x = a.r[3 * j] - ctrx, y = a.r[3 * j + 1] - ctry, zz = (a.r[3 * j + 2] + wz) - ctrz;
+            x -= rint(x);
+            y -= rint(y);
+            x *= box, y *= box, zz *= box;
+            ux[s] = x, uy[s] = y, uz[s] = zz;
+            const float fx = (float)x, fy = (float)y, fz = (float)zz;
+            const float n2 = fx * fx + fy * fy + fz * fz;
+            float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
+            d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
+            q2m = fmaxf(q2m, n2);
+          }
+        }
+        unsigned qb = __reduce_max_sync(FULL, __float_as_uint(q2m));
+        if (lane == 0) atomicMax(&s_q2max, qb);
+      }
+      __syncthreads();
+      // filter threshold (see pair_tile.cu): rounding of the filter <= ~2e-6 Q^2; 6e-6 Q^2 is used
+      const float q2max = __uint_as_float(s_q2max);
+      const float thr = (float)(rc2s * (1.0 + 1e-6) + 6e-6 * (double)q2max) * (1.0f + 2e-7f);
+
+      for (int ib = 0; ib < ni; ib += U_NT) {
+        const int il = ib + tid;
+        const bool act = il < ni;
+        const bool inA = il < nA;
+        const int own0 = inA ? ownA0 : ownB0;
+        const int i = act ? (inA ? sA + il : sB + (il - nA)) : 0;
+        const int k0 = inA ? 0 : 3;
+        int myc = 0, self = 0;
+        if (act) {
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1)
+            if (myc + step < ncz && cs[own0 + z + myc + step] <= i) myc += step;
+          self = S[(myc + 1) * U_K + k0 + 4] + (i - cs[own0 + z + myc]);
+        }
+        const double uix = ux[self], uiy = uy[self], uiz = uz[self];
+        const float *qs = qf + 8 * (self >> 1) + (self & 1);
+        const float qix = qs[0], qiy = qs[2], qiz = qs[4], qin = qs[6];
+        const float2 m2x = make_float2(-2.f * qix, -2.f * qix), m2y = make_float2(-2.f * qiy, -2.f * qiy),
+                     m2z = make_float2(-2.f * qiz, -2.f * qiz);
+        const float nt = qin - thr;
+        const float2 nti = make_float2(nt, nt);
+
+        // ---- phase 1: packed fp32 filter -> left-aligned mask words --------------------------------------------
+        uint2 mw[U_NWORDS];  // (mask word, staged index of the candidate of its bit 0 ... i.e. of bit 31, plus 31)
+        int nw = 0;
+        if (act) {
+#pragma unroll 1
+          for (int w = 0; w < 3; w++) {
+            const int eb = (myc + w) * U_K + k0;
+            const int b = S[eb], e = S[eb + 9];
+            if (e <= b) continue;
+            const int b0 = b & ~1;
+            const int npairs = ((e + 1) >> 1) - (b0 >> 1);
+            const int nw0 = nw;
+            const float4 *pp = qp + b0;  // = qp + 2 * (b0 >> 1)
+            for (int base = 0; base < npairs; base += 16) {
+              const int n = min(16, npairs - base);
+              unsigned wd = 0u;
+#pragma unroll 4
+              for (int k = 0; k < n; k++) {
+                const float4 A = pp[2 * (base + k)], B = pp[2 * (base + k) + 1];
+                float2 t = __fadd2_rn(make_float2(B.z, B.w), nti);
+                t = __ffma2_rn(m2z, make_float2(B.x, B.y), t);
+                t = __ffma2_rn(m2y, make_float2(A.z, A.w), t);
+                t = __ffma2_rn(m2x, make_float2(A.x, A.y), t);
+                wd = __funnelshift_l(__float_as_uint(t.x), wd, 1);
+                wd = __funnelshift_l(__float_as_uint(t.y), wd, 1);
+              }
+              wd <<= 2 * (16 - n);
+              mw[nw] = make_uint2(wd, (unsigned)(b0 + 2 * base + 31));  // bit p <-> candidate (b0 + 2*base + 31) - p
+              nw++;
+            }
+            // candidates outside [b, e) that rode along in the first / last pair, and the atom itself
+            if (b & 1) mw[nw0].x &= 0x7fffffffu;
+            if (e & 1) {
+              const int pos = e - b0;
+              mw[nw0 + (pos >> 5)].x &= ~(0x80000000u >> (pos & 31));
+            }
+            if (w == 1) {
+              const int pos = self - b0;
+              mw[nw0 + (pos >> 5)].x &= ~(0x80000000u >> (pos & 31));
+            }
+          }
+        }
+
+        // ---- phase 2: fp64 evaluation of the surviving pairs ----------------------------------------------------
+        // Every lane walks its own mask words, so in almost every iteration SOME lane moves on to its next word:
+        // that step is branch-free (selects + one always-issued local load whose result is needed an iteration
+        // later at the earliest).  Each iteration takes up to TWO pairs off the current word and evaluates them as
+        // two independent fp64 chains (the kernel is latency-, not fp64-throughput-bound); a dead slot gets
+        // s = 1e300, whose sr^6 underflows to exactly 0, so no branch is needed around the arithmetic.
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        int nd = 0;
+        int defer[4];
+        int ww = 0;
+        uint2 cur = make_uint2(0u, 0u), nxt = make_uint2(0u, 0u);  // (mask, staged index of bit 0's candidate + 31)
+        if (nw > 0) cur = mw[0];
+        if (nw > 1) nxt = mw[1];
+        while (ww < nw) {
+          const bool adv = cur.x == 0u;
+          if (adv) ww++;
+          const uint2 ld = mw[min(ww + 1, U_NWORDS - 1)];
+          if (adv) cur = nxt;
+          unsigned cm = cur.x;
+          const bool live0 = cm != 0u;
+          const int p0 = 31 - __clz(cm | 1u);
+          cm &= ~(1u << p0);
+          const bool live1 = cm != 0u;
+          const int p1 = 31 - __clz(cm | 1u);
+          cm &= ~(1u << p1);
+          cur.x = cm;
+          const int j0 = live0 ? (int)cur.y - p0 : 0, j1 = live1 ? (int)cur.y - p1 : 0;
+          const double dx0 = uix - lds_f64(ux_s + 8u * j0), dy0 = uiy - lds_f64(ux_s + 8u * (j0 + U_CAP)),
+                       dz0 = uiz - lds_f64(ux_s + 8u * (j0 + 2 * U_CAP));
+          const double dx1 = uix - lds_f64(ux_s + 8u * j1), dy1 = uiy - lds_f64(ux_s + 8u * (j1 + U_CAP)),
+                       dz1 = uiz - lds_f64(ux_s + 8u * (j1 + 2 * U_CAP));
+          double s0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), s1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+          const int e0 = __double2hiint(s0 - rc2s), e1 = __double2hiint(s1 - rc2s);
+          // |s - rc2s| <= band or s < sovr, tested conservatively on the high words (integer pipe, not fp64):
+          // such pairs are set aside and decided with the reference's exact operation sequence
+          const bool b0 = live0 & (((e0 & 0x7fffffff) <= band_hi) | (__double2hiint(s0) <= sovr_hi));
+          const bool b1 = live1 & (((e1 & 0x7fffffff) <= band_hi) | (__double2hiint(s1) <= sovr_hi));
+          if (b0 | b1) {
+            if (b0) defer[nd++] = j0;
+            if (b1) defer[nd++] = j1;
+            if (nd >= 3) {
+              for (int k = 0; k < nd; k++) U_EXACT(defer[k]);
+              nd = 0;
+            }
+          }
+          const bool v0 = live0 & !b0 & (e0 < 0), v1 = live1 & !b1 & (e1 < 0);  // e < 0 <=> s < rc2s
+          s0 = v0 ? s0 : 1e300;
+          s1 = v1 ? s1 : 1e300;
+          U_ACCUM(dx0, dy0, dz0, s0);
+          U_ACCUM(dx1, dy1, dz1, s1);
+          npf += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
+          if (adv) nxt = (ww + 1 < nw) ? ld : make_uint2(0u, 0u);
+        }
+        for (int k = 0; k < nd; k++) U_EXACT(defer[k]);
+        if (act) {
+          a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
+          a.f[3 * (size_t)i + 1] = 24.0 * fy;
+          a.f[3 * (size_t)i + 2] = 24.0 * fz;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_q2max = 0u, s_maxwin = 0;
+      z += ncz;
+    }
+    // cut = sr12 - sr6, pot = cut - pot_cut, vir = cut + sr12, lap = (22 sr12 - 5 sr6) sr2 (md_lj_module.py:104-108)
+    Acc acc;
+    {
+      const double cutacc = a12 - a6;
+      acc.pot = cutacc - p.pot_cut * (double)npf;
+      acc.a = cutacc;
+      acc.vir = cutacc + a12;
+      acc.lap = 22.0 * a14 - 5.0 * a8;
+      acc.hes = 0.0;
+      acc.np = npf;
+      acc.ovr = ovr;
+    }
+    block_store_partials<U_NT / 32>(acc, a.partials + 8 * (size_t)item);
+  }
+}
+
+// returns the number of partial rows written (= work items) or a negative status
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
+  static int grid = 0;
+  const size_t smem = tile2_smem_bytes();
+  if (grid == 0) {
+    ATLJ_CUDA(cudaFuncSetAttribute(pair_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    ATLJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_tile2_kernel, U_NT, smem));
+    ATLJ_CUDA(cudaGetDevice(&dev));
+    ATLJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    grid = (per_sm < 1 ? 1 : per_sm) * sms;
+  }
+  const int parts = pair_tile2_parts(a.g);
+  const int nyb = (a.g.sc + 1) / 2;
+  const int nitems = a.g.nx_own * nyb * parts;
+  pair_tile2_kernel<<<grid < nitems ? grid : nitems, U_NT, smem, st>>>(a, parts, nyb, nitems, work_counter);
+  ATLJ_LAUNCHED();
+  return nitems;
+}
+
+}  // namespace atlj

@@ -20,7 +20,9 @@ struct atlj_sim {
   double *f = nullptr;  // forces in the order of r[cur]
   atlj::CellBufs cb{};
   int ncell_alloc = 0;
-  double *partials = nullptr;  // [pair_grid_blocks()][8]
+  double *partials = nullptr;  // [partials_rows][8]
+  int partials_rows = 0;
+  int pair_kernel = 0;  // 0 = tile2 (LJ) / tile1 (WCA, hessian); 1 = tile1 everywhere; 2 = warp-per-atom
   double *scal = nullptr;      // 64 device scalars (thermostat state, reduction results)
   double *rec_dev = nullptr;   // per-step records
   int64_t rec_cap = 0;

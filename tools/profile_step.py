@@ -1,0 +1,24 @@
+"""Short device-resident NVE run for ncu: `python tools/profile_step.py [nc] [melt] [steps]`."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import DT, R_CUT, make_system  # noqa: E402
+from examples_b200.device import Simulation  # noqa: E402
+
+nc = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+melt = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+n, box, r, v = make_system(nc)
+sim = Simulation(box, R_CUT, r, v)
+sim.force()
+sim.run_nve(DT, melt, record=False)
+sim.enable_timing(True)
+sim.timing()
+rec = sim.run_nve(DT, steps)
+t = sim.timing()
+print("N=%d steps=%d pairs/atom=%.3f T=%.3f ms/step: pair %.4f cells %.4f integrate %.4f"
+      % (n, steps, rec[-1, 8] / n, rec[-1, 4] / (3 * n - 3), t["pair"] / steps, t["cells"] / steps,
+         t["integrate"] / steps))
+sim.close()
