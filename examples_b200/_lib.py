@@ -67,11 +67,8 @@ def lib():
     L.atlj_sim_run_nve.argtypes = [_vp, C.c_double, C.c_int, C.c_int, _vp]
     L.atlj_sim_run_baoab.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp]
     L.atlj_sim_run_baoab_noise.argtypes = [_vp, C.c_double, C.c_double, C.c_double, _vp, C.c_int, _vp]
-    L.atlj_sim_run_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
+    L.atlj_sim_run_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
     L.atlj_sim_run_sllod.argtypes = [_vp, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, _vp]
-    L.atlj_sim_mg_drift_pack.argtypes = [_vp, C.c_double, _vp, _vp, C.c_int64]
-    L.atlj_sim_mg_bin_pack.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64]
-    L.atlj_sim_mg_force_kick.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_double, _vp]
     L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
     L.atlj_host_alloc.restype = _vp
     L.atlj_host_alloc.argtypes = [C.c_int64]

@@ -86,7 +86,7 @@ static int ensure_partials(atlj_sim *s, int rows) {
   return ATLJ_OK;
 }
 
-static int ensure_rec(atlj_sim *s, int64_t nrec) {
+int sim_ensure_rec(atlj_sim *s, int64_t nrec) {
   if (nrec <= s->rec_cap) return ATLJ_OK;
   cudaFree(s->rec_dev);
   s->rec_dev = nullptr;
@@ -240,7 +240,7 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 4 * sizeof(int), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->scal, 0, 64 * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->f, 0, 3 * c * sizeof(double), s->st) == cudaSuccess;
-  if (ok) ok = ensure_rec(s, 64) == ATLJ_OK;
+  if (ok) ok = sim_ensure_rec(s, 64) == ATLJ_OK;
   if (!ok) {
     atlj_sim_destroy(s);
     return nullptr;
@@ -311,6 +311,7 @@ int atlj_sim_upload(atlj_sim *s, const double *r_host, const double *v_host, con
     return ATLJ_ERR_ARG;
   }
   s->n = n;
+  s->n_total = n;
   s->cur = 0;
   size_t b = sizeof(double) * 3 * (size_t)n;
   ATLJ_CUDA(cudaMemcpyAsync(s->r[0], r_host, b, cudaMemcpyHostToDevice, s->st));
@@ -354,7 +355,7 @@ int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_hos
 
 int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host) {
   if (!s || !s->configured || nsteps < 0) return ATLJ_ERR_ARG;
-  int rc = ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
   if (rc) return rc;
   const long long n3 = 3 * s->n;
   const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first

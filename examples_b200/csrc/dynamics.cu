@@ -1,30 +1,394 @@
-// Thermostatted / sheared integrators and the multi-GPU step phases (filled in after the NVE path).
+// Thermostatted / sheared integrators kept resident on the device.
+//
+// Reference loop bodies: bd_nvt_lj.py:91-127,221-233 (BAOAB Langevin), md_nvt_lj.py:101-159,270-288 (Nose-Hoover
+// chain), md_nvt_lj_le.py:84-129,226-240 (isokinetic SLLOD with Lees-Edwards boundaries).
+// Every elementwise statement between two force calls / global reductions is fused into one HBM pass; the global
+// sums are two-stage and fixed-order (deterministic); the handful of scalar coefficients that depend on those sums
+// (NHC chain, SLLOD c1,c2,g / alpha,beta,h,e) are computed by one-thread kernels on the device so a step never
+// waits for the host.  The elementwise arithmetic keeps NumPy's operation order (separately rounded _rn ops).
+#include <math.h>
+
 #include "common.cuh"
 #include "integrate.cuh"
 #include "sim.cuh"
 
+namespace atlj {
+
+// ---- counter-based Gaussian noise: Philox4x32-10 + Box-Muller ---------------------------------------------------
+// (replaces np.random.randn(n,3) of bd_nvt_lj.py:127; keyed by (seed), counter (atom id, step, draw) so the noise
+//  of an atom does not depend on which GPU or in which order it is processed)
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {  // uniform in (0,1), 53 bits
+  const unsigned long long x = ((unsigned long long)hi << 21) ^ (unsigned long long)(lo >> 11);
+  return ((double)(x & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void gauss3(unsigned long long seed, unsigned id, unsigned step, double g[3]) {
+  unsigned a[4], b[4];
+  philox4x32_10(id, step, 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32), a);
+  philox4x32_10(id, step, 1u, 0u, (unsigned)seed, (unsigned)(seed >> 32), b);
+  const double r0 = sqrt(-2.0 * log(u53(a[0], a[1]))), r1 = sqrt(-2.0 * log(u53(b[0], b[1])));
+  double s0, c0, s1, c1;
+  sincospi(2.0 * u53(a[2], a[3]), &s0, &c0);
+  sincospi(2.0 * u53(b[2], b[3]), &s1, &c1);
+  g[0] = r0 * c0, g[1] = r0 * s0, g[2] = r1 * c1;
+  (void)s1;
+}
+
+// ---- BAOAB: B(t) A(t) O(2t) A(t) fused, one thread per atom (bd_nvt_lj.py:223-226) ---------------------------------
+__global__ void __launch_bounds__(IT) baoab_kernel(int n, double *__restrict__ r, double *__restrict__ v,
+                                                   const double *__restrict__ f, const int *__restrict__ id, double t,
+                                                   double box, double decay, double amp,
+                                                   const double *__restrict__ noise, unsigned long long seed,
+                                                   unsigned step) {
+  for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
+    double g[3];
+    const int gid = id[i];
+    if (noise) {
+      g[0] = noise[3 * (size_t)gid], g[1] = noise[3 * (size_t)gid + 1], g[2] = noise[3 * (size_t)gid + 2];
+    } else {
+      gauss3(seed, (unsigned)gid, step, g);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const size_t e = 3 * (size_t)i + k;
+      double vv = __dadd_rn(v[e], __dmul_rn(t, f[e]));                          // b_propagator, :109
+      double x = wrap1(__dadd_rn(r[e], __ddiv_rn(__dmul_rn(t, vv), box)));      // a_propagator, :100-101
+      vv = __dadd_rn(__dmul_rn(vv, decay), __dmul_rn(amp, g[k]));               // o_propagator, :127
+      x = wrap1(__dadd_rn(x, __ddiv_rn(__dmul_rn(t, vv), box)));                // a_propagator
+      v[e] = vv;
+      r[e] = x;
+    }
+  }
+}
+
+// ---- Nose-Hoover chain scalars (md_nvt_lj.py:119-159), one thread -------------------------------------------------
+// st[0] = sum v^2 of the logical velocities, st[1] = pending velocity scale (applied by the next kick kernel),
+// st[2..2+m) = eta, st[10..10+m) = p_eta, st[18..18+m) = q.
+__device__ double exprel_neg(double x) {  // scipy.special.exprel(-x) = (1 - exp(-x)) / x
+  return fabs(x) < 1e-16 ? 1.0 : -expm1(-x) / x;
+}
+__device__ void nhc_u4(double *st, int m, double t, double temperature, double g, bool inwards) {
+  double *p_eta = st + 10;
+  const double *q = st + 18;
+  for (int jj = 0; jj < m; jj++) {
+    const int j = inwards ? m - 1 - jj : jj;
+    const double gj = j == 0 ? st[0] - g * temperature : (p_eta[j - 1] * p_eta[j - 1] / q[j - 1]) - temperature;
+    if (j == m - 1) {
+      p_eta[j] = p_eta[j] + t * gj;
+    } else {
+      const double x = t * p_eta[j + 1] / q[j + 1];
+      const double c = exprel_neg(x);
+      p_eta[j] = p_eta[j] * exp(-x) + t * gj * c;
+    }
+  }
+}
+__global__ void nhc_chain_kernel(double *st, int m, double dt, double temperature, double g, const double *ksq_in,
+                                 double *rec) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ksq_in) st[0] = *ksq_in;  // fresh sum v^2 from the kick kernel
+  nhc_u4(st, m, 0.25 * dt, temperature, g, true);
+  {  // u3 (md_nvt_lj.py:129-130): the elementwise v *= s is applied lazily by the next kernel that touches v
+    const double t = 0.5 * dt;
+    const double s = exp(-t * st[10] / st[18]);
+    for (int j = 0; j < m; j++) st[2 + j] += t * st[10 + j] / st[18 + j];
+    st[0] *= s * s;
+    st[1] *= s;
+  }
+  nhc_u4(st, m, 0.25 * dt, temperature, g, false);
+  if (rec) {
+    double ext = 0.0, es = 0.0;
+    for (int j = 0; j < m; j++) ext += 0.5 * st[10 + j] * st[10 + j] / st[18 + j];
+    for (int j = 1; j < m; j++) es += st[2 + j];
+    rec[4] = st[0];                                        // sum v^2 after the last thermostat scaling
+    rec[10] = ext + temperature * (g * st[2] + es);        // md_nvt_lj.py:44
+  }
+}
+
+// v *= *scale ; *scale = 1 afterwards (flush of the pending thermostat factor)
+__global__ void __launch_bounds__(IT) scale_v_kernel(long long n3, double *__restrict__ v, const double *scale) {
+  const double s = *scale;
+  for (long long t = (long long)blockIdx.x * IT + threadIdx.x; t < n3; t += (long long)gridDim.x * IT)
+    v[t] = __dmul_rn(v[t], s);
+}
+__global__ void set_scalar_kernel(double *p, double val) { *p = val; }
+
+// ---- SLLOD (md_nvt_lj_le.py:84-129) ------------------------------------------------------------------------------
+// coef[0] = g of b1, coef[1] = prefactor, coef[2] = dt_factor of b2 (device scalars written by the kernels below)
+__global__ void sllod_b1_coef_kernel(const double *sums /*Sxy, Syy, Svv*/, double x, double *coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double c1 = x * sums[0] / sums[2];
+  const double c2 = (x * x) * sums[1] / sums[2];
+  coef[0] = 1.0 / sqrt(1.0 - 2.0 * c1 + c2);
+}
+__global__ void sllod_b2_coef_kernel(const double *sums /*Sfv, Sff, Svv*/, double t, double *coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double alpha = sums[0] / sums[2];
+  const double beta = sqrt(sums[1] / sums[2]);
+  const double h = (alpha + beta) / (alpha - beta);
+  const double e = exp(-beta * t);
+  coef[2] = (1.0 + h - e - h / e) / ((1.0 - h) * beta);
+  coef[1] = (1.0 - h) / (e - h / e);
+}
+
+// a(t) and b1(t) on one atom; b1_first selects the order (b1 then a at the end of a step, a then b1 at its start)
+__global__ void __launch_bounds__(IT) sllod_ab1_kernel(int n, double *__restrict__ r, double *__restrict__ v, double t,
+                                                       double x, double strain_new, double box,
+                                                       const double *__restrict__ coef, int b1_first,
+                                                       double *__restrict__ partials) {
+  const double g = coef[0];
+  double s[3] = {0.0, 0.0, 0.0};  // sum vx*vy, sum vy^2, sum v^2 of the velocities left behind
+  for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
+    const size_t e = 3 * (size_t)i;
+    double vx = v[e], vy = v[e + 1], vz = v[e + 2];
+    double rx = r[e], ry = r[e + 1], rz = r[e + 2];
+    if (b1_first) {  // b1_propagator, :112-113
+      vx = __dsub_rn(vx, __dmul_rn(x, vy));
+      vx = __dmul_rn(g, vx), vy = __dmul_rn(g, vy), vz = __dmul_rn(g, vz);
+    }
+    // a_propagator, :92-98
+    rx = __dadd_rn(rx, __dmul_rn(x, ry));
+    rx = __dadd_rn(rx, __ddiv_rn(__dmul_rn(t, vx), box));
+    ry = __dadd_rn(ry, __ddiv_rn(__dmul_rn(t, vy), box));
+    rz = __dadd_rn(rz, __ddiv_rn(__dmul_rn(t, vz), box));
+    rx = __dsub_rn(rx, __dmul_rn(rint(ry), strain_new));
+    rx = wrap1(rx), ry = wrap1(ry), rz = wrap1(rz);
+    if (!b1_first) {
+      vx = __dsub_rn(vx, __dmul_rn(x, vy));
+      vx = __dmul_rn(g, vx), vy = __dmul_rn(g, vy), vz = __dmul_rn(g, vz);
+    }
+    r[e] = rx, r[e + 1] = ry, r[e + 2] = rz;
+    v[e] = vx, v[e + 1] = vy, v[e + 2] = vz;
+    s[0] += vx * vy;
+    s[1] += vy * vy;
+    s[2] += vx * vx + vy * vy + vz * vz;
+  }
+  block_reduce_store<3>(s, partials + 4 * (size_t)blockIdx.x);
+}
+
+// sums for b2: sum f.v, sum f^2, sum v^2
+__global__ void __launch_bounds__(IT) sllod_fv_sums_kernel(long long n3, const double *__restrict__ v,
+                                                           const double *__restrict__ f,
+                                                           double *__restrict__ partials) {
+  double s[3] = {0.0, 0.0, 0.0};
+  for (long long t = (long long)blockIdx.x * IT + threadIdx.x; t < n3; t += (long long)gridDim.x * IT) {
+    const double vv = v[t], ff = f[t];
+    s[0] += ff * vv;
+    s[1] += ff * ff;
+    s[2] += vv * vv;
+  }
+  block_reduce_store<3>(s, partials + 4 * (size_t)blockIdx.x);
+}
+
+// b2_propagator, :129: v = prefactor * (v + dt_factor * f); sums sum vx*vy, sum vy^2, sum v^2 of the new v
+__global__ void __launch_bounds__(IT) sllod_b2_kernel(int n, double *__restrict__ v, const double *__restrict__ f,
+                                                      const double *__restrict__ coef,
+                                                      double *__restrict__ partials) {
+  const double pre = coef[1], dtf = coef[2];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
+    const size_t e = 3 * (size_t)i;
+    const double vx = __dmul_rn(pre, __dadd_rn(v[e], __dmul_rn(dtf, f[e])));
+    const double vy = __dmul_rn(pre, __dadd_rn(v[e + 1], __dmul_rn(dtf, f[e + 1])));
+    const double vz = __dmul_rn(pre, __dadd_rn(v[e + 2], __dmul_rn(dtf, f[e + 2])));
+    v[e] = vx, v[e + 1] = vy, v[e + 2] = vz;
+    s[0] += vx * vy;
+    s[1] += vy * vy;
+    s[2] += vx * vx + vy * vy + vz * vz;
+  }
+  block_reduce_store<3>(s, partials + 4 * (size_t)blockIdx.x);
+}
+
+__global__ void sllod_rec_kernel(const double *sums_v /*Sxy,Syy,Svv*/, const double *sums_f /*Sfv,Sff,Svv*/,
+                                 double strain, double *rec) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  rec[4] = sums_v[2];
+  rec[5] = sums_f[1];
+  rec[9] = sums_v[0];
+  rec[10] = strain;
+}
+
+static int atom_blocks(int64_t n) { return integ_blocks(n); }
+
+}  // namespace atlj
+
 using namespace atlj;
 
-#define NOT_YET(name)                                   \
-  do {                                                  \
-    set_error(name ": not implemented in this build");  \
-    return ATLJ_ERR_ARG;                                \
-  } while (0)
+// scalar slots in s->scal (64 doubles)
+enum { SC_NHC = 0, SC_SUMV = 32, SC_SUMF = 36, SC_COEF = 40 };
+
+static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const double *noise_dev, uint64_t seed,
+                     int nsteps, double *rec_host) {
+  int rc;
+  const int n = (int)s->n;
+  const long long n3 = 3 * s->n;
+  const double t = dt / 2;  // bd_nvt_lj.py:223
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    Timer::begin(s, 2);
+    baoab_kernel<<<atom_blocks(n), IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], s->f, s->id[s->cur], t, s->p.box,
+                                                   decay, amp,
+                                                   noise_dev ? noise_dev + (size_t)k * 3 * (size_t)s->n_total : nullptr,
+                                                   seed, (unsigned)(s->step_count + k));
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+    if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
+    Timer::begin(s, 2);
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, t, s->partials, rec + 4))) return rc;
+    Timer::end(s);
+  }
+  s->step_count += nsteps;
+  return sim_copy_rec(s, rec_host, nsteps);
+}
 
 extern "C" {
-int atlj_sim_run_baoab(atlj_sim *, double, double, double, uint64_t, int, double *) { NOT_YET("atlj_sim_run_baoab"); }
-int atlj_sim_run_baoab_noise(atlj_sim *, double, double, double, const double *, int, double *) {
-  NOT_YET("atlj_sim_run_baoab_noise");
+
+int atlj_sim_run_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int nsteps,
+                       double *rec_host) {
+  if (!s || !s->configured || nsteps < 0) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc) return rc;
+  return baoab_run(s, dt, o_decay, o_noise, nullptr, seed, nsteps, rec_host);
 }
-int atlj_sim_run_nhc(atlj_sim *, double, double, int, double *, double *, const double *, int, double *) {
-  NOT_YET("atlj_sim_run_nhc");
+
+int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double o_decay, double o_noise, const double *noise_host,
+                             int nsteps, double *rec_host) {
+  if (!s || !s->configured || nsteps < 0 || !noise_host) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc) return rc;
+  const size_t need = (size_t)nsteps * 3 * (size_t)s->n_total;
+  if ((int64_t)need > s->noise_cap) {
+    cudaFree(s->noise_dev);
+    s->noise_dev = nullptr;
+    ATLJ_CUDA(cudaMalloc((void **)&s->noise_dev, sizeof(double) * (need ? need : 1)));
+    s->noise_cap = (int64_t)need;
+  }
+  ATLJ_CUDA(cudaMemcpyAsync(s->noise_dev, noise_host, sizeof(double) * need, cudaMemcpyHostToDevice, s->st));
+  return baoab_run(s, dt, o_decay, o_noise, s->noise_dev, 0, nsteps, rec_host);
 }
-int atlj_sim_run_sllod(atlj_sim *, double, double, double *, int, double *) { NOT_YET("atlj_sim_run_sllod"); }
-int atlj_sim_mg_drift_pack(atlj_sim *, double, double *, double *, int64_t) { NOT_YET("atlj_sim_mg_drift_pack"); }
-int atlj_sim_mg_bin_pack(atlj_sim *, const double *, const double *, int64_t, double *, double *, int64_t) {
-  NOT_YET("atlj_sim_mg_bin_pack");
+
+int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m, double *eta, double *p_eta,
+                     const double *q, int nsteps, double *rec_host) {
+  if (!s || !s->configured || nsteps < 0 || m < 1 || m > 8 || !eta || !p_eta || !q) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc) return rc;
+  const long long n3 = 3 * s->n;
+  double h[32];
+  memset(h, 0, sizeof(h));
+  h[1] = 1.0;
+  for (int j = 0; j < m; j++) h[2 + j] = eta[j], h[10 + j] = p_eta[j], h[18 + j] = q[j];
+  double *st = s->scal + SC_NHC;
+  ATLJ_CUDA(cudaMemcpyAsync(st, h, sizeof(h), cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));  // h is on the stack
+  // sum v^2 of the starting velocities -> st[0]
+  if ((rc = launch_vf_sums(s->st, n3, s->v[s->cur], s->f, s->partials, s->scal + SC_SUMV))) return rc;
+  const double *ksq = s->scal + SC_SUMV;
+  const double half_dt = 0.5 * dt;
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    Timer::begin(s, 2);
+    nhc_chain_kernel<<<1, 32, 0, s->st>>>(st, m, dt, temperature, g, k == 0 ? ksq : nullptr, nullptr);
+    ATLJ_LAUNCHED();
+    // u2(dt/2) u1(dt) with the pending thermostat factor folded in (md_nvt_lj.py:276-277)
+    if ((rc = launch_kick_drift(s->st, n3, s->r[s->cur], s->v[s->cur], s->f, half_dt, dt, s->p.box, st + 1))) return rc;
+    set_scalar_kernel<<<1, 1, 0, s->st>>>(st + 1, 1.0);
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+    if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
+    Timer::begin(s, 2);
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4))) return rc;
+    nhc_chain_kernel<<<1, 32, 0, s->st>>>(st, m, dt, temperature, g, rec + 4, rec);
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+  }
+  // apply the pending factor so that the stored velocities are the logical ones
+  scale_v_kernel<<<integ_blocks(n3), IT, 0, s->st>>>(n3, s->v[s->cur], st + 1);
+  ATLJ_LAUNCHED();
+  set_scalar_kernel<<<1, 1, 0, s->st>>>(st + 1, 1.0);
+  ATLJ_LAUNCHED();
+  ATLJ_CUDA(cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  rc = sim_copy_rec(s, rec_host, nsteps);  // synchronises
+  for (int j = 0; j < m; j++) eta[j] = h[2 + j], p_eta[j] = h[10 + j];
+  s->step_count += nsteps;
+  return rc;
 }
-int atlj_sim_mg_force_kick(atlj_sim *, const double *, const double *, int64_t, double, double *) {
-  NOT_YET("atlj_sim_mg_force_kick");
+
+int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strain, int nsteps, double *rec_host) {
+  if (!s || !s->configured || nsteps < 0 || !strain) return ATLJ_ERR_ARG;
+  if (s->p.model != ATLJ_MODEL_WCA) {
+    set_error("SLLOD needs the WCA / Lees-Edwards model (md_nvt_lj_le.py imports md_lj_le_module)");
+    return ATLJ_ERR_ARG;
+  }
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc) return rc;
+  const int n = (int)s->n;
+  const long long n3 = 3 * s->n;
+  const int nb = atom_blocks(n), nb3 = integ_blocks(n3);
+  double *sumv = s->scal + SC_SUMV, *sumf = s->scal + SC_SUMF, *coef = s->scal + SC_COEF;
+  const double t = dt / 2;              // md_nvt_lj_le.py:230
+  const double x = t * strain_rate;     // :89,105
+  double st = *strain;
+  auto advance = [&]() {                // :94-95
+    st = st + x;
+    st = st - rint(st);
+  };
+  // sums of the starting velocities for the first b1
+  {
+    double zero_coef[4] = {1.0, 1.0, 0.0, 0.0};
+    ATLJ_CUDA(cudaMemcpyAsync(coef, zero_coef, sizeof(zero_coef), cudaMemcpyHostToDevice, s->st));
+    ATLJ_CUDA(cudaStreamSynchronize(s->st));
+    // plain reduction of vx*vy, vy^2, v^2 without touching anything: b2 kernel with pre = 1, dtf = 0
+    sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, coef, s->partials);
+    ATLJ_LAUNCHED();
+    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
+  }
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    Timer::begin(s, 2);
+    // a(dt/2) then b1(dt/2)
+    sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
+    ATLJ_LAUNCHED();
+    advance();
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, s->p.box, coef, 0, s->partials);
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+    if ((rc = sim_force(s, st, false, rec, false))) return rc;
+    Timer::begin(s, 2);
+    // b2(dt)
+    sllod_fv_sums_kernel<<<nb3, IT, 0, s->st>>>(n3, s->v[s->cur], s->f, s->partials);
+    ATLJ_LAUNCHED();
+    if ((rc = launch_sums_final(s->st, s->partials, nb3, 3, sumf))) return rc;
+    sllod_b2_coef_kernel<<<1, 32, 0, s->st>>>(sumf, dt, coef);
+    ATLJ_LAUNCHED();
+    sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, coef, s->partials);
+    ATLJ_LAUNCHED();
+    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
+    // b1(dt/2) then a(dt/2)
+    sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
+    ATLJ_LAUNCHED();
+    advance();
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, s->p.box, coef, 1, s->partials);
+    ATLJ_LAUNCHED();
+    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
+    sllod_rec_kernel<<<1, 32, 0, s->st>>>(sumv, sumf, st, rec);
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+  }
+  *strain = st;
+  s->step_count += nsteps;
+  return sim_copy_rec(s, rec_host, nsteps);
 }
-}
+
+}  // extern "C"

@@ -12,32 +12,6 @@
 
 namespace atlj {
 
-constexpr int IT = 256;
-
-__device__ __forceinline__ double wrap1(double x) { return __dsub_rn(x, rint(x)); }
-
-// CTA reduction of K values, result row written by thread 0
-template <int K>
-__device__ __forceinline__ void block_reduce_store(double (&v)[K], double *__restrict__ row) {
-  __shared__ double red[IT / 32][K];
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < K; k++) red[warp][k] = v[k];
-  }
-  __syncthreads();
-  if (threadIdx.x < K) {
-    double s = 0.0;
-    for (int w = 0; w < IT / 32; w++) s += red[w][threadIdx.x];
-    row[threadIdx.x] = s;
-  }
-}
-
 // ---- velocity Verlet ---------------------------------------------------------------------------------------------
 // md_nve_lj.py:182-185: v = v + 0.5*dt*f ; r = r + dt*v/box ; r = r - rint(r)     (reads r,v,f, writes r,v)
 // vscale (device scalar, may be null) multiplies v first: pending Nose-Hoover U3 factor (md_nvt_lj.py:129).
@@ -89,6 +63,12 @@ __global__ void __launch_bounds__(256) sums_final_kernel(const double *__restric
     __syncthreads();
   }
   if (threadIdx.x < K) out[threadIdx.x] = sm[0][threadIdx.x];
+}
+
+int launch_sums_final(cudaStream_t st, const double *partials, int nblocks, int K, double *out) {
+  sums_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, K, out);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
 }
 
 int integ_blocks(long long n3) {

@@ -4,6 +4,35 @@
 
 namespace atlj {
 
+constexpr int IT = 256;
+
+__device__ __forceinline__ double wrap1(double x) { return __dsub_rn(x, rint(x)); }
+
+// CTA reduction of K values, result row written by thread 0
+template <int K>
+__device__ __forceinline__ void block_reduce_store(double (&v)[K], double *__restrict__ row) {
+  __shared__ double red[IT / 32][K];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) red[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double s = 0.0;
+    for (int w = 0; w < IT / 32; w++) s += red[w][threadIdx.x];
+    row[threadIdx.x] = s;
+  }
+}
+
+
+int launch_sums_final(cudaStream_t st, const double *partials, int nblocks, int K, double *out);  // K <= 4
+
 int integ_blocks(long long n3);
 int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const double *f, double half_dt, double dt,
                       double box, const double *vscale);

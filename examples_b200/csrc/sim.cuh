@@ -8,6 +8,8 @@ struct atlj_sim {
   cudaStream_t st = nullptr;
   int64_t cap = 0;  // atom capacity of every per-atom buffer
   int64_t n = 0;    // owned atoms
+  int64_t n_total = 0;       // atoms of the whole system (all ranks); indexes injected noise by global id
+  long long step_count = 0;  // steps taken so far (counter of the device RNG)
   bool configured = false;
   bool use_cells = false;  // sc >= 4: link-cell route; otherwise all pairs
   atlj::Geom g{};
@@ -49,4 +51,5 @@ struct Timer {
 int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs);
 int sim_check_flags(atlj_sim *s);
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
+int sim_ensure_rec(atlj_sim *s, int64_t nrec);
 }  // namespace atlj

@@ -102,25 +102,39 @@ class Simulation:
         _lib.check(_lib.lib().atlj_sim_run_nve(self._h, float(dt), int(nsteps), int(hessian), _ptr(rec)))
         return rec
 
+    @staticmethod
+    def _o_scalars(dt, gamma, temperature):
+        # the two scalars of o_propagator, with the reference's own expressions (bd_nvt_lj.py:124-127)
+        x = gamma * dt
+        c = -np.expm1(-2 * x)
+        c = np.sqrt(c)
+        return float(np.exp(-x)), float(c * np.sqrt(temperature))
+
     def run_baoab(self, dt, gamma, temperature, nsteps, seed=1, noise=None):
+        """BAOAB Langevin steps (bd_nvt_lj.py:221-233).  noise=None uses the device Philox generator; an array
+        (nsteps, n, 3) indexed by original atom number replaces np.random.randn of bd_nvt_lj.py:127 (tests)."""
         rec = np.zeros((nsteps, NREC))
+        decay, amp = self._o_scalars(dt, gamma, temperature)
         if noise is None:
-            _lib.check(_lib.lib().atlj_sim_run_baoab(self._h, float(dt), float(gamma), float(temperature), int(seed),
-                                                     int(nsteps), _ptr(rec)))
+            _lib.check(_lib.lib().atlj_sim_run_baoab(self._h, float(dt), decay, amp, int(seed), int(nsteps),
+                                                     _ptr(rec)))
         else:
             noise = _lib.as_f64(noise)
             assert noise.shape == (nsteps, self.n_total, 3)
-            _lib.check(_lib.lib().atlj_sim_run_baoab_noise(self._h, float(dt), float(gamma), float(temperature),
-                                                           _ptr(noise), int(nsteps), _ptr(rec)))
+            _lib.check(_lib.lib().atlj_sim_run_baoab_noise(self._h, float(dt), decay, amp, _ptr(noise), int(nsteps),
+                                                           _ptr(rec)))
         return rec
 
-    def run_nhc(self, dt, temperature, eta, p_eta, q, nsteps):
-        """eta, p_eta (updated in place) and q are the length-m chain arrays of md_nvt_lj.py:245-257."""
+    def run_nhc(self, dt, temperature, eta, p_eta, q, nsteps, g=None):
+        """Nose-Hoover chain steps (md_nvt_lj.py:270-288).  eta, p_eta (updated in place) and q are the length-m
+        chain arrays of md_nvt_lj.py:245-257; g = 3*(n-1) as in md_nvt_lj.py:244 unless given."""
         rec = np.zeros((nsteps, NREC))
         for a in (eta, p_eta, q):
             assert a.dtype == np.float64 and a.flags.c_contiguous
-        _lib.check(_lib.lib().atlj_sim_run_nhc(self._h, float(dt), float(temperature), len(q), _ptr(eta), _ptr(p_eta),
-                                               _ptr(q), int(nsteps), _ptr(rec)))
+        if g is None:
+            g = 3 * (self.n_total - 1)
+        _lib.check(_lib.lib().atlj_sim_run_nhc(self._h, float(dt), float(temperature), float(g), len(q), _ptr(eta),
+                                               _ptr(p_eta), _ptr(q), int(nsteps), _ptr(rec)))
         return rec
 
     def run_sllod(self, dt, strain_rate, strain, nsteps):

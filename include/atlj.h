@@ -120,32 +120,24 @@ int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_hos
 
 /* nsteps velocity-Verlet steps (md_nve_lj.py:178-192); rec_host (nsteps, ATLJ_NREC) or NULL. */
 int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host);
-/* BAOAB Langevin steps (bd_nvt_lj.py:91-127,221-233) with a counter-based device Gaussian RNG. */
-int atlj_sim_run_baoab(atlj_sim *s, double dt, double gamma, double temperature, uint64_t seed, int nsteps,
+/* BAOAB Langevin steps (bd_nvt_lj.py:91-127,221-233) with a counter-based device Gaussian RNG (Philox4x32-10 keyed
+ * by seed, counter = (global atom id, step)).  o_decay = exp(-gamma*dt) and o_noise = sqrt(1-exp(-2*gamma*dt)) *
+ * sqrt(temperature) are the two scalars of o_propagator (bd_nvt_lj.py:124-127), evaluated by the caller with the
+ * reference's expressions. */
+int atlj_sim_run_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int nsteps,
                        double *rec_host);
-/* Nose-Hoover chain steps (md_nvt_lj.py:101-159,270-288), chain length m <= 8; eta, p_eta, q host in/out. */
-int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, int m, double *eta, double *p_eta, const double *q,
-                     int nsteps, double *rec_host);
+/* Nose-Hoover chain steps (md_nvt_lj.py:101-159,270-288), chain length m <= 8, g = degrees of freedom
+ * (md_nvt_lj.py:244); eta, p_eta host in/out, q host in.  rec[10] = the thermostat part of the conserved energy
+ * (md_nvt_lj.py:44). */
+int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m, double *eta, double *p_eta,
+                     const double *q, int nsteps, double *rec_host);
 /* Isokinetic SLLOD steps (md_nvt_lj_le.py:84-129,226-240); *strain host in/out. */
 int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strain, int nsteps, double *rec_host);
 
 /* BAOAB with an injected noise array (nsteps, n, 3) indexed by GLOBAL atom id -- deterministic parity
  * tests against bd_nvt_lj.py:127 with the same numbers. */
-int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double gamma, double temperature, const double *noise_host,
+int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double o_decay, double o_noise, const double *noise_host,
                              int nsteps, double *rec_host);
-
-/* ---- phases of one multi-GPU NVE step (the exchange between them is done by the caller with
- * NCCL send/recv on the same stream; see examples_b200/slab.py) ------------------------------ */
-/* kick(dt/2) + drift(dt) + wrap, then split owned atoms into stay / go-left / go-right.  Leavers are packed
- * into the two send buffers: [0] = count, then per atom 7 doubles (r, v, id). */
-int atlj_sim_mg_drift_pack(atlj_sim *s, double dt, double *send_left_dev, double *send_right_dev, int64_t cap);
-/* append arrivals from the two receive buffers, bin + sort owned atoms, pack the boundary layers:
- * halo send buffers: [0] = count, [1..sc*sc] = per-cell counts, then 3 doubles per atom. */
-int atlj_sim_mg_bin_pack(atlj_sim *s, const double *recv_left_dev, const double *recv_right_dev, int64_t cap,
-                         double *halo_left_dev, double *halo_right_dev, int64_t halo_cap);
-/* unpack halos, pair kernel, kick(dt/2), local partial sums -> rec_dev[ATLJ_NREC] (device; caller all-reduces). */
-int atlj_sim_mg_force_kick(atlj_sim *s, const double *halo_from_left_dev, const double *halo_from_right_dev,
-                           int64_t halo_cap, double dt, double *rec_dev);
 
 /* ---- host-buffer step (the end-to-end path of bench.py) --------------------------------------
  * One velocity-Verlet step (md_nve_lj.py:178-192) whose state lives in HOST memory, as it does in the

@@ -42,3 +42,9 @@ def liquid_like(nc, density=0.75, sigma=0.05, seed=1):
     rng = np.random.default_rng(seed)
     r = r + rng.normal(0.0, sigma / box, size=r.shape)
     return n, box, np.ascontiguousarray(r - np.rint(r))
+
+
+@pytest.fixture(scope="session")
+def golden_dyn():
+    """Trajectories produced by executing the reference drivers' own propagators (oracle/make_golden_dynamics.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_dynamics.npz"))
