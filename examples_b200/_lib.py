@@ -69,6 +69,20 @@ def lib():
     L.atlj_sim_run_baoab_noise.argtypes = [_vp, C.c_double, C.c_double, C.c_double, _vp, C.c_int, _vp]
     L.atlj_sim_run_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
     L.atlj_sim_run_sllod.argtypes = [_vp, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, _vp]
+    L.atlj_sim_mg_enable.argtypes = [_vp, C.c_int64, C.c_int64]
+    L.atlj_sim_set_total.restype = None
+    L.atlj_sim_set_total.argtypes = [_vp, C.c_int64]
+    L.atlj_nccl_unique_id.argtypes = [C.c_char_p]
+    L.atlj_sim_mg_connect.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
+    L.atlj_sim_run_nve_mg.argtypes = [_vp, C.c_double, C.c_int, _vp]
+    L.atlj_sim_mg_phase1.argtypes = [_vp, C.c_double]
+    L.atlj_sim_mg_phase2.argtypes = [_vp]
+    L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]
+    L.atlj_sim_mg_buffer.restype = _vp
+    L.atlj_sim_mg_buffer.argtypes = [_vp, C.c_int]
+    L.atlj_sim_mg_buffer_bytes.restype = C.c_int64
+    L.atlj_sim_mg_buffer_bytes.argtypes = [_vp, C.c_int]
+    L.atlj_device_copy.argtypes = [_vp, _vp, C.c_int64]
     L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
     L.atlj_host_alloc.restype = _vp
     L.atlj_host_alloc.argtypes = [C.c_int64]

@@ -69,9 +69,10 @@ static int ensure_cells(atlj_sim *s, int ncell) {
   s->cb.cell_count = s->cb.cell_start = nullptr;
   int rc;
   if ((rc = dev_alloc(&s->cb.cell_count, (size_t)ncell))) return rc;
-  if ((rc = dev_alloc(&s->cb.cell_start, (size_t)ncell + 1))) return rc;
+  // padded table: one end sentinel per x layer (Geom::cs_idx); sized for the worst padding (sc = 1)
+  if ((rc = dev_alloc(&s->cb.cell_start, 2 * (size_t)ncell + 2))) return rc;
   ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)ncell, s->st));
-  ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_start, 0, sizeof(int) * ((size_t)ncell + 1), s->st));
+  ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_start, 0, sizeof(int) * (2 * (size_t)ncell + 2), s->st));
   s->ncell_alloc = ncell;
   return ATLJ_OK;
 }
@@ -131,7 +132,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     if (s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ)
       nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
     else
-      nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, false, n) : launch_pair_tile(s->st, a, false);
+      nb = launch_pair_tile(s->st, a, false);
     Timer::end(s);
     if (nb < 0) return nb;
     if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2))) return rc;
@@ -139,7 +140,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       a.fin = s->f;
       a.f = nullptr;
       Timer::begin(s, 3);
-      nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
+      nb = launch_pair_tile(s->st, a, true);
       Timer::end(s);
       if (nb < 0) return nb;
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
@@ -222,9 +223,9 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   }
   atlj_sim *s = new atlj_sim();
   s->st = (cudaStream_t)stream;
-  // A/B runs: "tile1" = first tiled kernel for every model, "warp" = first-generation warp-per-atom kernel
+  // A/B runs: ATLJ_PAIR_KERNEL=tile1 routes LJ forces through the first tiled kernel as well
   const char *op = getenv("ATLJ_PAIR_KERNEL");
-  s->pair_kernel = !op ? 0 : (strcmp(op, "warp") == 0 ? 2 : (strcmp(op, "tile1") == 0 ? 1 : 0));
+  s->pair_kernel = (op && strcmp(op, "tile1") == 0) ? 1 : 0;
   s->cap = capacity;
   size_t c = (size_t)capacity;
   bool ok = true;
@@ -251,6 +252,7 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
 void atlj_sim_destroy(atlj_sim *s) {
   if (!s) return;
   cudaStreamSynchronize(s->st);
+  sim_mg_destroy(s);
   for (int k = 0; k < 2; k++) cudaFree(s->r[k]), cudaFree(s->v[k]), cudaFree(s->id[k]);
   cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
@@ -556,7 +558,7 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.partials = s->partials;
     a.g = s->g;
     a.p = p;
-    nb = s->pair_kernel == 2 ? launch_pair_cells(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true);
+    nb = launch_pair_tile(s->st, a, true);
     if (nb < 0) return nb;
   } else {
     if (check_index)
@@ -596,9 +598,14 @@ int atlj_cells(const double *r_host, int64_t n, int sc, int le, double strain, i
       e = cudaMemcpyAsync(c_host, c_dev, sizeof(long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->st);
     if (e == cudaSuccess && perm_host)
       e = cudaMemcpyAsync(perm_host, s->id[alt], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st);
-    if (e == cudaSuccess && cell_start_host)
-      e = cudaMemcpyAsync(cell_start_host, s->cb.cell_start, sizeof(int) * ((size_t)s->g.ncell() + 1),
-                          cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess && cell_start_host) {  // drop the per-layer sentinels: plain CSR of sc^3 + 1 entries
+      const size_t sc2 = (size_t)sc * sc;
+      e = cudaMemcpy2DAsync(cell_start_host, sizeof(int) * sc2, s->cb.cell_start, sizeof(int) * (sc2 + 1),
+                            sizeof(int) * sc2, (size_t)sc, cudaMemcpyDeviceToHost, s->st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cell_start_host + sc2 * sc, s->cb.cell_start + s->g.cs_size() - 1, sizeof(int),
+                            cudaMemcpyDeviceToHost, s->st);
+    }
     if (e != cudaSuccess) {
       set_error("atlj_cells copy: %s", cudaGetErrorString(e));
       rc = ATLJ_ERR_CUDA;

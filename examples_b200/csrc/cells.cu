@@ -23,8 +23,10 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *
                                                           double *__restrict__ r_wr, int n, int le, double strain,
                                                           int *__restrict__ cellid, int *__restrict__ rank,
                                                           int *__restrict__ cell_count, int *__restrict__ err,
-                                                          long long *__restrict__ c_out) {
+                                                          long long *__restrict__ c_out,
+                                                          const int *__restrict__ n_dev, int drop_adjacent) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   double x = r_in[3 * i], y = r_in[3 * i + 1], z = r_in[3 * i + 2];
   if (le) x = __dsub_rn(x, __dmul_rn(rint(y), strain));  // md_lj_llle_module.py:94
@@ -47,7 +49,15 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *
   }
   bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc;  // md_lj_ll_module.py:109
   int lx = (int)c0 - g.x_lo + g.h;
-  if (!bad && (lx < g.h || lx >= g.h + g.nx_own)) bad = true;  // not an owned layer (caller migrates first)
+  if (!bad && (lx < g.h || lx >= g.h + g.nx_own)) {  // not an owned layer
+    const int left = g.x_lo == 0 ? g.sc - 1 : g.x_lo - 1, right = g.x_lo + g.nx_own == g.sc ? 0 : g.x_lo + g.nx_own;
+    if (drop_adjacent && ((int)c0 == left || (int)c0 == right)) {  // packed for migration by migrate_pack_kernel
+      cellid[i] = -1;
+      rank[i] = 0;
+      return;
+    }
+    bad = true;
+  }
   if (bad) {
     atomicOr(&err[0], 1);
     cellid[i] = -1;
@@ -60,11 +70,11 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *
 }
 
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
-                       double strain, const CellBufs &b, long long *c_out) {
+                       double strain, const CellBufs &b, long long *c_out, const int *n_dev, bool drop_adjacent) {
   ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   if (n > 0) {
     cell_assign_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, r_in, r_wrapped, n, le ? 1 : 0, strain, b.cellid, b.rank,
-                                                         b.cell_count, b.err, c_out);
+                                                         b.cell_count, b.err, c_out, n_dev, drop_adjacent ? 1 : 0);
     ATLJ_LAUNCHED();
   }
   return ATLJ_OK;
@@ -135,9 +145,10 @@ __global__ void __launch_bounds__(SCAN_T) scan_tile_offsets_kernel(int *__restri
 }
 
 // phase C: final exclusive scan, cell_start[first + c] = base + prefix; also writes the end sentinel
+// start is the padded table of the whole local grid (Geom::cs_idx); k-th owned cell sits in layer h + k / sc2
 __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restrict__ cnt, int n,
                                                             const int *__restrict__ tile_off, int base_off,
-                                                            int *__restrict__ start) {
+                                                            int *__restrict__ start, int sc2, int h) {
   __shared__ int sm[SCAN_T / 32];
   __shared__ int total;
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
@@ -151,9 +162,14 @@ __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restric
   int off = block_exclusive_scan(s, sm, &total) + tile_off[blockIdx.x] + base_off;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < n) start[base + k] = off;
+    const int c = base + k;
+    if (c < n) {
+      const int layer = c / sc2, w = c - layer * sc2;
+      const int idx = (h + layer) * (sc2 + 1) + w;
+      start[idx] = off;
+      if (w == sc2 - 1) start[idx + 1] = off + v[k];  // end sentinel of this layer
+    }
     off += v[k];
-    if (base + k == n - 1) start[n] = off;
   }
 }
 
@@ -169,23 +185,26 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
   ATLJ_LAUNCHED();
   scan_tile_offsets_kernel<<<1, SCAN_T, 0, st>>>(b.block_sums, ntiles);
   ATLJ_LAUNCHED();
-  scan_final_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums, base, b.cell_start + first);
+  scan_final_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums, base, b.cell_start, g.sc * g.sc,
+                                               g.h);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }
 
 // ---- 3. scatter keys into their cells ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cell_scatter_kernel(int n, int base, const int *__restrict__ cellid,
+__global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
+                                                           const int *__restrict__ cellid,
                                                            const int *__restrict__ rank,
                                                            const int *__restrict__ cell_start,
                                                            const int *__restrict__ id_in,
                                                            unsigned long long *__restrict__ keys) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int cid = cellid[i];
   if (cid < 0) return;
   unsigned id = id_in ? (unsigned)id_in[i] : (unsigned)i;
-  int slot = cell_start[cid] - base + rank[i];
+  int slot = cell_start[g.cs_idx(cid)] - base + rank[i];
   keys[slot] = ((unsigned long long)id << 32) | (unsigned)i;
 }
 
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const 
   c += g.first_own_cell();
   int n = cell_count[c];
   if (n < 2) return;
-  unsigned long long *k = keys + (cell_start[c] - base);
+  unsigned long long *k = keys + (cell_start[g.cs_idx(c)] - base);
   if (n <= 32) {  // insertion sort; keys arrive nearly ordered when the atoms were in cell order already
     for (int a = 1; a < n; a++) {
       unsigned long long x = k[a];
@@ -245,11 +264,13 @@ __global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const 
 // ---- 5. gather into cell order ---------------------------------------------------------------------------------
 // One thread per (atom, component) so that the writes are perfectly coalesced; the reads hit 24-byte records
 // whose three components are fetched by neighbouring threads.
-__global__ void __launch_bounds__(256) cell_gather_kernel(int n, const unsigned long long *__restrict__ keys,
+__global__ void __launch_bounds__(256) cell_gather_kernel(int n, const int *__restrict__ n_dev,
+                                                          const unsigned long long *__restrict__ keys,
                                                           const double *__restrict__ r_in,
                                                           const double *__restrict__ v_in, double *__restrict__ r_out,
                                                           double *__restrict__ v_out, int *__restrict__ id_out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (t >= 3 * n) return;
   int s = t / 3, k = t - 3 * s;
   unsigned long long key = keys[s];
@@ -259,15 +280,20 @@ __global__ void __launch_bounds__(256) cell_gather_kernel(int n, const unsigned 
   if (k == 0 && id_out) id_out[s] = (int)(key >> 32);
 }
 
+// n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); after the sort the
+// number of atoms kept is the end sentinel of the last owned layer, which the gather reads from the device as well
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
-                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out) {
+                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
+                            const int *n_dev) {
   if (n <= 0) return ATLJ_OK;
-  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, base, b.cellid, b.rank, b.cell_start, id_in, b.keys);
+  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in,
+                                                       b.keys);
   ATLJ_LAUNCHED();
   int nc = g.n_own_cells();
   cell_sort_kernel<<<(nc + 127) / 128, 128, 0, st>>>(g, base, b.cell_start, b.cell_count, b.keys);
   ATLJ_LAUNCHED();
-  cell_gather_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, b.keys, r_in, v_in, r_out, v_out, id_out);
+  const int *n_kept = n_dev ? b.cell_start + g.cs_idx((g.h + g.nx_own) * g.sc * g.sc - 1) + 1 : nullptr;
+  cell_gather_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, n_kept, b.keys, r_in, v_in, r_out, v_out, id_out);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -42,6 +42,11 @@ struct Geom {
   int h;       // halo layers on each side (0 or 1)
   int nxl;     // nx_own + 2h
   __host__ __device__ int ncell() const { return nxl * sc * sc; }
+  // cell_start carries one end sentinel PER x LAYER: entry of cell c is cs_idx(c) = c + c / sc^2.  Layers can then
+  // sit anywhere in the sorted arrays ([owned | left halo | right halo] on a slab) and a z row never reads past its
+  // own layer.
+  __host__ __device__ int cs_size() const { return nxl * (sc * sc + 1); }
+  __host__ __device__ int cs_idx(int cell) const { return cell + cell / (sc * sc); }
   __host__ __device__ int n_own_cells() const { return nx_own * sc * sc; }
   __host__ __device__ int first_own_cell() const { return h * sc * sc; }
 };
@@ -125,13 +130,17 @@ struct CellBufs {
 };
 
 // wrap + cell assignment + per-cell counts (+ optional int64 triplets out)
+// n_dev (may be null): device-side atom count, n is then only an upper bound; drop_adjacent: atoms that sit one layer
+// outside the slab are skipped silently (they were packed for migration) instead of raising the index error
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
-                       double strain, const CellBufs &b, long long *c_out);
+                       double strain, const CellBufs &b, long long *c_out, const int *n_dev = nullptr,
+                       bool drop_adjacent = false);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
-                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out);
+                            const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
+                            const int *n_dev = nullptr);
 
 struct PairArgs {
   const double *r;       // sorted positions (owned + halo), AoS
@@ -143,8 +152,7 @@ struct PairArgs {
   Geom g;
   Phys p;
 };
-int pair_grid_blocks();  // blocks of the persistent pair kernel (partials has this many rows)
-int launch_pair_cells(cudaStream_t st, const PairArgs &a, bool hessian, int natoms_hint);
+int pair_grid_blocks();  // upper bound of the all-pairs kernel's CTAs (partials has at least this many rows)
 int pair_tile_grid(const Geom &g);  // CTAs of the tiled kernel (rows of partials it writes)
 int launch_pair_tile(cudaStream_t st, const PairArgs &a, bool hessian);  // -> CTAs launched or a negative status
 int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the second-generation LJ kernel

@@ -7,195 +7,17 @@
 // contraction), rint = round-half-even, IEEE reciprocal.  Everything downstream of the predicates is ordinary
 // fp64 and agrees with NumPy to summation-order rounding.
 //
-// Design (not the reference's): FULL stencil, every atom gathers its own force, so no atomics and a
-// deterministic result; the double-counted totals are halved exactly like the reference's own same-cell blocks
-// (md_lj_ll_module.py:156-159).  One CTA per i-cell, PW warps.  The candidates of the 27 (LE: up to 30) neighbour
-// cells are staged once per cell into shared memory: fp64 coordinates for the exact arithmetic plus an fp32
-// copy relative to the cell centre (cell units).  For each i atom one warp sweeps the candidates 32 at a time
-// with a cheap fp32 distance prefilter (7 FP32 ops / candidate instead of 15 FP64), compacts the survivors into
-// a ring buffer with ballot/popc, and evaluates them 32 at a time with every lane busy in fp64.  The prefilter
-// threshold carries a 1e-4 relative margin (fp32 error bound ~1.5e-6), so it never rejects a pair the
-// exact fp64 test accepts; the exact test then decides.  Per-atom forces are finished with a warp-shuffle
-// reduction, totals accumulate per lane in fp64 and are reduced per CTA, then by launch_finalize in fixed order.
+// This file holds the all-pairs kernel (small systems, sc < 4: the reference's N = 256 case) and the fixed-order
+// final reduction; the link-cell kernels are pair_tile.cu (WCA / Lees-Edwards, hessian) and pair_tile2.cu (LJ).
+// FULL stencil everywhere: every atom gathers its own force, so no atomics and a deterministic result; the
+// double-counted totals are halved exactly like the reference's own same-cell blocks (md_lj_ll_module.py:156-159).
 #include "common.cuh"
 #include "pair_math.cuh"
 
 namespace atlj {
 
-constexpr int PW = 4;      // warps per CTA
-constexpr int CAP = 512;   // staged candidates per chunk (27 cells x ~12-15 atoms fits; larger sets loop)
 
 int pair_grid_blocks() { return 148 * 16; }
-
-// ---- link-cell kernel --------------------------------------------------------------------------------------------
-template <int MODEL, bool HESS>
-__global__ void __launch_bounds__(32 * PW) pair_cells_kernel(PairArgs a) {
-  constexpr bool LE = (MODEL == ATLJ_MODEL_WCA);
-  __shared__ double xs[CAP], ys[CAP], zs[CAP];
-  __shared__ float4 qs[CAP];
-  __shared__ double gxs[HESS ? CAP : 1], gys[HESS ? CAP : 1], gzs[HESS ? CAP : 1];
-  __shared__ int nb_start[32];
-  __shared__ int nb_off[33];
-  __shared__ int queue[PW][64];
-
-  const Geom g = a.g;
-  const Phys p = a.p;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int sc = g.sc;
-  const double scd = (double)sc;
-  const double sci = 1.0 / scd;
-  const int n_own = g.n_own_cells();
-  const int first = g.first_own_cell();
-  int *q = queue[warp];
-
-  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0ull, 0};
-
-  for (int oc = blockIdx.x; oc < n_own; oc += gridDim.x) {
-    const int cell = first + oc;
-    const int ni = a.cell_count[cell];
-    if (ni == 0) continue;  // uniform over the CTA
-    const int istart = a.cell_start[cell];
-    const int lx = cell / (sc * sc), cy = (cell / sc) % sc, cz = cell % sc;
-
-    __syncthreads();  // the previous cell's consumers are done with shared memory
-    if (warp == 0) {
-      int nc = lane < MAX_NB ? neighbour_cell(g, LE, p.shift, lx, cy, cz, lane) : -1;
-      int cnt = nc >= 0 ? a.cell_count[nc] : 0;
-      int st = nc >= 0 ? a.cell_start[nc] : 0;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
-      }
-      nb_start[lane] = st;
-      nb_off[lane] = incl - cnt;
-      if (lane == 31) nb_off[32] = incl;
-    }
-    __syncthreads();
-    const int M = nb_off[32];
-
-    // centre of the i-cell in box units (approximate geometry only: used for the fp32 prefilter copy)
-    const double ctrx = ((lx - g.h + g.x_lo) + 0.5) * sci - 0.5;
-    const double ctry = (cy + 0.5) * sci - 0.5;
-    const double ctrz = (cz + 0.5) * sci - 0.5;
-
-    for (int c0 = 0; c0 < M; c0 += CAP) {
-      const int mc = min(CAP, M - c0);
-      if (c0 > 0) __syncthreads();
-      // ---- stage candidates c0 .. c0+mc
-      for (int s = threadIdx.x; s < mc; s += 32 * PW) {
-        int gi = c0 + s;
-        int k = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (nb_off[k + step] <= gi) k += step;
-        int j = nb_start[k] + (gi - nb_off[k]);
-        double x = a.r[3 * (size_t)j], y = a.r[3 * (size_t)j + 1], z = a.r[3 * (size_t)j + 2];
-        xs[s] = x;
-        ys[s] = y;
-        zs[s] = z;
-        double ux = x - ctrx, uy = y - ctry, uz = z - ctrz;  // nearest image of j relative to the cell centre
-        if (LE) ux -= rint(uy) * p.strain;
-        ux -= rint(ux);
-        uy -= rint(uy);
-        uz -= rint(uz);
-        qs[s] = make_float4((float)(ux * scd), (float)(uy * scd), (float)(uz * scd), __int_as_float(j));
-        if (HESS) {
-          gxs[s] = a.fin[3 * (size_t)j];
-          gys[s] = a.fin[3 * (size_t)j + 1];
-          gzs[s] = a.fin[3 * (size_t)j + 2];
-        }
-      }
-      __syncthreads();
-
-      // ---- each warp takes i atoms of the cell in turn
-      for (int ii = warp; ii < ni; ii += PW) {
-        const int i = istart + ii;
-        const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
-        const float qix = (float)((rix - ctrx) * scd), qiy = (float)((riy - ctry) * scd),
-                    qiz = (float)((riz - ctrz) * scd);
-        double fix = 0.0, fiy = 0.0, fiz = 0.0;
-        if (HESS) {
-          fix = a.fin[3 * (size_t)i];
-          fiy = a.fin[3 * (size_t)i + 1];
-          fiz = a.fin[3 * (size_t)i + 2];
-        }
-        double fx = 0.0, fy = 0.0, fz = 0.0;
-        int qhead = 0, qn = 0;
-
-        auto dense = [&](int sj, bool act) {
-          double dx, dy, dz, s;
-          bool in = pair_sep<LE>(rix, riy, riz, xs[sj], ys[sj], zs[sj], p.strain, p.r_cut_box_sq, dx, dy, dz, s);
-          if (act && in) {
-            if (HESS)
-              pair_hess_term(p, dx, dy, dz, s, fix - gxs[sj], fiy - gys[sj], fiz - gzs[sj], acc);
-            else
-              pair_force_term<MODEL>(p, dx, dy, dz, s, fx, fy, fz, acc);
-          }
-        };
-
-        for (int b = 0; b < mc; b += 32) {
-          const int s = b + lane;
-          bool pass = false;
-          if (s < mc) {
-            float4 c = qs[s];
-            float ddx = qix - c.x, ddy = qiy - c.y, ddz = qiz - c.z;
-            float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            pass = (d2 < p.rc2_cell) && (__float_as_int(c.w) != i);
-          }
-          const unsigned m = __ballot_sync(FULL, pass);
-          if (pass) q[(qhead + qn + __popc(m & lt_mask)) & 63] = s;
-          qn += __popc(m);
-          if (qn >= 32) {
-            __syncwarp();
-            dense(q[(qhead + lane) & 63], true);
-            qhead = (qhead + 32) & 63;
-            qn -= 32;
-          }
-        }
-        if (qn > 0) {
-          __syncwarp();
-          const bool act = lane < qn;
-          dense(act ? q[(qhead + lane) & 63] : 0, act);
-        }
-        __syncwarp();
-        if (!HESS) {
-          fx = warp_sum(fx);
-          fy = warp_sum(fy);
-          fz = warp_sum(fz);
-          if (lane < 3) {
-            double v = 24.0 * (lane == 0 ? fx : (lane == 1 ? fy : fz));  // md_lj_module.py:143
-            double *dst = a.f + 3 * (size_t)i + lane;
-            *dst = (c0 == 0) ? v : *dst + v;
-          }
-        }
-      }
-    }
-  }
-  block_store_partials<PW>(acc, a.partials + 8 * (size_t)blockIdx.x);
-}
-
-int launch_pair_cells(cudaStream_t st, const PairArgs &a, bool hessian, int natoms_hint) {
-  (void)natoms_hint;
-  int blocks = a.g.n_own_cells() < pair_grid_blocks() ? a.g.n_own_cells() : pair_grid_blocks();
-  if (blocks < 1) blocks = 1;
-  if (a.p.model == ATLJ_MODEL_LJ) {
-    if (hessian)
-      pair_cells_kernel<ATLJ_MODEL_LJ, true><<<blocks, 32 * PW, 0, st>>>(a);
-    else
-      pair_cells_kernel<ATLJ_MODEL_LJ, false><<<blocks, 32 * PW, 0, st>>>(a);
-  } else {
-    if (hessian) {
-      set_error("hessian is defined for the LJ model only (md_lj_le_module.py has none)");
-      return ATLJ_ERR_ARG;
-    }
-    pair_cells_kernel<ATLJ_MODEL_WCA, false><<<blocks, 32 * PW, 0, st>>>(a);
-  }
-  ATLJ_LAUNCHED();
-  return blocks;
-}
 
 // ---- all-pairs kernel (small systems: sc < 4, e.g. the reference's N=256 case) ------------------------------------
 // One thread per atom i, all j != i streamed through a shared-memory tile; exact same pair arithmetic.

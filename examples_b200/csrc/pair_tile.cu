@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, int parts) {
   const int sc = g.sc, tid = threadIdx.x, lane = tid & 31;
   const int rowid = blockIdx.x / parts, part = blockIdx.x - rowid * parts;
   const int lx = g.h + rowid / sc, cy = rowid % sc;
-  const int own0 = (lx * sc + cy) * sc;
+  const int own0 = g.cs_idx((lx * sc + cy) * sc);  // index of the row's first cell in the padded cell_start
   const int zA = (int)((long long)sc * part / parts), zB = (int)((long long)sc * (part + 1) / parts);
   const int *__restrict__ cs = a.cell_start;
   const double box = p.box;
@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, int parts) {
   const double ctrx = ((lx - g.h + g.x_lo) + 0.5) * sci - 0.5;
   const double ctry = (cy + 0.5) * sci - 0.5;
 
-  if (tid < NROWMAX) rowcell0[tid] = tid < NR ? neighbour_cell(g, LE, p.shift, lx, cy, 0, 3 * tid + 1) : -1;
+  if (tid < NROWMAX) {
+    const int c = tid < NR ? neighbour_cell(g, LE, p.shift, lx, cy, 0, 3 * tid + 1) : -1;
+    rowcell0[tid] = c < 0 ? -1 : g.cs_idx(c);
+  }
   if (tid == 0) s_q2max = 0u, s_maxwin = 0;
 
   Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0ull, 0};

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(U_NT, 4)
     const int lx = g.h + xo, y0 = 2 * yb;
     const bool two = (y0 + 1 < sc);
     const int zA = (int)((long long)sc * part / parts), zB = (int)((long long)sc * (part + 1) / parts);
-    const int ownA0 = (lx * sc + y0) * sc, ownB0 = ownA0 + sc;
+    const int ownA0 = g.cs_idx((lx * sc + y0) * sc), ownB0 = ownA0 + sc;  // rows in the padded cell_start
     if (tid < U_K) {
       // row k = yi*3 + xi holds cells (lx-1+xi, y0-1+yi); yi = 0..2 are the dy = -1,0,1 neighbours of row y0 and
       // yi = 1..3 those of row y0+1; the ids come from the stencil function the bit-exact tests cover
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(U_NT, 4)
         c = neighbour_cell(g, false, 0, lx, y0, 0, xi * 9 + yi * 3 + 1);
       else
         c = two ? neighbour_cell(g, false, 0, lx, y0 + 1, 0, xi * 9 + 2 * 3 + 1) : -1;
-      rowcell0[tid] = c;
+      rowcell0[tid] = c < 0 ? -1 : g.cs_idx(c);
     }
     const double ctrx = ((lx - g.h + g.x_lo) + 0.5) * sci - 0.5;
     const double ctry = (y0 + (two ? 1.0 : 0.5)) * sci - 0.5;

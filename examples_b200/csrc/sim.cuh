@@ -4,6 +4,19 @@
 
 #include "common.cuh"
 
+// slab decomposition state (mg.cu)
+struct MgState {
+  bool on = false;
+  int rank = 0, world = 1, left = 0, right = 0;
+  int64_t mig_cap = 0, halo_cap = 0;  // atoms per message
+  size_t mig_bytes = 0, halo_bytes = 0;
+  unsigned char *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};    // [0] left, [1] right
+  unsigned char *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // recv[0] = from the left
+  int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended
+  int *cnt_host = nullptr;  // pinned: [0] owned atoms after the sort, [4..7] error flags
+  void *comm = nullptr;     // ncclComm_t
+};
+
 struct atlj_sim {
   cudaStream_t st = nullptr;
   int64_t cap = 0;  // atom capacity of every per-atom buffer
@@ -24,14 +37,13 @@ struct atlj_sim {
   int ncell_alloc = 0;
   double *partials = nullptr;  // [partials_rows][8]
   int partials_rows = 0;
-  int pair_kernel = 0;  // 0 = tile2 (LJ) / tile1 (WCA, hessian); 1 = tile1 everywhere; 2 = warp-per-atom
+  int pair_kernel = 0;  // 0 = tile2 (LJ force) / tile1 (WCA, hessian); 1 = tile1 everywhere
   double *scal = nullptr;      // 64 device scalars (thermostat state, reduction results)
   double *rec_dev = nullptr;   // per-step records
   int64_t rec_cap = 0;
   double *noise_dev = nullptr;  // injected noise (tests)
   int64_t noise_cap = 0;
-  // multi-GPU slab bookkeeping
-  int n_halo_left = 0, n_halo_right = 0;
+  MgState mg;
   // timing
   cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // stopwatch (atlj_sim_timer_*)
   bool timing = false;
@@ -52,4 +64,5 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
 int sim_check_flags(atlj_sim *s);
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
 int sim_ensure_rec(atlj_sim *s, int64_t nrec);
+void sim_mg_destroy(atlj_sim *s);
 }  // namespace atlj

@@ -1,0 +1,179 @@
+"""Slab domain decomposition of the LJ hot path across the GPUs of one box (one rank per GPU).
+
+No reference counterpart: the reference's only distributed program is replica exchange.  The cell grid is
+the reference's (sc = floor(box/r_cut), md_lj_ll_module.py:106); rank k owns the contiguous x layers
+[x_lo, x_hi) = partition(sc, world)[k] and keeps one halo layer on each side.  The per-step exchange (migration,
+halo, all-reduce of the step record) runs inside libatlj on the sim's stream through NCCL send/recv
+(csrc/mg.cu); this module holds the host-side logic: the partition, the initial scatter of a configuration, capacity
+sizing, the NCCL bootstrap over torch.distributed, and a single-GPU emulation of several ranks (device copies in place
+of NCCL) used by the GPU tests.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .device import NREC, Simulation
+
+
+def partition(sc, world):
+    """x cell layers of each rank: contiguous, as even as possible, every rank at least one layer."""
+    assert world >= 1 and sc >= world, "need at least one cell layer per rank"
+    base, extra = divmod(sc, world)
+    out, lo = [], 0
+    for k in range(world):
+        hi = lo + base + (1 if k < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def x_layer(r, sc):
+    """Global x cell layer of every atom, with the reference's expression (md_lj_ll_module.py:88,108)."""
+    x = r[:, 0] - np.rint(r[:, 0])
+    return np.floor((x + 0.5) * sc).astype(np.int64)
+
+
+def owned_mask(r, sc, x_lo, x_hi):
+    c0 = x_layer(r, sc)
+    return (c0 >= x_lo) & (c0 < x_hi)
+
+
+def halo_mask(r, sc, x_lo, x_hi):
+    """Atoms of the two layers adjacent to the slab (periodic)."""
+    c0 = x_layer(r, sc)
+    return (c0 == (x_lo - 1) % sc) | (c0 == x_hi % sc)
+
+
+def capacities(n_total, sc, nx_own, slack=1.5):
+    """Per-rank buffer sizes (atoms): owned + halo capacity, migration message, halo message."""
+    per_layer = n_total / sc
+    halo_cap = int(per_layer * slack) + 1024
+    mig_cap = max(4096, int(per_layer * 0.05))
+    cap = int(per_layer * nx_own * 1.25) + 2 * halo_cap + 2 * mig_cap + 1024
+    return cap, mig_cap, halo_cap
+
+
+class SlabRank(Simulation):
+    """One rank's share of the system: a Simulation restricted to x layers [x_lo, x_hi) with halo/migration buffers."""
+
+    def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0):
+        self.rank, self.world = rank, world
+        n_total = r_all.shape[0]
+        sc = math.floor(box / r_cut)
+        assert sc >= 4, "the cell route needs sc >= 4"
+        self.x_lo, self.x_hi = partition(sc, world)[rank]
+        r_all = np.ascontiguousarray(r_all - np.rint(r_all))
+        mine = np.flatnonzero(owned_mask(r_all, sc, self.x_lo, self.x_hi)).astype(np.int32)
+        cap, mig_cap, halo_cap = capacities(n_total, sc, self.x_hi - self.x_lo)
+        v = None if v_all is None else np.ascontiguousarray(v_all[mine])
+        super().__init__(box, r_cut, np.ascontiguousarray(r_all[mine]), v, model=model, ids=mine, capacity=cap,
+                         stream=stream, slab=(self.x_lo, self.x_hi))
+        self.n_total = n_total
+        L = _lib.lib()
+        L.atlj_sim_set_total(self._h, n_total)
+        _lib.check(L.atlj_sim_mg_enable(self._h, mig_cap, halo_cap))
+
+    # ---- the three device phases (emulation) and their buffers ----------------------------------------------------
+    def phase1(self, dt):
+        _lib.check(_lib.lib().atlj_sim_mg_phase1(self._h, float(dt)))
+
+    def phase2(self):
+        _lib.check(_lib.lib().atlj_sim_mg_phase2(self._h))
+
+    def phase3(self, dt):
+        rec = np.zeros(NREC)
+        _lib.check(_lib.lib().atlj_sim_mg_phase3(self._h, float(dt), rec.ctypes.data))
+        return rec
+
+    def buffer(self, which):
+        L = _lib.lib()
+        return L.atlj_sim_mg_buffer(self._h, which), L.atlj_sim_mg_buffer_bytes(self._h, which)
+
+    # ---- NCCL path ------------------------------------------------------------------------------------------------
+    def connect(self, unique_id):
+        _lib.check(_lib.lib().atlj_sim_mg_connect(self._h, self.rank, self.world, unique_id))
+
+    def run_nve(self, dt, nsteps, hessian=False, record=True):
+        assert not hessian, "hessian is not part of the multi-GPU loop"
+        rec = np.zeros((nsteps, NREC)) if record else None
+        _lib.check(_lib.lib().atlj_sim_run_nve_mg(self._h, float(dt), int(nsteps),
+                                                  None if rec is None else rec.ctypes.data))
+        return rec
+
+    def force(self, strain=0.0, hessian=False):
+        """Force evaluation on the current positions = one step with dt = 0 (kick and drift are exact no-ops)."""
+        return self.run_nve(0.0, 1)[0]
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().atlj_nccl_unique_id(buf))
+    return buf.raw
+
+
+class SlabSimulation(SlabRank):
+    """The rank of THIS process in a torch.distributed job (one process per GPU): bootstraps libatlj's own NCCL
+    communicator by broadcasting the unique id through torch.distributed."""
+
+    def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0):
+        import torch.distributed as dist
+        super().__init__(box, r_cut, r_all, v_all, rank, world, model=model, stream=stream)
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.connect(ids[0])
+
+
+class EmulatedSlabs:
+    """`world` ranks on ONE GPU in one process: the two exchanges of a step are device-to-device copies and the
+    all-reduce is a host sum.  Same kernels, same message formats, same ordering as the NCCL path."""
+
+    def __init__(self, box, r_cut, r, v, world, model="lj"):
+        self.world = world
+        self.ranks = [SlabRank(box, r_cut, r, v, k, world, model=model) for k in range(world)]
+
+    def _exchange(self, send_left, send_right, recv_left, recv_right):
+        L = _lib.lib()
+        w = self.world
+        for k, me in enumerate(self.ranks):
+            left, right = self.ranks[(k - 1) % w], self.ranks[(k + 1) % w]
+            src, nb = me.buffer(send_left)
+            dst, _ = left.buffer(recv_right)      # my message to the left arrives "from the right" there
+            _lib.check(L.atlj_device_copy(dst, src, nb))
+            src, nb = me.buffer(send_right)
+            dst, _ = right.buffer(recv_left)
+            _lib.check(L.atlj_device_copy(dst, src, nb))
+
+    def step(self, dt):
+        for s in self.ranks:
+            s.phase1(dt)
+        self._exchange(0, 1, 2, 3)
+        for s in self.ranks:
+            s.phase2()
+        self._exchange(4, 5, 6, 7)
+        rec = sum(s.phase3(dt) for s in self.ranks)
+        rec[7] = 1.0 if rec[7] > 0 else 0.0
+        return rec
+
+    def force(self):
+        return self.step(0.0)
+
+    def run_nve(self, dt, nsteps):
+        return np.array([self.step(dt) for _ in range(nsteps)])
+
+    def gather(self):
+        """r, v, f of the whole system in the original atom order."""
+        n = self.ranks[0].n_total
+        r, v, f = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3))
+        seen = np.zeros(n, dtype=np.int64)
+        for s in self.ranks:
+            rs, vs, fs, ids = s.download_sorted()
+            r[ids], v[ids], f[ids] = rs, vs, fs
+            seen[ids] += 1
+        assert np.all(seen == 1), "every atom must be owned by exactly one rank"
+        return r, v, f
+
+    def close(self):
+        for s in self.ranks:
+            s.close()

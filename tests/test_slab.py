@@ -1,0 +1,125 @@
+"""Slab domain decomposition.
+
+CPU (gloo, world_size 2): the host-side logic -- partition, ownership, halo selection, ring exchange -- checked by
+computing the forces on each rank's owned atoms from owned + received halo atoms with the C oracle and comparing with
+the single-domain oracle forces.
+GPU: several ranks emulated on one device (device copies in place of NCCL; same kernels, same message formats) against
+the single-domain CUDA path: totals, forces, a 60-step trajectory with atoms migrating between slabs."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, liquid_like, rel_err
+
+
+def test_partition_covers_all_layers():
+    from examples_b200.slab import partition
+    for sc in (4, 5, 13, 55, 111):
+        for world in (1, 2, 3, 4, 8):
+            if sc < world:
+                continue
+            p = partition(sc, world)
+            assert p[0][0] == 0 and p[-1][1] == sc
+            assert all(a[1] == b[0] for a, b in zip(p, p[1:]))
+            sizes = [hi - lo for lo, hi in p]
+            assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, ROOT)
+        from examples_b200.slab import halo_mask, owned_mask, partition, x_layer
+        from oracle import oracle as O
+        n, box, r = liquid_like(10, 0.75, 0.06)  # N = 4000, sc = 6
+        sc = math.floor(box / 2.5)
+        x_lo, x_hi = partition(sc, world)[rank]
+        own = owned_mask(r, sc, x_lo, x_hi)
+        ids = np.flatnonzero(own)
+        # ring exchange of the boundary layers: first owned layer to the left, last owned layer to the right
+        c0 = x_layer(r, sc)
+        first, last = np.flatnonzero(c0 == x_lo), np.flatnonzero(c0 == x_hi - 1)
+        left, right = (rank - 1) % world, (rank + 1) % world
+
+        def sendrecv(payload, dst, src):
+            size = torch.tensor([payload.size], dtype=torch.int64)
+            got = torch.zeros(1, dtype=torch.int64)
+            reqs = [dist.isend(size, dst), dist.irecv(got, src)]
+            [q_.wait() for q_ in reqs]
+            buf = torch.empty(int(got.item()), dtype=torch.float64)
+            reqs = [dist.isend(torch.from_numpy(payload.ravel().copy()), dst), dist.irecv(buf, src)]
+            [q_.wait() for q_ in reqs]
+            return buf.numpy().reshape(-1, 4)
+
+        pack = lambda idx: np.concatenate([r[idx], idx[:, None].astype(np.float64)], axis=1)
+        from_right = sendrecv(pack(first), left, right)   # the right neighbour's first layer = my right halo
+        from_left = sendrecv(pack(last), right, left)
+        halo = np.concatenate([from_left, from_right])
+        hid = halo[:, 3].astype(np.int64)
+        want = np.flatnonzero(halo_mask(r, sc, x_lo, x_hi))
+        assert sorted(set(hid.tolist())) == sorted(want.tolist()), "halo = the two adjacent layers"
+        # forces on owned atoms from owned + halo (all pairs on the subset, minimum image in the full box)
+        sub = np.concatenate([r[ids], halo[:, :3]])
+        _, f_sub, _, _ = O.force(np.ascontiguousarray(sub), box, 2.5, cells=False)
+        _, f_all, _, _ = O.force(r, box, 2.5, cells=True)
+        err = rel_err(f_sub[:len(ids)], f_all[ids])
+        cnt = torch.tensor([len(ids)], dtype=torch.int64)
+        dist.all_reduce(cnt)
+        q.put((rank, err, int(cnt.item()), n))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_scheme_two_ranks_gloo(oracle):
+    """world_size 2 on CPU: ownership is a partition of the atoms, one halo layer per side is sufficient, the ring
+    exchange delivers exactly the adjacent layers."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, q)) for k in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, err, total, n in res:
+        assert err < 1e-10 and total == n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nc,world", [(10, 2), (10, 3), (20, 4), (14, 8)])
+def test_emulated_slabs_match_single_domain(nc, world):
+    from examples_b200.device import Simulation
+    from examples_b200.lattice import ran_velocities
+    from examples_b200.slab import EmulatedSlabs
+    n, box, r = liquid_like(nc, 0.75, 0.06)
+    v = ran_velocities(n, 1.5)
+    one = Simulation(box, 2.5, r, v)
+    rec1 = one.force()
+    many = EmulatedSlabs(box, 2.5, r, v, world)
+    recm = many.force()
+    assert recm[11] == n and recm[8] == rec1[8], "atoms conserved, in-range pair count exact"
+    assert rel_err(recm[:4], rec1[:4]) < 1e-10 and recm[7] == rec1[7]
+    r1, v1, f1 = one.download()
+    rm, vm, fm = many.gather()
+    assert rel_err(fm, f1) < 1e-10 and np.array_equal(rm, r1)
+    # a trajectory: atoms cross slab boundaries; every step's scalars and the final state agree
+    nsteps = 60
+    t1 = one.run_nve(0.005, nsteps)
+    tm = many.run_nve(0.005, nsteps)
+    assert np.all(tm[:, 11] == n)
+    for k in (0, 1, 2, 3, 4, 5):
+        assert rel_err(tm[:, k], t1[:, k]) < 1e-9, k
+    assert np.array_equal(tm[:, 8], t1[:, 8])
+    r1, v1, f1 = one.download()
+    rm, vm, fm = many.gather()
+    assert rel_err(rm, r1) < 1e-9 and rel_err(vm, v1) < 1e-9 and rel_err(fm, f1) < 1e-8
+    owners0 = [set(s.download_sorted()[3].tolist()) for s in many.ranks]
+    assert sum(len(o) for o in owners0) == n
+    one.close(), many.close()
