@@ -277,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
     n_rank = n_total / world
     flops = FLOP_PER_PAIR * pairs_per_step / world
     ach = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
-    roofline = {"kernel": "pair_cells_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12,
+    roofline = {"kernel": "pair_tile2_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12,
                 "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
                 "peak_source": "register-resident DFMA probe (atlj_measure_fp64_peak) in this run; "
                                "MEASURED_PEAKS.json has no fp64 figure",

@@ -55,9 +55,12 @@ class Simulation:
         self.upload(r, v, ids)
 
     def close(self):
-        if getattr(self, "_h", None):
-            _lib.lib().atlj_sim_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().atlj_sim_destroy(h)
+            except Exception:  # interpreter shutdown: the module globals are already gone
+                pass
 
     __del__ = close
 
