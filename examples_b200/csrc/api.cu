@@ -226,6 +226,8 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   // A/B runs: ATLJ_PAIR_KERNEL=tile1 routes LJ forces through the first tiled kernel as well
   const char *op = getenv("ATLJ_PAIR_KERNEL");
   s->pair_kernel = (op && strcmp(op, "tile1") == 0) ? 1 : 0;
+  const char *uf = getenv("ATLJ_UNFUSED");  // A/B runs: the unfused 12-launch velocity-Verlet step
+  s->unfused = uf && uf[0] == '1';
   s->cap = capacity;
   size_t c = (size_t)capacity;
   bool ok = true;
@@ -235,10 +237,10 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   }
   ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
        dev_alloc(&s->cb.rank, c) == ATLJ_OK && dev_alloc(&s->cb.keys, c) == ATLJ_OK &&
-       dev_alloc(&s->cb.block_sums, 8192) == ATLJ_OK && dev_alloc(&s->cb.err, 4) == ATLJ_OK &&
-       dev_alloc(&s->scal, 64) == ATLJ_OK;
+       dev_alloc(&s->cb.block_sums, 8192) == ATLJ_OK && dev_alloc(&s->cb.err, 8) == ATLJ_OK &&
+       dev_alloc(&s->scal, 64) == ATLJ_OK && dev_alloc(&s->vf_partials, 4 * 4096) == ATLJ_OK;
   if (ok) ok = ensure_partials(s, pair_grid_blocks()) == ATLJ_OK;
-  if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 4 * sizeof(int), s->st) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 8 * sizeof(int), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->scal, 0, 64 * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->f, 0, 3 * c * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = sim_ensure_rec(s, 64) == ATLJ_OK;
@@ -256,7 +258,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   for (int k = 0; k < 2; k++) cudaFree(s->r[k]), cudaFree(s->v[k]), cudaFree(s->id[k]);
   cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
-  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev);
+  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials);
   if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
@@ -361,6 +363,50 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
   if (rc) return rc;
   const long long n3 = 3 * s->n;
   const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first
+  if (!with_hessian && s->use_cells && nsteps > 0 && !s->unfused) {
+    // Fused loop: between two pair kernels ONE pass does the trailing half kick of the finished step (with its sums),
+    // the leading half kick, the drift, the wrap and the cell assignment, and finishes the record of the step that
+    // just ended (two-level fixed-order reduction of the pair kernel's per-item rows and of sum v^2, sum f^2 inside
+    // that kernel).  7 launches per step instead of 12; results identical to the unfused sequence below up to the
+    // order of the final sums.
+    const int n = (int)s->n;
+    Phys p = s->p;
+    p.strain = 0.0, p.shift = 0;
+    int nb_prev = 0;
+    double *rec_prev = nullptr;
+    const bool tile2 = s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;  // finishes its record inside the kernel
+    for (int k = 0; k < nsteps; k++) {
+      double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+      ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));
+      const int cur = s->cur, alt = 1 - cur;
+      Timer::begin(s, 2);
+      const int nvf = launch_kdk_assign(s->st, s->g, n, s->r[cur], s->v[cur], s->f, half_dt, dt, p.box, k > 0, s->cb,
+                                        s->vf_partials, rec_prev, s->partials, nb_prev, p.model);
+      if (nvf < 0) return nvf;
+      Timer::end(s);
+      Timer::begin(s, 1);
+      if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
+      if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
+                                        s->v[alt], s->id[alt])))
+        return rc;
+      Timer::end(s);
+      s->cur = alt;
+      PairArgs a;
+      a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
+      a.f = s->f, a.partials = s->partials, a.g = s->g, a.p = p;
+      Timer::begin(s, 0);
+      nb_prev = tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false);
+      Timer::end(s);
+      if (nb_prev < 0) return nb_prev;
+      rec_prev = rec;
+    }
+    Timer::begin(s, 2);
+    if ((rc = launch_finalize(s->st, s->partials, nb_prev, p.model, false, rec_prev, s->cb.err + 2))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_prev + 4))) return rc;
+    Timer::end(s);
+    s->step_count += nsteps;
+    return sim_copy_rec(s, rec_host, nsteps);
+  }
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     Timer::begin(s, 2);
@@ -372,6 +418,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4))) return rc;
     Timer::end(s);
   }
+  s->step_count += nsteps;
   return sim_copy_rec(s, rec_host, nsteps);
 }
 

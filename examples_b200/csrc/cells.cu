@@ -8,11 +8,13 @@
 //                    arrival rank inside the cell                                  (reads 24 B, writes 8 B / atom)
 //   2. cell_scan   : exclusive scan of the histogram -> cell_start                 (4 B / cell, three small kernels)
 //   3. cell_scatter: key = (atom id << 32 | source index) -> slot cell_start + rank
-//   4. cell_sort   : one thread per cell orders its <= ~30 keys by atom id (the arrival rank of step 1 is
-//                    scheduling dependent, the sorted result is not) -> "ascending atom index" of the reference
-//   5. gather      : r (and v, id) copied into cell order
+//   4. cell_sortgather: per block of 128 cells, keys to shared memory, one thread per cell orders its <= ~30 keys
+//                    by atom id (the arrival rank of step 1 is scheduling dependent, the sorted result is not) ->
+//                    "ascending atom index" of the reference; then r (and v, id) are gathered into cell order
 // All HBM-bound; see DESIGN.md for bytes per atom.
 #include "common.cuh"
+#include "integrate.cuh"
+#include "pair_math.cuh"
 
 namespace atlj {
 
@@ -78,6 +80,130 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
     ATLJ_LAUNCHED();
   }
   return ATLJ_OK;
+}
+
+// ---- fused integration + assignment (single-GPU velocity-Verlet loop) ------------------------------------------------
+// One HBM pass per step for everything between two force evaluations (md_nve_lj.py:190 of step k-1, then :182-185 of
+// step k, then md_lj_ll_module.py:88,106-109):  v += hdt*f [sum v^2, sum f^2 of the finished step]  ->  v += hdt*f
+// -> r += dt*v/box -> wrap -> cell triplet, histogram, arrival rank.  Same separately-rounded operations as
+// kick_sums_kernel + kick_drift_kernel + cell_assign_kernel, so results are bit-identical to the unfused sequence.
+__global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
+                                                        const double *__restrict__ f, double half_dt, double dt,
+                                                        double box, int first_kick, int *__restrict__ cellid,
+                                                        int *__restrict__ rank, int *__restrict__ cell_count,
+                                                        int *__restrict__ err, double *__restrict__ partials,
+                                                        double *__restrict__ rec_vf,
+                                                        const double *__restrict__ pair_partials, int pair_rows,
+                                                        int model) {
+  // tiles of IT atoms: the 3*IT components are streamed with perfectly coalesced accesses (one component per thread
+  // and pass), the wrapped coordinates are parked in shared memory, then one thread per atom does the integer part
+  __shared__ double xs[3 * IT];
+  double s[2] = {0.0, 0.0};
+  const double scd = (double)g.sc;
+  const int ntiles = (n + IT - 1) / IT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t e0 = 3 * (size_t)tile * IT;
+    const int ne = min(3 * IT, 3 * n - (int)e0 > 0 ? (int)(3 * (size_t)n - e0) : 0);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int l = threadIdx.x + k * IT;
+      if (l < ne) {
+        const size_t e = e0 + l;
+        const double ff = f[e];
+        double vv = v[e];
+        if (first_kick) {
+          vv = __dadd_rn(vv, __dmul_rn(half_dt, ff));
+          s[0] += vv * vv;
+          s[1] += ff * ff;
+        }
+        vv = __dadd_rn(vv, __dmul_rn(half_dt, ff));
+        double x = wrap1(__dadd_rn(r[e], __ddiv_rn(__dmul_rn(dt, vv), box)));
+        x = __dsub_rn(x, rint(x));  // the force routine wraps again (md_lj_ll_module.py:88); idempotent
+        v[e] = vv;
+        r[e] = x;
+        xs[l] = x;
+      }
+    }
+    __syncthreads();
+    const int i = tile * IT + threadIdx.x;
+    if (i < n) {
+      const double w0 = xs[3 * threadIdx.x], w1 = xs[3 * threadIdx.x + 1], w2 = xs[3 * threadIdx.x + 2];
+      const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(w0, 0.5), scd));  // md_lj_ll_module.py:108
+      const long long c1 = (long long)floor(__dmul_rn(__dadd_rn(w1, 0.5), scd));
+      const long long c2 = (long long)floor(__dmul_rn(__dadd_rn(w2, 0.5), scd));
+      const bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc;  // :109
+      if (bad) {
+        atomicOr(&err[0], 1);
+        cellid[i] = -1;
+        rank[i] = 0;
+      } else {
+        const int cid = (((int)c0 + g.h - g.x_lo) * g.sc + (int)c1) * g.sc + (int)c2;
+        cellid[i] = cid;
+        rank[i] = atomicAdd(&cell_count[cid], 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (!first_kick) return;
+  // ---- finish the record of the step that just ended -----------------------------------------------------------------
+  // level 1: this CTA's {sum v^2, sum f^2} and its fixed slice of the pair kernel's per-item rows -> one row of 12
+  // level 2: the CTA that finishes last sums the rows in fixed order and writes the record (deterministic)
+  constexpr int ROW = 12;
+  block_reduce_store<2>(s, partials + ROW * (size_t)blockIdx.x);
+  if (threadIdx.x >= 32 && threadIdx.x < 39) {
+    const int k = threadIdx.x - 32;
+    const int r0 = (int)((long long)pair_rows * blockIdx.x / gridDim.x);
+    const int r1 = (int)((long long)pair_rows * (blockIdx.x + 1) / gridDim.x);
+    double t = 0.0;
+    for (int b = r0; b < r1; b++) t += pair_partials[8 * (size_t)b + k];
+    partials[ROW * (size_t)blockIdx.x + 2 + k] = t;
+  }
+  __shared__ int s_last;
+  __shared__ double fin[IT / 32][9];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&err[4], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) t[k] += __ldcg(partials + ROW * (size_t)b + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) fin[threadIdx.x >> 5][k] = t[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 9; k++) {
+      double a = 0.0;
+      for (int w = 0; w < IT / 32; w++) a += fin[w][k];
+      t[k] = a;
+    }
+    rec_vf[4] = t[0], rec_vf[5] = t[1];
+    if (pair_partials) finalize_totals(t + 2, model, false, rec_vf);
+    err[4] = 0;
+    err[2] = 0;  // work counter of the tiled pair kernel
+  }
+}
+
+// -> number of CTAs (= rows of vf partials written when first_kick)
+int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
+                      double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
+                      const double *pair_partials, int pair_rows, int model) {
+  ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+  const int nb = integ_blocks(n);
+  kdk_assign_kernel<<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, first_kick ? 1 : 0, b.cellid, b.rank,
+                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model);
+  ATLJ_LAUNCHED();
+  return nb;
 }
 
 // ---- 2. exclusive scan over the owned cells ------------------------------------------------------------------
@@ -209,16 +335,11 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const 
 }
 
 // ---- 4. order each cell by atom id -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const int *__restrict__ cell_start,
-                                                        const int *__restrict__ cell_count,
-                                                        unsigned long long *__restrict__ keys) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.n_own_cells()) return;
-  c += g.first_own_cell();
-  int n = cell_count[c];
+// insertion sort for ordinary cells (keys arrive nearly ordered when the atoms were in cell order already), heap
+// sort for crowded ones (dense blobs); in place, k may point to shared or global memory
+__device__ __forceinline__ void sort_cell_keys(unsigned long long *k, int n) {
   if (n < 2) return;
-  unsigned long long *k = keys + (cell_start[g.cs_idx(c)] - base);
-  if (n <= 32) {  // insertion sort; keys arrive nearly ordered when the atoms were in cell order already
+  if (n <= 32) {
     for (int a = 1; a < n; a++) {
       unsigned long long x = k[a];
       int b = a - 1;
@@ -228,7 +349,7 @@ __global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const 
       }
       k[b + 1] = x;
     }
-  } else {  // heap sort for crowded cells (dense blobs); O(n log n), in place
+  } else {
     for (int start = n / 2 - 1; start >= 0; start--) {
       int root = start;
       for (;;) {
@@ -261,27 +382,60 @@ __global__ void __launch_bounds__(128) cell_sort_kernel(Geom g, int base, const 
   }
 }
 
-// ---- 5. gather into cell order ---------------------------------------------------------------------------------
-// One thread per (atom, component) so that the writes are perfectly coalesced; the reads hit 24-byte records
-// whose three components are fetched by neighbouring threads.
-__global__ void __launch_bounds__(256) cell_gather_kernel(int n, const int *__restrict__ n_dev,
-                                                          const unsigned long long *__restrict__ keys,
-                                                          const double *__restrict__ r_in,
-                                                          const double *__restrict__ v_in, double *__restrict__ r_out,
-                                                          double *__restrict__ v_out, int *__restrict__ id_out) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n_dev) n = min(n, *n_dev);
-  if (t >= 3 * n) return;
-  int s = t / 3, k = t - 3 * s;
-  unsigned long long key = keys[s];
-  unsigned src = (unsigned)(key & 0xffffffffull);
-  r_out[t] = r_in[3 * (size_t)src + k];
-  if (v_in) v_out[t] = v_in[3 * (size_t)src + k];
-  if (k == 0 && id_out) id_out[s] = (int)(key >> 32);
+// ---- 4+5. order each cell by atom id and gather r, v, id into cell order ----------------------------------------
+// One CTA takes SG_CELLS consecutive owned cells: their keys are one contiguous run of slots, which is loaded into
+// shared memory with coalesced reads, sorted there (one thread per cell; the arrival rank of step 1 is scheduling
+// dependent, the sorted result is not -> "ascending atom index" of md_lj_ll_module.py:118-119), and then drives the
+// gather: one thread per (atom, component), so the writes of r, v in cell order are perfectly coalesced.  A run that
+// does not fit (crowded cells) is sorted in global memory instead.
+constexpr int SG_CELLS = 128;
+constexpr int SG_KEYS = 3072;  // 24 KB of keys per CTA
+
+__global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int base,
+                                                                    const int *__restrict__ cell_start,
+                                                                    const int *__restrict__ cell_count,
+                                                                    unsigned long long *__restrict__ keys,
+                                                                    const double *__restrict__ r_in,
+                                                                    const double *__restrict__ v_in,
+                                                                    double *__restrict__ r_out,
+                                                                    double *__restrict__ v_out,
+                                                                    int *__restrict__ id_out) {
+  __shared__ unsigned long long sk[SG_KEYS];
+  __shared__ int s_lo, s_hi;
+  const int nown = g.n_own_cells(), first = g.first_own_cell();
+  const int c0 = blockIdx.x * SG_CELLS;
+  const int c = c0 + threadIdx.x;
+  int mystart = 0, mycnt = 0;
+  if (c < nown) {
+    mystart = cell_start[g.cs_idx(first + c)] - base;
+    mycnt = cell_count[first + c];
+  }
+  if (threadIdx.x == 0) s_lo = mystart;
+  const int clast = min(c0 + SG_CELLS, nown) - 1;
+  if (c == clast) s_hi = mystart + mycnt;
+  __syncthreads();
+  const int lo = s_lo, tot = s_hi - s_lo;
+  const bool fits = tot <= SG_KEYS;
+  unsigned long long *kbase = fits ? sk : keys + lo;
+  if (fits) {
+    for (int s = threadIdx.x; s < tot; s += SG_CELLS) sk[s] = keys[lo + s];
+    __syncthreads();
+  }
+  sort_cell_keys(kbase + (mystart - lo), mycnt);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * tot; e += SG_CELLS) {
+    const int s = e / 3, k = e - 3 * s;
+    const unsigned long long key = kbase[s];
+    const size_t src = (size_t)(key & 0xffffffffull);
+    const size_t dst = 3 * (size_t)(lo + s) + k;
+    r_out[dst] = r_in[3 * src + k];
+    if (v_in) v_out[dst] = v_in[3 * src + k];
+    if (k == 0 && id_out) id_out[lo + s] = (int)(key >> 32);
+  }
 }
 
-// n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); after the sort the
-// number of atoms kept is the end sentinel of the last owned layer, which the gather reads from the device as well
+// n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); the sort + gather
+// walks cells, not atoms, so it needs no count at all
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
                             const int *n_dev) {
@@ -290,10 +444,8 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
                                                        b.keys);
   ATLJ_LAUNCHED();
   int nc = g.n_own_cells();
-  cell_sort_kernel<<<(nc + 127) / 128, 128, 0, st>>>(g, base, b.cell_start, b.cell_count, b.keys);
-  ATLJ_LAUNCHED();
-  const int *n_kept = n_dev ? b.cell_start + g.cs_idx((g.h + g.nx_own) * g.sc * g.sc - 1) + 1 : nullptr;
-  cell_gather_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(n, n_kept, b.keys, r_in, v_in, r_out, v_out, id_out);
+  cell_sortgather_kernel<<<(nc + SG_CELLS - 1) / SG_CELLS, SG_CELLS, 0, st>>>(g, base, b.cell_start, b.cell_count,
+                                                                              b.keys, r_in, v_in, r_out, v_out, id_out);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -135,6 +135,13 @@ struct CellBufs {
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
                        double strain, const CellBufs &b, long long *c_out, const int *n_dev = nullptr,
                        bool drop_adjacent = false);
+// fused kick [+ sums] + kick + drift + wrap + cell assignment of the single-GPU NVE loop; returns the number of CTAs
+// (= rows of vf_partials written when first_kick) or a negative status
+// rec_vf (used when first_kick): the finished step's record: its [4], [5] = sum v^2, sum f^2 and, when pair_partials
+// is given, the pair kernel's totals (per-item rows reduced in fixed order) are written by the kernel's last CTA
+int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
+                      double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
+                      const double *pair_partials, int pair_rows, int model);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
@@ -156,12 +163,15 @@ int pair_grid_blocks();  // upper bound of the all-pairs kernel's CTAs (partials
 int pair_tile_grid(const Geom &g);  // CTAs of the tiled kernel (rows of partials it writes)
 int launch_pair_tile(cudaStream_t st, const PairArgs &a, bool hessian);  // -> CTAs launched or a negative status
 int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the second-generation LJ kernel
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);  // -> items or a negative status
+// -> items (= rows of partials written) or a negative status; *work_counter must be 0 on entry (launch_finalize and
+// the fused integration kernel reset it)
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)
 // (also zeroes *reset_counter, the work counter of the tiled kernel, when it is not null)
+// vf_partials (may be null): [nvf][4] partial {sum v^2, sum f^2} of the integration kernel, reduced into rec[4], rec[5]
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
-                    int *reset_counter = nullptr);
+                    int *reset_counter = nullptr, const double *vf_partials = nullptr, int nvf = 0);
 
 }  // namespace atlj

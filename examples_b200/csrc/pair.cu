@@ -95,52 +95,46 @@ int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, 
 }
 
 // ---- fixed-order reduction of the CTA partials + the reference's final scaling ------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,
-                                                       int hessian, double *__restrict__ rec,
-                                                       int *__restrict__ reset_counter) {
+constexpr int FIN_T = 1024;
+__global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,
+                                                         int hessian, double *__restrict__ rec,
+                                                         int *__restrict__ reset_counter,
+                                                         const double *__restrict__ vf_partials, int nvf) {
   if (threadIdx.x == 0 && reset_counter) *reset_counter = 0;
-  __shared__ double sm[256][7];
-  double v[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int b = threadIdx.x; b < nblocks; b += 256) {
+  __shared__ double sm[FIN_T / 32][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblocks; b += FIN_T) {
 #pragma unroll
     for (int k = 0; k < 7; k++) v[k] += partials[8 * (size_t)b + k];
   }
+  if (vf_partials)
+    for (int b = threadIdx.x; b < nvf; b += FIN_T) v[7] += vf_partials[4 * (size_t)b], v[8] += vf_partials[4 * (size_t)b + 1];
 #pragma unroll
-  for (int k = 0; k < 7; k++) sm[threadIdx.x][k] = v[k];
-  __syncthreads();
-  for (int o = 128; o >= 1; o >>= 1) {
-    if (threadIdx.x < o) {
+  for (int k = 0; k < 9; k++) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) sm[threadIdx.x][k] += sm[threadIdx.x + o][k];
-    }
-    __syncthreads();
+    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
   }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) sm[warp][k] = v[k];
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    // every pair was visited from both ends: halve (exact), then scale as md_lj_module.py:143-147
-    double a = sm[0][0] * 0.5, pot = sm[0][1] * 0.5, vir = sm[0][2] * 0.5, lap = sm[0][3] * 0.5;
-    if (hessian) {
-      rec[6] = sm[0][4] * 0.5;
-    } else {
-      if (model == ATLJ_MODEL_LJ) {
-        rec[0] = a * 4.0;            // cut
-        rec[1] = pot * 4.0;          // pot
-        rec[2] = vir * 24.0 / 3.0;   // vir
-        rec[3] = lap * 24.0 * 2.0;   // lap
-      } else {
-        rec[0] = pot * 4.0;          // md_lj_le_module.py:144-148
-        rec[1] = vir * 24.0 / 3.0;
-        rec[2] = lap * 24.0 * 2.0;
-        rec[3] = a * 24.0;           // pyx
-      }
-      rec[7] = sm[0][6] > 0.0 ? 1.0 : 0.0;  // ovr
-      rec[8] = sm[0][5] * 0.5;              // in-range pairs, counted once
+    double t[9];
+    for (int k = 0; k < 9; k++) {
+      double s = 0.0;
+      for (int w = 0; w < FIN_T / 32; w++) s += sm[w][k];
+      t[k] = s;
     }
+    finalize_totals(t, model, hessian != 0, rec);
+    if (vf_partials) rec[4] = t[7], rec[5] = t[8];
   }
 }
 
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
-                    int *reset_counter) {
-  finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter);
+                    int *reset_counter, const double *vf_partials, int nvf) {
+  finalize_kernel<<<1, FIN_T, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter, vf_partials, nvf);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

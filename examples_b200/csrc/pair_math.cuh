@@ -109,6 +109,29 @@ __device__ __forceinline__ void block_store_partials(Acc acc, double *__restrict
 }
 
 
+// Final halving + scaling of the summed partials t = {a, pot, vir, lap, hes, npairs, ovr} into the step record
+// (every pair was visited from both ends: halve, exactly; then md_lj_module.py:143-147 / md_lj_le_module.py:144-148)
+__device__ __forceinline__ void finalize_totals(const double *t, int model, bool hessian, double *__restrict__ rec) {
+  const double a = t[0] * 0.5, pot = t[1] * 0.5, vir = t[2] * 0.5, lap = t[3] * 0.5;
+  if (hessian) {
+    rec[6] = t[4] * 0.5;
+    return;
+  }
+  if (model == ATLJ_MODEL_LJ) {
+    rec[0] = a * 4.0;            // cut
+    rec[1] = pot * 4.0;          // pot
+    rec[2] = vir * 24.0 / 3.0;   // vir
+    rec[3] = lap * 24.0 * 2.0;   // lap
+  } else {
+    rec[0] = pot * 4.0;
+    rec[1] = vir * 24.0 / 3.0;
+    rec[2] = lap * 24.0 * 2.0;
+    rec[3] = a * 24.0;           // pyx
+  }
+  rec[7] = t[6] > 0.0 ? 1.0 : 0.0;  // ovr
+  rec[8] = t[5] * 0.5;              // in-range pairs, counted once
+}
+
 // 1/x to ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + two Newton steps; used only where no predicate depends on it
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;

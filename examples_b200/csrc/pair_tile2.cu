@@ -40,7 +40,7 @@ int pair_tile2_parts(const Geom &g) {
   int maxp = g.sc / 4 < 1 ? 1 : g.sc / 4;
   if (forced > 0) return forced > maxp ? maxp : forced;
   int rows2 = g.nx_own * ((g.sc + 1) / 2);
-  int want = (148 * 4 * 5 + rows2 - 1) / rows2;  // ~5 items per resident CTA
+  int want = (148 * 4 * 8 + rows2 - 1) / rows2;  // ~8 items per resident CTA (measured best at 2 M atoms)
   return want < 1 ? 1 : (want > maxp ? maxp : want);
 }
 int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * pair_tile2_parts(g); }
@@ -456,7 +456,6 @@ __global__ void __launch_bounds__(U_NT, 4)
   }
 }
 
-// returns the number of partial rows written (= work items) or a negative status
 int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
   static int grid = 0;
   const size_t smem = tile2_smem_bytes();
