@@ -34,7 +34,7 @@ static int device_ok() {
 }
 
 // ---- timing -------------------------------------------------------------------------------------------------------
-void Timer::begin(atlj_sim *s, int cat) {
+void Timer::begin(atlj_sim *s, int cat, cudaStream_t st, bool other_stream) {
   if (!s->timing) return;
   cudaEvent_t e0, e1;
   if (s->ev_free.size() >= 2) {
@@ -44,15 +44,16 @@ void Timer::begin(atlj_sim *s, int cat) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
   }
-  cudaEventRecord(e0, s->st);
-  s->ev_open.push_back({e0, e1, cat});
+  cudaEventRecord(e0, other_stream ? st : s->st);
+  (other_stream ? s->ev_open2 : s->ev_open).push_back({e0, e1, cat});
 }
-void Timer::end(atlj_sim *s) {
+void Timer::end(atlj_sim *s, cudaStream_t st, bool other_stream) {
   if (!s->timing) return;
-  auto &t = s->ev_open.back();
-  cudaEventRecord(t.e1, s->st);
+  auto &open = other_stream ? s->ev_open2 : s->ev_open;
+  auto &t = open.back();
+  cudaEventRecord(t.e1, other_stream ? st : s->st);
   s->ev_done.push_back(t);
-  s->ev_open.pop_back();
+  open.pop_back();
 }
 
 // ---- allocation ---------------------------------------------------------------------------------------------------
@@ -263,6 +264,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
   for (auto &t : s->ev_open) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+  for (auto &t : s->ev_open2) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
   delete s;
 }
 
@@ -492,13 +494,14 @@ int atlj_sim_enable_timing(atlj_sim *s, int on) {
   return ATLJ_OK;
 }
 
-int atlj_sim_timing(atlj_sim *s, double ms[4]) {
+int atlj_sim_timing(atlj_sim *s, double ms[8]) {
   if (!s) return ATLJ_ERR_ARG;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
-  for (int k = 0; k < 4; k++) ms[k] = 0.0;
+  if (s->mg.st2) ATLJ_CUDA(cudaStreamSynchronize(s->mg.st2));
+  for (int k = 0; k < 8; k++) ms[k] = 0.0;
   for (auto &t : s->ev_done) {
     float m = 0.f;
-    if (cudaEventElapsedTime(&m, t.e0, t.e1) == cudaSuccess) ms[t.cat & 3] += m;
+    if (cudaEventElapsedTime(&m, t.e0, t.e1) == cudaSuccess) ms[t.cat & 7] += m;
     s->ev_free.push_back(t.e0);
     s->ev_free.push_back(t.e1);
   }

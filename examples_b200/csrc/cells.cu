@@ -26,9 +26,16 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *
                                                           int *__restrict__ cellid, int *__restrict__ rank,
                                                           int *__restrict__ cell_count, int *__restrict__ err,
                                                           long long *__restrict__ c_out,
-                                                          const int *__restrict__ n_dev, int drop_adjacent) {
+                                                          const int *__restrict__ n_dev, int drop_adjacent,
+                                                          const int *__restrict__ i0_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n_dev) n = min(n, *n_dev);
+  if (i0_dev) {  // a sub-range [*i0_dev, *n_dev) of the atoms (arrivals appended behind the old ones); n = its bound
+    if (i >= n) return;
+    i += *i0_dev;
+    n = *n_dev;
+  } else if (n_dev) {
+    n = min(n, *n_dev);
+  }
   if (i >= n) return;
   double x = r_in[3 * i], y = r_in[3 * i + 1], z = r_in[3 * i + 2];
   if (le) x = __dsub_rn(x, __dmul_rn(rint(y), strain));  // md_lj_llle_module.py:94
@@ -72,11 +79,13 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(Geom g, const double *
 }
 
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
-                       double strain, const CellBufs &b, long long *c_out, const int *n_dev, bool drop_adjacent) {
-  ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+                       double strain, const CellBufs &b, long long *c_out, const int *n_dev, bool drop_adjacent,
+                       const int *i0_dev) {
+  if (!i0_dev) ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   if (n > 0) {
     cell_assign_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, r_in, r_wrapped, n, le ? 1 : 0, strain, b.cellid, b.rank,
-                                                         b.cell_count, b.err, c_out, n_dev, drop_adjacent ? 1 : 0);
+                                                         b.cell_count, b.err, c_out, n_dev, drop_adjacent ? 1 : 0,
+                                                         i0_dev);
     ATLJ_LAUNCHED();
   }
   return ATLJ_OK;
@@ -391,7 +400,7 @@ __device__ __forceinline__ void sort_cell_keys(unsigned long long *k, int n) {
 constexpr int SG_CELLS = 128;
 constexpr int SG_KEYS = 3072;  // 24 KB of keys per CTA
 
-__global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int base,
+__global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int base, int block0,
                                                                     const int *__restrict__ cell_start,
                                                                     const int *__restrict__ cell_count,
                                                                     unsigned long long *__restrict__ keys,
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int b
   __shared__ unsigned long long sk[SG_KEYS];
   __shared__ int s_lo, s_hi;
   const int nown = g.n_own_cells(), first = g.first_own_cell();
-  const int c0 = blockIdx.x * SG_CELLS;
+  const int c0 = (block0 + blockIdx.x) * SG_CELLS;
   const int c = c0 + threadIdx.x;
   int mystart = 0, mycnt = 0;
   if (c < nown) {
@@ -435,19 +444,40 @@ __global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int b
 }
 
 // n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); the sort + gather
-// walks cells, not atoms, so it needs no count at all
+// walks cells, not atoms, so it needs no count at all.
+// which: 0 = everything; 1 = scatter + the blocks of cells covering the first and last owned layer (what the halo
+// messages are packed from); 2 = the remaining blocks (a slab rank runs them while the halo exchange is in flight)
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev) {
+                            const int *n_dev, int which) {
   if (n <= 0) return ATLJ_OK;
-  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in,
-                                                       b.keys);
-  ATLJ_LAUNCHED();
-  int nc = g.n_own_cells();
-  cell_sortgather_kernel<<<(nc + SG_CELLS - 1) / SG_CELLS, SG_CELLS, 0, st>>>(g, base, b.cell_start, b.cell_count,
-                                                                              b.keys, r_in, v_in, r_out, v_out, id_out);
-  ATLJ_LAUNCHED();
-  return ATLJ_OK;
+  if (which != 2) {
+    cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in,
+                                                         b.keys);
+    ATLJ_LAUNCHED();
+  }
+  const int nc = g.n_own_cells(), sc2 = g.sc * g.sc;
+  const int nblk = (nc + SG_CELLS - 1) / SG_CELLS;
+  int lo = 0, hi = nblk;  // interior blocks [lo, hi)
+  if (which != 0) {
+    lo = (sc2 + SG_CELLS - 1) / SG_CELLS;
+    hi = (nc - sc2) / SG_CELLS;
+    if (hi < lo) lo = hi = nblk;  // one or two layers: everything is boundary
+  }
+  auto run = [&](int b0, int cnt) -> int {
+    if (cnt <= 0) return ATLJ_OK;
+    cell_sortgather_kernel<<<cnt, SG_CELLS, 0, st>>>(g, base, b0, b.cell_start, b.cell_count, b.keys, r_in, v_in, r_out,
+                                                     v_out, id_out);
+    ATLJ_LAUNCHED();
+    return ATLJ_OK;
+  };
+  int rc = ATLJ_OK;
+  if (which == 0) return run(0, nblk);
+  if (which == 1) {
+    if ((rc = run(0, lo))) return rc;
+    return run(hi, nblk - hi);
+  }
+  return run(lo, hi - lo);
 }
 
 }  // namespace atlj

@@ -134,7 +134,7 @@ struct CellBufs {
 // outside the slab are skipped silently (they were packed for migration) instead of raising the index error
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
                        double strain, const CellBufs &b, long long *c_out, const int *n_dev = nullptr,
-                       bool drop_adjacent = false);
+                       bool drop_adjacent = false, const int *i0_dev = nullptr);
 // fused kick [+ sums] + kick + drift + wrap + cell assignment of the single-GPU NVE loop; returns the number of CTAs
 // (= rows of vf_partials written when first_kick) or a negative status
 // rec_vf (used when first_kick): the finished step's record: its [4], [5] = sum v^2, sum f^2 and, when pair_partials
@@ -147,7 +147,7 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev = nullptr);
+                            const int *n_dev = nullptr, int which = 0);
 
 struct PairArgs {
   const double *r;       // sorted positions (owned + halo), AoS
@@ -165,7 +165,10 @@ int launch_pair_tile(cudaStream_t st, const PairArgs &a, bool hessian);  // -> C
 int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the second-generation LJ kernel
 // -> items (= rows of partials written) or a negative status; *work_counter must be 0 on entry (launch_finalize and
 // the fused integration kernel reset it)
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);
+// xo_count < 0: all owned x layers; otherwise layers xo_first + k*xo_step, k < xo_count, rows written from row0 on
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int xo_first = 0, int xo_step = 1,
+                      int xo_count = -1, int parts = 0, int row0 = 0);
+int pair_tile2_max_parts(const Geom &g);
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)

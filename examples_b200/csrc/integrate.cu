@@ -17,7 +17,9 @@ namespace atlj {
 // vscale (device scalar, may be null) multiplies v first: pending Nose-Hoover U3 factor (md_nvt_lj.py:129).
 __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__restrict__ r, double *__restrict__ v,
                                                         const double *__restrict__ f, double half_dt, double dt,
-                                                        double box, const double *__restrict__ vscale) {
+                                                        double box, const double *__restrict__ vscale,
+                                                        const int *__restrict__ n_dev) {
+  if (n_dev) n3 = min(n3, 3ll * *n_dev);  // atom count kept on the device (slab path): n3 is an upper bound
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
   long long stride = (long long)gridDim.x * IT;
   double sc = vscale ? *vscale : 1.0;
@@ -34,7 +36,8 @@ __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__
 // md_nve_lj.py:190 + the sums of :43-45: v = v + 0.5*dt*f ; partial sum v^2, sum f^2
 __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__restrict__ v,
                                                        const double *__restrict__ f, double half_dt,
-                                                       double *__restrict__ partials) {
+                                                       double *__restrict__ partials, const int *__restrict__ n_dev) {
+  if (n_dev) n3 = min(n3, 3ll * *n_dev);
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
   long long stride = (long long)gridDim.x * IT;
   double s[2] = {0.0, 0.0};
@@ -78,17 +81,17 @@ int integ_blocks(long long n3) {
 }
 
 int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const double *f, double half_dt, double dt,
-                      double box, const double *vscale) {
+                      double box, const double *vscale, const int *n_dev) {
   if (n3 <= 0) return ATLJ_OK;
-  kick_drift_kernel<<<integ_blocks(n3), IT, 0, st>>>(n3, r, v, f, half_dt, dt, box, vscale);
+  kick_drift_kernel<<<integ_blocks(n3), IT, 0, st>>>(n3, r, v, f, half_dt, dt, box, vscale, n_dev);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }
 
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
-                     double *out2) {
+                     double *out2, const int *n_dev) {
   int nb = integ_blocks(n3);
-  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials);
+  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev);
   ATLJ_LAUNCHED();
   sums_final_kernel<<<1, 256, 0, st>>>(partials, nb, 2, out2);
   ATLJ_LAUNCHED();

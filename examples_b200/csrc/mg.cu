@@ -31,12 +31,13 @@ constexpr int HDR_INTS = 16;  // 64-byte header of every message; [0] = number o
 __host__ __device__ static inline size_t halo_counts_ints(int sc) { return (((size_t)sc * sc + 15) / 16) * 16; }
 
 // ---- phase 1: pack the atoms that left the slab ------------------------------------------------------------------
-__global__ void __launch_bounds__(256) migrate_pack_kernel(Geom g, int n, const double *__restrict__ r,
+__global__ void __launch_bounds__(256) migrate_pack_kernel(Geom g, int n, const int *__restrict__ n_dev,
+                                                           const double *__restrict__ r,
                                                            const double *__restrict__ v, const int *__restrict__ id,
                                                            unsigned char *send_left, unsigned char *send_right,
                                                            int cap, int *__restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= min(n, *n_dev)) return;
   double x = r[3 * (size_t)i];
   x = __dsub_rn(x, rint(x));
   const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(x, 0.5), (double)g.sc));  // md_lj_ll_module.py:108
@@ -66,9 +67,11 @@ __global__ void __launch_bounds__(256) migrate_pack_kernel(Geom g, int n, const 
 __global__ void __launch_bounds__(256) append_kernel(const unsigned char *__restrict__ recv_left,
                                                      const unsigned char *__restrict__ recv_right, int cap,
                                                      double *__restrict__ r, double *__restrict__ v,
-                                                     int *__restrict__ id, int n_old, long long capacity,
-                                                     int *__restrict__ n_after, int *__restrict__ err) {
+                                                     int *__restrict__ id, const int *__restrict__ n_old_dev,
+                                                     long long capacity, int *__restrict__ n_after,
+                                                     int *__restrict__ err) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_old = *n_old_dev;
   const int cl = min(*reinterpret_cast<const int *>(recv_left), cap);
   const int cr = min(*reinterpret_cast<const int *>(recv_right), cap);
   if (t == 0) {
@@ -110,10 +113,11 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, int lx, const in
 // ---- phase 3: a received layer becomes halo layer lx of the local grid ---------------------------------------------
 // cell_start of the layer = base + exclusive scan of the per-cell counts (one CTA; sc^2 <= 1024 * 64)
 __global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, int lx, const unsigned char *__restrict__ buf,
-                                                       const unsigned char *__restrict__ before, int n_own,
-                                                       int *__restrict__ cs, long long capacity, int cap,
-                                                       int *__restrict__ err) {
+                                                       const unsigned char *__restrict__ before,
+                                                       const int *__restrict__ n_own_dev, int *__restrict__ cs,
+                                                       long long capacity, int cap, int *__restrict__ err) {
   __shared__ int wsum[32];
+  const int n_own = *n_own_dev;
   const int sc2 = g.sc * g.sc;
   const int *hdr = reinterpret_cast<const int *>(buf);
   const int *cnt = hdr + HDR_INTS;
@@ -157,8 +161,10 @@ __global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, int lx, const uns
 }
 
 __global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned char *__restrict__ buf,
-                                                        const unsigned char *__restrict__ before, int n_own, int cap,
+                                                        const unsigned char *__restrict__ before,
+                                                        const int *__restrict__ n_own_dev, int cap,
                                                         long long capacity, double *__restrict__ r_sorted) {
+  const int n_own = *n_own_dev;
   const int *hdr = reinterpret_cast<const int *>(buf);
   const double *pos = reinterpret_cast<const double *>(hdr + HDR_INTS + halo_counts_ints(g.sc));
   const long long base = n_own + (before ? min(*reinterpret_cast<const int *>(before), cap) : 0);
@@ -168,7 +174,9 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned c
   for (long long e = gt; e < 3 * total; e += stride) r_sorted[3 * base + e] = pos[e];
 }
 
-__global__ void set_nown_kernel(double *rec, int n_own) { rec[11] = (double)n_own; }
+__global__ void set_nown_kernel(double *rec, const int *n_own) { rec[11] = (double)*n_own; }
+// after the sort the number of owned atoms is the end sentinel of the last owned layer
+__global__ void copy_int_kernel(int *dst, const int *src) { *dst = *src; }
 
 // ---- NCCL, bound at run time ----------------------------------------------------------------------------------------
 struct NcclApi {
@@ -231,63 +239,82 @@ static int nccl_load() {
 
 // my "to the left" message lands in the left neighbour's "from the right" buffer and vice versa.  With two ranks
 // both neighbours are the same peer; sends and receives between one pair match in order, hence recv right first.
-static int exchange(atlj_sim *s, unsigned char *const send[2], unsigned char *const recv[2], size_t bytes) {
+static int exchange(atlj_sim *s, cudaStream_t st, unsigned char *const send[2], unsigned char *const recv[2],
+                    size_t bytes) {
   MgState &m = s->mg;
   ncclComm_t comm = (ncclComm_t)m.comm;
   ATLJ_NCCL(g_nccl.GroupStart());
-  ATLJ_NCCL(g_nccl.Send(send[0], bytes, ncclChar, m.left, comm, s->st));
-  ATLJ_NCCL(g_nccl.Send(send[1], bytes, ncclChar, m.right, comm, s->st));
-  ATLJ_NCCL(g_nccl.Recv(recv[1], bytes, ncclChar, m.right, comm, s->st));
-  ATLJ_NCCL(g_nccl.Recv(recv[0], bytes, ncclChar, m.left, comm, s->st));
+  ATLJ_NCCL(g_nccl.Send(send[0], bytes, ncclChar, m.left, comm, st));
+  ATLJ_NCCL(g_nccl.Send(send[1], bytes, ncclChar, m.right, comm, st));
+  ATLJ_NCCL(g_nccl.Recv(recv[1], bytes, ncclChar, m.right, comm, st));
+  ATLJ_NCCL(g_nccl.Recv(recv[0], bytes, ncclChar, m.left, comm, st));
   ATLJ_NCCL(g_nccl.GroupEnd());
   return ATLJ_OK;
 }
 
 // ---- the three phases ---------------------------------------------------------------------------------------------------
+// The number of owned atoms changes every step and lives on the device (cnt_dev[1]); kernels are launched over the
+// capacity and read it, so a step needs no host synchronisation.  The host copy s->n is refreshed at the end of a run.
 static int phase1(atlj_sim *s, double dt) {
   int rc;
   MgState &m = s->mg;
-  const int n = (int)s->n;
+  const int nup = (int)s->cap;
+  const int *n_dev = m.cnt_dev + 1;
   Timer::begin(s, 2);
-  if ((rc = launch_kick_drift(s->st, 3ll * n, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box, nullptr)))
+  if ((rc = launch_kick_drift(s->st, 3ll * nup, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box, nullptr,
+                              n_dev)))
     return rc;
   Timer::end(s);
   Timer::begin(s, 3);
   ATLJ_CUDA(cudaMemsetAsync(m.mig_send[0], 0, sizeof(int) * HDR_INTS, s->st));
   ATLJ_CUDA(cudaMemsetAsync(m.mig_send[1], 0, sizeof(int) * HDR_INTS, s->st));
-  if (n > 0) {
-    migrate_pack_kernel<<<(n + 255) / 256, 256, 0, s->st>>>(s->g, n, s->r[s->cur], s->v[s->cur], s->id[s->cur],
-                                                            m.mig_send[0], m.mig_send[1], (int)m.mig_cap, s->cb.err);
-    ATLJ_LAUNCHED();
-  }
+  migrate_pack_kernel<<<(nup + 255) / 256, 256, 0, s->st>>>(s->g, nup, n_dev, s->r[s->cur], s->v[s->cur],
+                                                            s->id[s->cur], m.mig_send[0], m.mig_send[1],
+                                                            (int)m.mig_cap, s->cb.err);
+  ATLJ_LAUNCHED();
   Timer::end(s);
   return ATLJ_OK;
 }
 
-static int phase2(atlj_sim *s) {
+// phase 2 in three pieces so that the two exchanges can hide behind independent work:
+//   2a  cell assignment of the atoms already held (leavers are skipped)          -- overlaps the migration exchange
+//   2b  arrivals appended and assigned, scan, scatter, sort+gather of the blocks of cells that cover the first and
+//       last owned layer, halo messages packed
+//   2c  sort+gather of the remaining (interior) blocks                            -- overlaps the halo exchange
+static int phase2a(atlj_sim *s) {
+  MgState &m = s->mg;
+  Timer::begin(s, 1);
+  int rc = launch_cell_assign(s->st, s->g, s->r[s->cur], s->r[s->cur], (int)s->cap, false, 0.0, s->cb, nullptr,
+                              m.cnt_dev + 1, true);
+  Timer::end(s);
+  return rc;
+}
+
+static int phase2b(atlj_sim *s) {
   int rc;
   MgState &m = s->mg;
-  const int n_old = (int)s->n, cap = (int)m.mig_cap;
+  const int cap = (int)m.mig_cap, nup = (int)s->cap;
   const int cur = s->cur, alt = 1 - cur;
   Timer::begin(s, 3);
   append_kernel<<<(2 * cap + 255) / 256, 256, 0, s->st>>>(m.mig_recv[0], m.mig_recv[1], cap, s->r[cur], s->v[cur],
-                                                         s->id[cur], n_old, (long long)s->cap, m.cnt_dev, s->cb.err);
+                                                         s->id[cur], m.cnt_dev + 1, (long long)s->cap, m.cnt_dev,
+                                                         s->cb.err);
   ATLJ_LAUNCHED();
+  if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], 2 * cap, false, 0.0, s->cb, nullptr, m.cnt_dev, true,
+                               m.cnt_dev + 1)))
+    return rc;
   Timer::end(s);
-  long long n_up = (long long)n_old + 2ll * cap;
-  if (n_up > s->cap) n_up = s->cap;
   Timer::begin(s, 1);
-  if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], (int)n_up, false, 0.0, s->cb, nullptr, m.cnt_dev,
-                               true)))
-    return rc;
   if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
-  if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, (int)n_up, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
-                                    s->v[alt], s->id[alt], m.cnt_dev)))
+  if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, nup, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
+                                    s->id[alt], m.cnt_dev, 1)))
     return rc;
   Timer::end(s);
-  s->cur = alt;
-  Timer::begin(s, 3);
+  Timer::begin(s, 5);
   const int sc2 = s->g.sc * s->g.sc;
+  copy_int_kernel<<<1, 1, 0, s->st>>>(m.cnt_dev + 1,
+                                      s->cb.cell_start + (size_t)(s->g.h + s->g.nx_own - 1) * (sc2 + 1) + sc2);
+  ATLJ_LAUNCHED();
   const int blocks = 148 * 2;
   halo_pack_kernel<<<blocks, 256, 0, s->st>>>(s->g, s->g.h, s->cb.cell_start, s->r[alt], m.halo_send[0],
                                               (int)m.halo_cap, s->cb.err);
@@ -295,57 +322,87 @@ static int phase2(atlj_sim *s) {
   halo_pack_kernel<<<blocks, 256, 0, s->st>>>(s->g, s->g.h + s->g.nx_own - 1, s->cb.cell_start, s->r[alt],
                                               m.halo_send[1], (int)m.halo_cap, s->cb.err);
   ATLJ_LAUNCHED();
-  // the one host synchronisation of a step: the new number of owned atoms (end sentinel of the last owned layer)
-  const int *n_own_dev = s->cb.cell_start + (size_t)(s->g.h + s->g.nx_own - 1) * (sc2 + 1) + sc2;
-  ATLJ_CUDA(cudaMemcpyAsync(m.cnt_host, n_own_dev, sizeof(int), cudaMemcpyDeviceToHost, s->st));
-  ATLJ_CUDA(cudaMemcpyAsync(m.cnt_host + 4, s->cb.err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
-  ATLJ_CUDA(cudaStreamSynchronize(s->st));
   Timer::end(s);
-  if (m.cnt_host[4] || m.cnt_host[5]) return sim_check_flags(s);
-  s->n = m.cnt_host[0];
   return ATLJ_OK;
 }
 
+static int phase2c(atlj_sim *s) {
+  const int cur = s->cur, alt = 1 - cur;
+  Timer::begin(s, 1);
+  int rc = launch_cell_sort_gather(s->st, s->g, s->cb, (int)s->cap, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
+                                   s->v[alt], s->id[alt], s->mg.cnt_dev, 2);
+  Timer::end(s);
+  s->cur = alt;
+  return rc;
+}
+
+// the received layers become the halo layers 0 and nxl-1 of the local grid, behind the owned atoms
+static int unpack_halos(atlj_sim *s, cudaStream_t st) {
+  MgState &m = s->mg;
+  const Geom &g = s->g;
+  const int *n_dev = m.cnt_dev + 1;
+  halo_cs_kernel<<<1, 1024, 0, st>>>(g, 0, m.halo_recv[0], nullptr, n_dev, s->cb.cell_start, (long long)s->cap,
+                                     (int)m.halo_cap, s->cb.err);
+  ATLJ_LAUNCHED();
+  halo_cs_kernel<<<1, 1024, 0, st>>>(g, g.nxl - 1, m.halo_recv[1], m.halo_recv[0], n_dev, s->cb.cell_start,
+                                     (long long)s->cap, (int)m.halo_cap, s->cb.err);
+  ATLJ_LAUNCHED();
+  halo_copy_kernel<<<148, 256, 0, st>>>(g, m.halo_recv[0], nullptr, n_dev, (int)m.halo_cap, (long long)s->cap,
+                                        s->r[1 - s->cur]);
+  ATLJ_LAUNCHED();
+  halo_copy_kernel<<<148, 256, 0, st>>>(g, m.halo_recv[1], m.halo_recv[0], n_dev, (int)m.halo_cap, (long long)s->cap,
+                                        s->r[1 - s->cur]);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+
+// emulation path: phase 2c has already swapped the buffers, so "alt" of unpack_halos is the current one
+static int unpack_halos_current(atlj_sim *s) {
+  s->cur = 1 - s->cur;
+  int rc = unpack_halos(s, s->st);
+  s->cur = 1 - s->cur;
+  return rc;
+}
+
+static PairArgs pair_args(atlj_sim *s) {
+  PairArgs a;
+  a.r = s->r[s->cur], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
+  a.f = s->f, a.partials = s->partials, a.g = s->g, a.p = s->p;
+  a.p.strain = 0.0, a.p.shift = 0;
+  return a;
+}
+
+// pair kernel over the owned rows (the halos are in place) + kick + local sums
 static int phase3(atlj_sim *s, double dt, double *rec) {
   int rc;
   MgState &m = s->mg;
-  const int n = (int)s->n, cur = s->cur;
-  const Geom &g = s->g;
   ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));
-  Timer::begin(s, 3);
-  halo_cs_kernel<<<1, 1024, 0, s->st>>>(g, 0, m.halo_recv[0], nullptr, n, s->cb.cell_start, (long long)s->cap,
-                                        (int)m.halo_cap, s->cb.err);
-  ATLJ_LAUNCHED();
-  halo_cs_kernel<<<1, 1024, 0, s->st>>>(g, g.nxl - 1, m.halo_recv[1], m.halo_recv[0], n, s->cb.cell_start,
-                                        (long long)s->cap, (int)m.halo_cap, s->cb.err);
-  ATLJ_LAUNCHED();
-  halo_copy_kernel<<<148, 256, 0, s->st>>>(g, m.halo_recv[0], nullptr, n, (int)m.halo_cap, (long long)s->cap, s->r[cur]);
-  ATLJ_LAUNCHED();
-  halo_copy_kernel<<<148, 256, 0, s->st>>>(g, m.halo_recv[1], m.halo_recv[0], n, (int)m.halo_cap, (long long)s->cap,
-                                           s->r[cur]);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  PairArgs a;
-  a.r = s->r[cur];
-  a.fin = nullptr;
-  a.cell_start = s->cb.cell_start;
-  a.cell_count = s->cb.cell_count;
-  a.f = s->f;
-  a.partials = s->partials;
-  a.g = g;
-  a.p = s->p;
-  a.p.strain = 0.0, a.p.shift = 0;
+  const PairArgs a = pair_args(s);
   Timer::begin(s, 0);
-  int nb = (s->pair_kernel == 0 && a.p.model == ATLJ_MODEL_LJ) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
-                                                               : launch_pair_tile(s->st, a, false);
+  const int nb = (s->pair_kernel == 0 && a.p.model == ATLJ_MODEL_LJ) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
+                                                                   : launch_pair_tile(s->st, a, false);
   Timer::end(s);
   if (nb < 0) return nb;
   if ((rc = launch_finalize(s->st, s->partials, nb, a.p.model, false, rec, s->cb.err + 2))) return rc;
   Timer::begin(s, 2);
-  if ((rc = launch_kick_sums(s->st, 3ll * n, s->v[cur], s->f, 0.5 * dt, s->partials, rec + 4))) return rc;
-  set_nown_kernel<<<1, 1, 0, s->st>>>(rec, n);
+  if ((rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, m.cnt_dev + 1)))
+    return rc;
+  set_nown_kernel<<<1, 1, 0, s->st>>>(rec, m.cnt_dev + 1);
   ATLJ_LAUNCHED();
   Timer::end(s);
+  return ATLJ_OK;
+}
+
+// host copy of the owned count <-> device
+static int push_n(atlj_sim *s) {
+  s->mg.cnt_host[0] = (int)s->n;
+  ATLJ_CUDA(cudaMemcpyAsync(s->mg.cnt_dev + 1, s->mg.cnt_host, sizeof(int), cudaMemcpyHostToDevice, s->st));
+  return ATLJ_OK;
+}
+static int pull_n(atlj_sim *s) {
+  ATLJ_CUDA(cudaMemcpyAsync(s->mg.cnt_host, s->mg.cnt_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  s->n = s->mg.cnt_host[0];
   return ATLJ_OK;
 }
 
@@ -359,6 +416,8 @@ static void mg_free(atlj_sim *s) {
   m.cnt_dev = nullptr;
   if (m.cnt_host) cudaFreeHost(m.cnt_host);
   m.cnt_host = nullptr;
+  if (m.st2) cudaStreamDestroy(m.st2), cudaEventDestroy(m.e1), cudaEventDestroy(m.e2);
+  m.st2 = nullptr;
   if (m.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m.comm);
   m.comm = nullptr;
   m.on = false;
@@ -398,8 +457,15 @@ int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap) {
   ATLJ_CUDA(cudaMalloc((void **)&m.cnt_dev, 16 * sizeof(int)));
   ATLJ_CUDA(cudaMemsetAsync(m.cnt_dev, 0, 16 * sizeof(int), s->st));
   ATLJ_CUDA(cudaHostAlloc((void **)&m.cnt_host, 16 * sizeof(int), cudaHostAllocDefault));
+  {
+    int lo = 0, hi = 0;
+    ATLJ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ATLJ_CUDA(cudaStreamCreateWithPriority(&m.st2, cudaStreamNonBlocking, hi));  // exchanges get SM slots first
+  }
+  ATLJ_CUDA(cudaEventCreateWithFlags(&m.e1, cudaEventDisableTiming));
+  ATLJ_CUDA(cudaEventCreateWithFlags(&m.e2, cudaEventDisableTiming));
   m.on = true;
-  return ATLJ_OK;
+  return push_n(s);
 }
 
 /* which: 0/1 migration send left/right, 2/3 migration recv from left/right, 4/5 halo send left/right,
@@ -425,20 +491,22 @@ void atlj_sim_set_total(atlj_sim *s, int64_t n_total) {
 
 int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
   if (!s || !s->mg.on) return ATLJ_ERR_ARG;
-  int rc = phase1(s, dt);
-  if (rc) return rc;
+  int rc = push_n(s);
+  if (rc || (rc = phase1(s, dt))) return rc;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
   return ATLJ_OK;
 }
 int atlj_sim_mg_phase2(atlj_sim *s) {
   if (!s || !s->mg.on) return ATLJ_ERR_ARG;
-  return phase2(s);
+  int rc = phase2a(s);
+  if (rc || (rc = phase2b(s)) || (rc = phase2c(s)) || (rc = pull_n(s))) return rc;
+  return sim_check_flags(s);
 }
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
   if (!s || !s->mg.on) return ATLJ_ERR_ARG;
   int rc = sim_ensure_rec(s, 1);
   if (rc) return rc;
-  if ((rc = phase3(s, dt, s->rec_dev))) return rc;
+  if ((rc = unpack_halos_current(s)) || (rc = phase3(s, dt, s->rec_dev))) return rc;
   return sim_copy_rec(s, rec_host, 1);
 }
 
@@ -473,22 +541,47 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
   if (rc) return rc;
   MgState &m = s->mg;
+  if ((rc = push_n(s))) return rc;
+  // Per step, main stream | second (high-priority) stream:
+  //   kick, drift, pack leavers        |
+  //   assign the atoms already held    | migration exchange
+  //   append + assign arrivals, scan, sort boundary blocks, pack halos
+  //   sort interior blocks             | halo exchange, unpack
+  //   pair kernel, finalize, kick      |
+  // The NCCL kernels need a few free SM slots, which the saturating pair kernel never leaves, so the exchanges are
+  // hidden behind the short-lived cell-build kernels instead (measured: behind the pair kernel they simply wait).
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     if ((rc = phase1(s, dt))) return rc;
-    Timer::begin(s, 3);
-    if ((rc = exchange(s, m.mig_send, m.mig_recv, m.mig_bytes))) return rc;
-    Timer::end(s);
-    if ((rc = phase2(s))) return rc;
-    Timer::begin(s, 3);
-    if ((rc = exchange(s, m.halo_send, m.halo_recv, m.halo_bytes))) return rc;
-    Timer::end(s);
+    ATLJ_CUDA(cudaEventRecord(m.e1, s->st));
+    ATLJ_CUDA(cudaStreamWaitEvent(m.st2, m.e1, 0));
+    Timer::begin(s, 4, m.st2, true);
+    if ((rc = exchange(s, m.st2, m.mig_send, m.mig_recv, m.mig_bytes))) return rc;
+    Timer::end(s, m.st2, true);
+    ATLJ_CUDA(cudaEventRecord(m.e2, m.st2));
+    if ((rc = phase2a(s))) return rc;
+    ATLJ_CUDA(cudaStreamWaitEvent(s->st, m.e2, 0));
+    if ((rc = phase2b(s))) return rc;
+    ATLJ_CUDA(cudaEventRecord(m.e1, s->st));
+    ATLJ_CUDA(cudaStreamWaitEvent(m.st2, m.e1, 0));
+    Timer::begin(s, 6, m.st2, true);
+    if ((rc = exchange(s, m.st2, m.halo_send, m.halo_recv, m.halo_bytes))) return rc;
+    if ((rc = unpack_halos(s, m.st2))) return rc;  // writes behind the owned atoms of r[alt]; 2c swaps cur
+    Timer::end(s, m.st2, true);
+    ATLJ_CUDA(cudaEventRecord(m.e2, m.st2));
+    if ((rc = phase2c(s))) return rc;
+    ATLJ_CUDA(cudaStreamWaitEvent(s->st, m.e2, 0));
     if ((rc = phase3(s, dt, rec))) return rc;
+  }
+  // the records are read on the host only now: ONE all-reduce for all steps
+  if (nsteps > 0) {
     Timer::begin(s, 3);
-    ATLJ_NCCL(g_nccl.AllReduce(rec, rec, ATLJ_NREC, ncclDouble, ncclSum, (ncclComm_t)m.comm, s->st));
+    ATLJ_NCCL(g_nccl.AllReduce(s->rec_dev, s->rec_dev, (size_t)nsteps * ATLJ_NREC, ncclDouble, ncclSum,
+                               (ncclComm_t)m.comm, s->st));
     Timer::end(s);
   }
   s->step_count += nsteps;
+  if ((rc = pull_n(s))) return rc;
   rc = sim_copy_rec(s, rec_host, nsteps);
   if (rec_host)
     for (int k = 0; k < nsteps; k++)

@@ -43,7 +43,9 @@ int pair_tile2_parts(const Geom &g) {
   int want = (148 * 4 * 8 + rows2 - 1) / rows2;  // ~8 items per resident CTA (measured best at 2 M atoms)
   return want < 1 ? 1 : (want > maxp ? maxp : want);
 }
-int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * pair_tile2_parts(g); }
+int pair_tile2_max_parts(const Geom &g) { return g.sc / 4 < 1 ? 1 : g.sc / 4; }
+// upper bound of the partial rows any combination of launches over this geometry writes
+int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * pair_tile2_max_parts(g); }
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
@@ -102,7 +104,8 @@ __device__ __forceinline__ double rcp46(double s) {
   } while (0)
 
 __global__ void __launch_bounds__(U_NT, 4)
-    pair_tile2_kernel(PairArgs a, int parts, int nyb, int nitems, int *__restrict__ work_counter) {
+    pair_tile2_kernel(PairArgs a, int parts, int nyb, int nitems, int *__restrict__ work_counter, int xo_first,
+                      int xo_step, int row0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
   double *uy = ux + U_CAP;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(U_NT, 4)
     const int item = s_item;
     if (item >= nitems) break;
     const int part = item % parts, t2 = item / parts;
-    const int yb = t2 % nyb, xo = t2 / nyb;
+    const int yb = t2 % nyb, xo = xo_first + (t2 / nyb) * xo_step;  // owned x layer of this item
     const int lx = g.h + xo, y0 = 2 * yb;
     const bool two = (y0 + 1 < sc);
     const int zA = (int)((long long)sc * part / parts), zB = (int)((long long)sc * (part + 1) / parts);
@@ -452,11 +455,15 @@ __global__ void __launch_bounds__(U_NT, 4)
       acc.np = npf;
       acc.ovr = ovr;
     }
-    block_store_partials<U_NT / 32>(acc, a.partials + 8 * (size_t)item);
+    block_store_partials<U_NT / 32>(acc, a.partials + 8 * (size_t)(row0 + item));
   }
 }
 
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
+// The owned x layers xo_first, xo_first + xo_step, ... (xo_count of them; default = all) are processed; partial rows
+// are written from row0 on.  A slab rank launches its interior layers while the halo is still in flight and the two
+// boundary layers afterwards.  parts <= 0 selects the default split of the rows along z.
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int xo_first, int xo_step, int xo_count,
+                      int parts, int row0) {
   static int grid = 0;
   const size_t smem = tile2_smem_bytes();
   if (grid == 0) {
@@ -467,10 +474,13 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
     ATLJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     grid = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  const int parts = pair_tile2_parts(a.g);
+  if (xo_count < 0) xo_first = 0, xo_step = 1, xo_count = a.g.nx_own;
+  if (xo_count == 0) return 0;
+  if (parts <= 0) parts = pair_tile2_parts(a.g);
   const int nyb = (a.g.sc + 1) / 2;
-  const int nitems = a.g.nx_own * nyb * parts;
-  pair_tile2_kernel<<<grid < nitems ? grid : nitems, U_NT, smem, st>>>(a, parts, nyb, nitems, work_counter);
+  const int nitems = xo_count * nyb * parts;
+  pair_tile2_kernel<<<grid < nitems ? grid : nitems, U_NT, smem, st>>>(a, parts, nyb, nitems, work_counter, xo_first,
+                                                                     xo_step, row0);
   ATLJ_LAUNCHED();
   return nitems;
 }

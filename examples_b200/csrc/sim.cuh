@@ -12,9 +12,11 @@ struct MgState {
   size_t mig_bytes = 0, halo_bytes = 0;
   unsigned char *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};    // [0] left, [1] right
   unsigned char *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // recv[0] = from the left
-  int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended
-  int *cnt_host = nullptr;  // pinned: [0] owned atoms after the sort, [4..7] error flags
+  int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended, [1] owned atoms (after the sort)
+  int *cnt_host = nullptr;  // pinned mirror of cnt_dev[1]
   void *comm = nullptr;     // ncclComm_t
+  cudaStream_t st2 = nullptr;  // halo exchange + boundary layers, concurrent with the interior pair kernel
+  cudaEvent_t e1 = nullptr, e2 = nullptr;
 };
 
 struct atlj_sim {
@@ -53,14 +55,17 @@ struct atlj_sim {
     cudaEvent_t e0, e1;
     int cat;
   };
+  std::vector<Ev> ev_open2;  // brackets open on the second stream
   std::vector<cudaEvent_t> ev_free;
   std::vector<Ev> ev_open, ev_done;
 };
 
 namespace atlj {
 struct Timer {
-  static void begin(atlj_sim *s, int cat);  // cat: 0 pair, 1 cells, 2 integrate, 3 other
-  static void end(atlj_sim *s);
+  // cat: 0 pair, 1 cells, 2 integrate, 3 other, 4 migration exchange, 5 halo pack, 6 halo exchange + unpack,
+  // 7 boundary pair; st = the stream the bracketed work runs on (default: the sim's stream)
+  static void begin(atlj_sim *s, int cat, cudaStream_t st = nullptr, bool other_stream = false);
+  static void end(atlj_sim *s, cudaStream_t st = nullptr, bool other_stream = false);
 };
 int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs);
 int sim_check_flags(atlj_sim *s);

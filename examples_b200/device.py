@@ -173,6 +173,7 @@ class Simulation:
     def timing(self):
         """Accumulated device milliseconds {pair, cells, integrate, other} since the last call (CUDA events on
         the launching stream)."""
-        ms = np.zeros(4)
+        ms = np.zeros(8)
         _lib.check(_lib.lib().atlj_sim_timing(self._h, ms))
-        return dict(pair=ms[0], cells=ms[1], integrate=ms[2], other=ms[3])
+        return dict(pair=ms[0], cells=ms[1], integrate=ms[2], other=ms[3], mig_exchange=ms[4], halo_pack=ms[5],
+                    halo_exchange=ms[6], pair_boundary=ms[7])

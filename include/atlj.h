@@ -186,7 +186,9 @@ int atlj_measure_fp64_peak(double *flops_per_s);
 /* Device time (ms) of the most recent pair-kernel / cell-build / integration launches, by CUDA events
  * recorded on the sim's stream when timing is enabled. */
 int atlj_sim_enable_timing(atlj_sim *s, int on);
-int atlj_sim_timing(atlj_sim *s, double ms[4]); /* accumulated {pair, cells, integrate, other} ms; resets */
+/* accumulated ms, then reset: {pair, cells, integrate, other, migration exchange, halo pack, halo exchange + unpack
+ * (second stream), boundary-layer pair kernel (second stream)}; the last four are used by the slab path only */
+int atlj_sim_timing(atlj_sim *s, double ms[8]);
 
 #ifdef __cplusplus
 }
