@@ -78,11 +78,13 @@ def lib():
     L.atlj_sim_mg_phase1.argtypes = [_vp, C.c_double]
     L.atlj_sim_mg_phase2.argtypes = [_vp]
     L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]
-    L.atlj_sim_mg_buffer.restype = _vp
-    L.atlj_sim_mg_buffer.argtypes = [_vp, C.c_int]
-    L.atlj_sim_mg_buffer_bytes.restype = C.c_int64
-    L.atlj_sim_mg_buffer_bytes.argtypes = [_vp, C.c_int]
-    L.atlj_device_copy.argtypes = [_vp, _vp, C.c_int64]
+    L.atlj_sim_mg_arena.restype = _vp
+    L.atlj_sim_mg_arena.argtypes = [_vp]
+    L.atlj_sim_mg_arena_bytes.restype = C.c_int64
+    L.atlj_sim_mg_arena_bytes.argtypes = [_vp]
+    L.atlj_sim_mg_set_peers.argtypes = [_vp, _vp, _vp]
+    L.atlj_sim_mg_ipc_handle.argtypes = [_vp, C.c_char_p]
+    L.atlj_sim_mg_ipc_open.argtypes = [_vp, C.c_char_p, C.c_char_p]
     L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
     L.atlj_host_alloc.restype = _vp
     L.atlj_host_alloc.argtypes = [C.c_int64]

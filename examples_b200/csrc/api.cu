@@ -497,7 +497,6 @@ int atlj_sim_enable_timing(atlj_sim *s, int on) {
 int atlj_sim_timing(atlj_sim *s, double ms[8]) {
   if (!s) return ATLJ_ERR_ARG;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
-  if (s->mg.st2) ATLJ_CUDA(cudaStreamSynchronize(s->mg.st2));
   for (int k = 0; k < 8; k++) ms[k] = 0.0;
   for (auto &t : s->ev_done) {
     float m = 0.f;

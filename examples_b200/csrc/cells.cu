@@ -103,10 +103,14 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
                                                         int *__restrict__ err, double *__restrict__ partials,
                                                         double *__restrict__ rec_vf,
                                                         const double *__restrict__ pair_partials, int pair_rows,
-                                                        int model) {
+                                                        int model, SlabArgs sl) {
   // tiles of IT atoms: the 3*IT components are streamed with perfectly coalesced accesses (one component per thread
-  // and pass), the wrapped coordinates are parked in shared memory, then one thread per atom does the integer part
+  // and pass), the wrapped coordinates (and, on a slab, the velocities) are parked in shared memory, then one thread
+  // per atom does the integer part
   __shared__ double xs[3 * IT];
+  __shared__ double vs[3 * IT];
+  const bool slab = sl.to_left != nullptr;
+  if (sl.n_dev) n = min(n, *sl.n_dev);
   double s[2] = {0.0, 0.0};
   const double scd = (double)g.sc;
   const int ntiles = (n + IT - 1) / IT;
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
         v[e] = vv;
         r[e] = x;
         xs[l] = x;
+        if (slab) vs[l] = vv;
       }
     }
     __syncthreads();
@@ -140,12 +145,35 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
       const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(w0, 0.5), scd));  // md_lj_ll_module.py:108
       const long long c1 = (long long)floor(__dmul_rn(__dadd_rn(w1, 0.5), scd));
       const long long c2 = (long long)floor(__dmul_rn(__dadd_rn(w2, 0.5), scd));
-      const bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc;  // :109
+      bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc;  // :109
+      const bool foreign = !bad && (c0 < g.x_lo || c0 >= g.x_lo + g.nx_own);
+      if (foreign) {
+        // the atom left the slab: hand it (r, v, id) to the neighbour, straight into its receive buffer
+        const int left = g.x_lo == 0 ? g.sc - 1 : g.x_lo - 1;
+        const int right = g.x_lo + g.nx_own == g.sc ? 0 : g.x_lo + g.nx_own;
+        const int dir = !slab ? -1 : (c0 == left ? 0 : (c0 == right ? 1 : -1));
+        if (dir < 0) {
+          bad = true;  // single domain: cannot happen; slab: moved more than one layer in a step
+        } else {
+          const int slot = atomicAdd(&sl.mig_cnt[dir], 1);
+          if (slot >= sl.mig_cap) {
+            atomicOr(&err[1], 1);
+          } else {
+            double *d = reinterpret_cast<double *>((dir ? sl.to_right : sl.to_left) + 64) + 7 * (size_t)slot;
+            d[0] = w0, d[1] = w1, d[2] = w2;
+            d[3] = vs[3 * threadIdx.x], d[4] = vs[3 * threadIdx.x + 1], d[5] = vs[3 * threadIdx.x + 2];
+            d[6] = (double)sl.id[i];
+            __threadfence_system();
+          }
+          cellid[i] = -1;
+          rank[i] = 0;
+        }
+      }
       if (bad) {
         atomicOr(&err[0], 1);
         cellid[i] = -1;
         rank[i] = 0;
-      } else {
+      } else if (!foreign) {
         const int cid = (((int)c0 + g.h - g.x_lo) * g.sc + (int)c1) * g.sc + (int)c2;
         cellid[i] = cid;
         rank[i] = atomicAdd(&cell_count[cid], 1);
@@ -153,19 +181,21 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
     }
     __syncthreads();
   }
-  if (!first_kick) return;
-  // ---- finish the record of the step that just ended -----------------------------------------------------------------
+  if (!first_kick && !slab) return;
+  // ---- finish the record of the step that just ended; publish the migration messages ------------------------------
   // level 1: this CTA's {sum v^2, sum f^2} and its fixed slice of the pair kernel's per-item rows -> one row of 12
   // level 2: the CTA that finishes last sums the rows in fixed order and writes the record (deterministic)
   constexpr int ROW = 12;
-  block_reduce_store<2>(s, partials + ROW * (size_t)blockIdx.x);
-  if (threadIdx.x >= 32 && threadIdx.x < 39) {
-    const int k = threadIdx.x - 32;
-    const int r0 = (int)((long long)pair_rows * blockIdx.x / gridDim.x);
-    const int r1 = (int)((long long)pair_rows * (blockIdx.x + 1) / gridDim.x);
-    double t = 0.0;
-    for (int b = r0; b < r1; b++) t += pair_partials[8 * (size_t)b + k];
-    partials[ROW * (size_t)blockIdx.x + 2 + k] = t;
+  if (first_kick) {
+    block_reduce_store<2>(s, partials + ROW * (size_t)blockIdx.x);
+    if (threadIdx.x >= 32 && threadIdx.x < 39) {
+      const int k = threadIdx.x - 32;
+      const int r0 = (int)((long long)pair_rows * blockIdx.x / gridDim.x);
+      const int r1 = (int)((long long)pair_rows * (blockIdx.x + 1) / gridDim.x);
+      double t = 0.0;
+      for (int b = r0; b < r1; b++) t += pair_partials[8 * (size_t)b + k];
+      partials[ROW * (size_t)blockIdx.x + 2 + k] = t;
+    }
   }
   __shared__ int s_last;
   __shared__ double fin[IT / 32][9];
@@ -175,42 +205,56 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) t[k] += __ldcg(partials + ROW * (size_t)b + k);
-  }
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) fin[threadIdx.x >> 5][k] = t[k];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < 9; k++) {
-      double a = 0.0;
-      for (int w = 0; w < IT / 32; w++) a += fin[w][k];
-      t[k] = a;
+  if (slab && threadIdx.x == 0) {
+    // header: [0] = number of atoms, [1] = step stamp, released at system scope after the count
+    for (int dir = 0; dir < 2; dir++) {
+      int *hdr = reinterpret_cast<int *>(dir ? sl.to_right : sl.to_left);
+      hdr[0] = min(atomicAdd(&sl.mig_cnt[dir], 0), sl.mig_cap);
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(sl.stamp) : "memory");
+      sl.mig_cnt[dir] = 0;
     }
-    rec_vf[4] = t[0], rec_vf[5] = t[1];
-    if (pair_partials) finalize_totals(t + 2, model, false, rec_vf);
-    err[4] = 0;
-    err[2] = 0;  // work counter of the tiled pair kernel
   }
+  if (first_kick) {
+    double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) t[k] += __ldcg(partials + ROW * (size_t)b + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) fin[threadIdx.x >> 5][k] = t[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 9; k++) {
+        double a = 0.0;
+        for (int w = 0; w < IT / 32; w++) a += fin[w][k];
+        t[k] = a;
+      }
+      rec_vf[4] = t[0], rec_vf[5] = t[1];
+      if (pair_partials) finalize_totals(t + 2, model, false, rec_vf);
+      err[2] = 0;  // work counter of the tiled pair kernel
+    }
+  }
+  if (threadIdx.x == 0) err[4] = 0;
 }
 
 // -> number of CTAs (= rows of vf partials written when first_kick)
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
-                      const double *pair_partials, int pair_rows, int model) {
+                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab) {
   ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   const int nb = integ_blocks(n);
+  SlabArgs sl = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
+  if (slab) sl = *slab;
   kdk_assign_kernel<<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, first_kick ? 1 : 0, b.cellid, b.rank,
-                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model);
+                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model, sl);
   ATLJ_LAUNCHED();
   return nb;
 }

@@ -135,13 +135,21 @@ struct CellBufs {
 int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, double *r_wrapped, int n, bool le,
                        double strain, const CellBufs &b, long long *c_out, const int *n_dev = nullptr,
                        bool drop_adjacent = false, const int *i0_dev = nullptr);
-// fused kick [+ sums] + kick + drift + wrap + cell assignment of the single-GPU NVE loop; returns the number of CTAs
+// slab extras of the fused integration kernel (all null / 0 on a single GPU)
+struct SlabArgs {
+  const int *n_dev;                  // owned atoms, kept on the device (n is then an upper bound)
+  const int *id;                     // global ids of the atoms held
+  unsigned char *to_left, *to_right; // the neighbours' migration buffers (peer memory): leavers are packed into them
+  int mig_cap, stamp;                // atoms per message; stamp published in the header when the message is complete
+  int *mig_cnt;                      // [0], [1] slot counters
+};
+// fused kick [+ sums] + kick + drift + wrap + cell assignment of the NVE loop; returns the number of CTAs
 // (= rows of vf_partials written when first_kick) or a negative status
 // rec_vf (used when first_kick): the finished step's record: its [4], [5] = sum v^2, sum f^2 and, when pair_partials
 // is given, the pair kernel's totals (per-item rows reduced in fixed order) are written by the kernel's last CTA
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
-                      const double *pair_partials, int pair_rows, int model);
+                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab = nullptr);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays

@@ -4,18 +4,24 @@
 // this path is the single-domain result on the same configuration.  Each rank owns a contiguous range of x cell
 // layers [x_lo, x_hi) of the reference's cell grid (md_lj_ll_module.py:106-109) and keeps one halo layer on each side.
 // One velocity-Verlet step (md_nve_lj.py:178-192) is
-//   phase 1  kick + drift + wrap on the owned atoms; atoms that left the slab are packed (r, v, id) for the neighbour
-//            -> exchange 1 (migration, tens of atoms per face)
-//   phase 2  arrivals appended, owned atoms binned and sorted (same counting sort as the single-GPU path), first and
-//            last owned layer packed: per-cell counts + positions, already in cell order
-//            -> exchange 2 (halo, one layer of positions per face: ~1.5e5 atoms = 3.5 MB at 16 M atoms / 8 GPUs)
+//   phase 1  kick + drift + wrap on the owned atoms; atoms that left the slab are packed (r, v, id) STRAIGHT INTO THE
+//            NEIGHBOUR'S receive buffer over NVLink (tens of atoms per face)
+//   phase 2  cell assignment of the atoms already held; arrivals appended and assigned; scan; counting sort; the
+//            first and last owned layer are packed -- per-cell counts + positions, already in cell order -- again
+//            straight into the neighbours' receive buffers (one layer per face: ~6e4 atoms = 1.4 MB at 2 M atoms/GPU)
 //   phase 3  halo layers unpacked behind the owned atoms ([owned | left halo | right halo]; the per-layer sentinels of
 //            the padded cell_start make that legal), full-stencil pair kernel on the owned rows (no force return
-//            traffic), kick, local sums -> all-reduce of the 12-double step record.
-// Transport: NCCL point-to-point send/recv on the sim's stream (NVLink 5 / NVSwitch), bound at run time with dlopen so
-// that libatlj has no link-time dependency on a particular NCCL build (torch's bundled 2.28 or the system 2.27).
-// The phases are also exported one by one so that the exchange can be emulated with device copies on a single GPU
-// (tests/test_slab.py) -- kernels of different ranks never wait on each other, so that emulation is safe.
+//            traffic), kick, local sums.  The 12-double step records are all-reduced ONCE per run (NCCL).
+//
+// Transport.  The exchange is fused into the pack kernels: peer memory is mapped once (CUDA IPC between the one-process-
+// per-GPU ranks, plain pointers when several ranks are emulated in one process) and the pack kernels store over
+// NVLink 5 / NVSwitch into the neighbour's buffer; the CTA that finishes last publishes the message with a system-
+// scope release of a step stamp in the buffer's header, and the consumer's stream holds a one-thread kernel that
+// acquires that stamp.  No copy, no SM-hungry communication kernel, no host synchronisation per step.
+// Receive buffers are double-buffered by step parity; that is sufficient flow control because a rank cannot start
+// step s before it has consumed its neighbours' step s-1 messages, which they sent only after consuming the step s-2
+// messages that used the same parity.  (An NCCL send/recv version of this exchange measured 35 us latency per
+// exchange and could not overlap with the saturating pair kernel: profiles/r1_slab_history.md.)
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
@@ -26,41 +32,25 @@
 
 namespace atlj {
 
-constexpr int HDR_INTS = 16;  // 64-byte header of every message; [0] = number of atoms
+constexpr int HDR_INTS = 16;  // 64-byte header of every message: [0] = number of atoms, [1] = step stamp (ready flag)
 
 __host__ __device__ static inline size_t halo_counts_ints(int sc) { return (((size_t)sc * sc + 15) / 16) * 16; }
 
-// ---- phase 1: pack the atoms that left the slab ------------------------------------------------------------------
-__global__ void __launch_bounds__(256) migrate_pack_kernel(Geom g, int n, const int *__restrict__ n_dev,
-                                                           const double *__restrict__ r,
-                                                           const double *__restrict__ v, const int *__restrict__ id,
-                                                           unsigned char *send_left, unsigned char *send_right,
-                                                           int cap, int *__restrict__ err) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= min(n, *n_dev)) return;
-  double x = r[3 * (size_t)i];
-  x = __dsub_rn(x, rint(x));
-  const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(x, 0.5), (double)g.sc));  // md_lj_ll_module.py:108
-  if (c0 >= g.x_lo && c0 < g.x_lo + g.nx_own) return;
-  const int left = g.x_lo == 0 ? g.sc - 1 : g.x_lo - 1, right = g.x_lo + g.nx_own == g.sc ? 0 : g.x_lo + g.nx_own;
-  unsigned char *buf;
-  if (c0 == left)
-    buf = send_left;
-  else if (c0 == right)
-    buf = send_right;
-  else {
-    atomicOr(&err[0], 1);  // moved more than one layer in a step, or a coordinate on the +0.5 face ('Index error')
-    return;
+__device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
+  hdr[0] = count;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(stamp) : "memory");
+}
+
+// the consumer side: spins until the producer (another GPU) has published the message of this step
+__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (const int *h : {hdr_a, hdr_b}) {
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(h + 1) : "memory");
+    } while (v != stamp);
   }
-  const int slot = atomicAdd(reinterpret_cast<int *>(buf), 1);
-  if (slot >= cap) {
-    atomicOr(&err[1], 1);
-    return;
-  }
-  double *d = reinterpret_cast<double *>(buf + sizeof(int) * HDR_INTS) + 7 * (size_t)slot;
-#pragma unroll
-  for (int k = 0; k < 3; k++) d[k] = r[3 * (size_t)i + k], d[3 + k] = v[3 * (size_t)i + k];
-  d[6] = (double)id[i];
 }
 
 // ---- phase 2: append the arrivals behind the atoms already held ----------------------------------------------------
@@ -83,19 +73,30 @@ __global__ void __launch_bounds__(256) append_kernel(const unsigned char *__rest
   if (k >= (which ? cr : cl)) return;
   const long long dst = (long long)n_old + (which ? cl : 0) + k;
   if (dst >= capacity) return;
-  const double *s = reinterpret_cast<const double *>((which ? recv_right : recv_left) + sizeof(int) * HDR_INTS) + 7 * (size_t)k;
+  const double *s =
+      reinterpret_cast<const double *>((which ? recv_right : recv_left) + sizeof(int) * HDR_INTS) + 7 * (size_t)k;
 #pragma unroll
   for (int c = 0; c < 3; c++) r[3 * dst + c] = s[c], v[3 * dst + c] = s[3 + c];
   id[dst] = (int)s[6];
 }
 
-// one owned layer -> message: header, per-cell counts, positions (already contiguous and in cell order)
-__global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, int lx, const int *__restrict__ cs,
-                                                        const double *__restrict__ r_sorted, unsigned char *buf,
-                                                        int cap, int *__restrict__ err) {
+// first / last owned layer -> message in the left / right neighbour's buffer (blockIdx.y = direction): header,
+// per-cell counts, positions (already contiguous and in cell order).  done[dir] counts finished CTAs; the last one
+// publishes.  Thread (0,0,0) also moves the new owned count (end sentinel of the last owned layer) to n_own.
+__global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, const int *__restrict__ cs,
+                                                        const double *__restrict__ r_sorted, unsigned char *to_left,
+                                                        unsigned char *to_right, int cap, int stamp,
+                                                        int *__restrict__ done, int *__restrict__ err,
+                                                        int *__restrict__ n_own, double *__restrict__ rec) {
   const int sc2 = g.sc * g.sc;
+  const int dir = blockIdx.y;
+  const int lx = dir == 0 ? g.h : g.h + g.nx_own - 1;
   const int *row = cs + (size_t)lx * (sc2 + 1);
-  int *hdr = reinterpret_cast<int *>(buf);
+  if (dir == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    *n_own = row[sc2];
+    if (rec) rec[11] = (double)row[sc2];
+  }
+  int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
   int *cnt = hdr + HDR_INTS;
   double *pos = reinterpret_cast<double *>(cnt + halo_counts_ints(g.sc));
   const int start = row[0];
@@ -104,19 +105,32 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, int lx, const in
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&err[1], 1);
     total = cap;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) hdr[0] = total;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   for (long long c = gt; c < sc2; c += stride) cnt[c] = row[c + 1] - row[c];
   for (long long e = gt; e < 3ll * total; e += stride) pos[e] = r_sorted[3 * (size_t)start + e];
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&done[dir], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    publish(hdr, total, stamp);
+    done[dir] = 0;
+  }
 }
 
 // ---- phase 3: a received layer becomes halo layer lx of the local grid ---------------------------------------------
 // cell_start of the layer = base + exclusive scan of the per-cell counts (one CTA; sc^2 <= 1024 * 64)
-__global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, int lx, const unsigned char *__restrict__ buf,
-                                                       const unsigned char *__restrict__ before,
+__global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, const unsigned char *__restrict__ from_left,
+                                                       const unsigned char *__restrict__ from_right,
                                                        const int *__restrict__ n_own_dev, int *__restrict__ cs,
                                                        long long capacity, int cap, int *__restrict__ err) {
   __shared__ int wsum[32];
+  // block 0: the left neighbour's layer -> local layer 0, behind the owned atoms; block 1: the right neighbour's
+  // layer -> local layer nxl-1, behind the left halo
+  const int lx = blockIdx.x == 0 ? 0 : g.nxl - 1;
+  const unsigned char *buf = blockIdx.x == 0 ? from_left : from_right;
+  const unsigned char *before = blockIdx.x == 0 ? nullptr : from_left;
   const int n_own = *n_own_dev;
   const int sc2 = g.sc * g.sc;
   const int *hdr = reinterpret_cast<const int *>(buf);
@@ -160,10 +174,12 @@ __global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, int lx, const uns
   }
 }
 
-__global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned char *__restrict__ buf,
-                                                        const unsigned char *__restrict__ before,
+__global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned char *__restrict__ from_left,
+                                                        const unsigned char *__restrict__ from_right,
                                                         const int *__restrict__ n_own_dev, int cap,
                                                         long long capacity, double *__restrict__ r_sorted) {
+  const unsigned char *buf = blockIdx.y == 0 ? from_left : from_right;
+  const unsigned char *before = blockIdx.y == 0 ? nullptr : from_left;
   const int n_own = *n_own_dev;
   const int *hdr = reinterpret_cast<const int *>(buf);
   const double *pos = reinterpret_cast<const double *>(hdr + HDR_INTS + halo_counts_ints(g.sc));
@@ -174,21 +190,14 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned c
   for (long long e = gt; e < 3 * total; e += stride) r_sorted[3 * base + e] = pos[e];
 }
 
-__global__ void set_nown_kernel(double *rec, const int *n_own) { rec[11] = (double)*n_own; }
-// after the sort the number of owned atoms is the end sentinel of the last owned layer
-__global__ void copy_int_kernel(int *dst, const int *src) { *dst = *src; }
 
-// ---- NCCL, bound at run time ----------------------------------------------------------------------------------------
+// ---- NCCL (only the per-run all-reduce of the step records), bound at run time -------------------------------------
 struct NcclApi {
   void *handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -217,11 +226,7 @@ static int nccl_load() {
   ATLJ_SYM(GetUniqueId, "ncclGetUniqueId");
   ATLJ_SYM(CommInitRank, "ncclCommInitRank");
   ATLJ_SYM(CommDestroy, "ncclCommDestroy");
-  ATLJ_SYM(Send, "ncclSend");
-  ATLJ_SYM(Recv, "ncclRecv");
   ATLJ_SYM(AllReduce, "ncclAllReduce");
-  ATLJ_SYM(GroupStart, "ncclGroupStart");
-  ATLJ_SYM(GroupEnd, "ncclGroupEnd");
   ATLJ_SYM(GetErrorString, "ncclGetErrorString");
 #undef ATLJ_SYM
   g_nccl.handle = h;
@@ -237,68 +242,53 @@ static int nccl_load() {
     }                                                                                                   \
   } while (0)
 
-// my "to the left" message lands in the left neighbour's "from the right" buffer and vice versa.  With two ranks
-// both neighbours are the same peer; sends and receives between one pair match in order, hence recv right first.
-static int exchange(atlj_sim *s, cudaStream_t st, unsigned char *const send[2], unsigned char *const recv[2],
-                    size_t bytes) {
-  MgState &m = s->mg;
-  ncclComm_t comm = (ncclComm_t)m.comm;
-  ATLJ_NCCL(g_nccl.GroupStart());
-  ATLJ_NCCL(g_nccl.Send(send[0], bytes, ncclChar, m.left, comm, st));
-  ATLJ_NCCL(g_nccl.Send(send[1], bytes, ncclChar, m.right, comm, st));
-  ATLJ_NCCL(g_nccl.Recv(recv[1], bytes, ncclChar, m.right, comm, st));
-  ATLJ_NCCL(g_nccl.Recv(recv[0], bytes, ncclChar, m.left, comm, st));
-  ATLJ_NCCL(g_nccl.GroupEnd());
-  return ATLJ_OK;
+// ---- receive arena: [kind: migration, halo][from: left, right][parity] ------------------------------------------------
+static inline size_t arena_off(const MgState &m, int kind, int from, int parity) {
+  const size_t mig = m.mig_bytes, halo = m.halo_bytes;
+  return kind == 0 ? (size_t)(2 * from + parity) * mig : 4 * mig + (size_t)(2 * from + parity) * halo;
+}
+static inline unsigned char *my_recv(const MgState &m, int kind, int from, int parity) {
+  return m.arena + arena_off(m, kind, from, parity);
+}
+// where my message towards `dir` (0 = left, 1 = right) lands: the neighbour's "from the other side" buffer
+static inline unsigned char *peer_recv(const MgState &m, int kind, int dir, int parity) {
+  return m.peer_arena[dir] + arena_off(m, kind, 1 - dir, parity);
 }
 
-// ---- the three phases ---------------------------------------------------------------------------------------------------
+// ---- the phases -----------------------------------------------------------------------------------------------------------
 // The number of owned atoms changes every step and lives on the device (cnt_dev[1]); kernels are launched over the
 // capacity and read it, so a step needs no host synchronisation.  The host copy s->n is refreshed at the end of a run.
-static int phase1(atlj_sim *s, double dt) {
+
+// phase 1: ONE kernel: [trailing half kick + record of the finished step] + leading half kick + drift + wrap + cell
+// assignment of the atoms that stay + leavers packed into the neighbours' buffers and published
+static int phase1(atlj_sim *s, double dt, bool first_kick, double *rec_prev, int nb_prev) {
+  MgState &m = s->mg;
+  const int par = (int)(m.step & 1);
+  SlabArgs sl;
+  sl.n_dev = m.cnt_dev + 1, sl.id = s->id[s->cur];
+  sl.to_left = peer_recv(m, 0, 0, par), sl.to_right = peer_recv(m, 0, 1, par);
+  sl.mig_cap = (int)m.mig_cap, sl.stamp = (int)(m.step + 1), sl.mig_cnt = m.cnt_dev + 4;
+  Timer::begin(s, 2);
+  const int nb = launch_kdk_assign(s->st, s->g, (int)s->cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
+                                   first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev, s->p.model, &sl);
+  Timer::end(s);
+  return nb < 0 ? nb : ATLJ_OK;
+}
+
+// phase 2: arrivals appended and assigned, scan, counting sort, boundary layers packed into the neighbours' buffers
+static int phase2(atlj_sim *s, double *rec) {
   int rc;
   MgState &m = s->mg;
-  const int nup = (int)s->cap;
-  const int *n_dev = m.cnt_dev + 1;
-  Timer::begin(s, 2);
-  if ((rc = launch_kick_drift(s->st, 3ll * nup, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box, nullptr,
-                              n_dev)))
-    return rc;
-  Timer::end(s);
-  Timer::begin(s, 3);
-  ATLJ_CUDA(cudaMemsetAsync(m.mig_send[0], 0, sizeof(int) * HDR_INTS, s->st));
-  ATLJ_CUDA(cudaMemsetAsync(m.mig_send[1], 0, sizeof(int) * HDR_INTS, s->st));
-  migrate_pack_kernel<<<(nup + 255) / 256, 256, 0, s->st>>>(s->g, nup, n_dev, s->r[s->cur], s->v[s->cur],
-                                                            s->id[s->cur], m.mig_send[0], m.mig_send[1],
-                                                            (int)m.mig_cap, s->cb.err);
+  const int cap = (int)m.mig_cap, nup = (int)s->cap, par = (int)(m.step & 1), stamp = (int)(m.step + 1);
+  const int cur = s->cur, alt = 1 - cur;
+  Timer::begin(s, 4);
+  const unsigned char *ml = my_recv(m, 0, 0, par), *mr = my_recv(m, 0, 1, par);
+  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(ml), reinterpret_cast<const int *>(mr), stamp);
   ATLJ_LAUNCHED();
   Timer::end(s);
-  return ATLJ_OK;
-}
-
-// phase 2 in three pieces so that the two exchanges can hide behind independent work:
-//   2a  cell assignment of the atoms already held (leavers are skipped)          -- overlaps the migration exchange
-//   2b  arrivals appended and assigned, scan, scatter, sort+gather of the blocks of cells that cover the first and
-//       last owned layer, halo messages packed
-//   2c  sort+gather of the remaining (interior) blocks                            -- overlaps the halo exchange
-static int phase2a(atlj_sim *s) {
-  MgState &m = s->mg;
-  Timer::begin(s, 1);
-  int rc = launch_cell_assign(s->st, s->g, s->r[s->cur], s->r[s->cur], (int)s->cap, false, 0.0, s->cb, nullptr,
-                              m.cnt_dev + 1, true);
-  Timer::end(s);
-  return rc;
-}
-
-static int phase2b(atlj_sim *s) {
-  int rc;
-  MgState &m = s->mg;
-  const int cap = (int)m.mig_cap, nup = (int)s->cap;
-  const int cur = s->cur, alt = 1 - cur;
   Timer::begin(s, 3);
-  append_kernel<<<(2 * cap + 255) / 256, 256, 0, s->st>>>(m.mig_recv[0], m.mig_recv[1], cap, s->r[cur], s->v[cur],
-                                                         s->id[cur], m.cnt_dev + 1, (long long)s->cap, m.cnt_dev,
-                                                         s->cb.err);
+  append_kernel<<<(2 * cap + 255) / 256, 256, 0, s->st>>>(ml, mr, cap, s->r[cur], s->v[cur], s->id[cur], m.cnt_dev + 1,
+                                                         (long long)s->cap, m.cnt_dev, s->cb.err);
   ATLJ_LAUNCHED();
   if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], 2 * cap, false, 0.0, s->cb, nullptr, m.cnt_dev, true,
                                m.cnt_dev + 1)))
@@ -307,61 +297,17 @@ static int phase2b(atlj_sim *s) {
   Timer::begin(s, 1);
   if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
   if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, nup, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
-                                    s->id[alt], m.cnt_dev, 1)))
+                                    s->id[alt], m.cnt_dev)))
     return rc;
   Timer::end(s);
-  Timer::begin(s, 5);
-  const int sc2 = s->g.sc * s->g.sc;
-  copy_int_kernel<<<1, 1, 0, s->st>>>(m.cnt_dev + 1,
-                                      s->cb.cell_start + (size_t)(s->g.h + s->g.nx_own - 1) * (sc2 + 1) + sc2);
-  ATLJ_LAUNCHED();
-  const int blocks = 148 * 2;
-  halo_pack_kernel<<<blocks, 256, 0, s->st>>>(s->g, s->g.h, s->cb.cell_start, s->r[alt], m.halo_send[0],
-                                              (int)m.halo_cap, s->cb.err);
-  ATLJ_LAUNCHED();
-  halo_pack_kernel<<<blocks, 256, 0, s->st>>>(s->g, s->g.h + s->g.nx_own - 1, s->cb.cell_start, s->r[alt],
-                                              m.halo_send[1], (int)m.halo_cap, s->cb.err);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  return ATLJ_OK;
-}
-
-static int phase2c(atlj_sim *s) {
-  const int cur = s->cur, alt = 1 - cur;
-  Timer::begin(s, 1);
-  int rc = launch_cell_sort_gather(s->st, s->g, s->cb, (int)s->cap, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
-                                   s->v[alt], s->id[alt], s->mg.cnt_dev, 2);
-  Timer::end(s);
   s->cur = alt;
-  return rc;
-}
-
-// the received layers become the halo layers 0 and nxl-1 of the local grid, behind the owned atoms
-static int unpack_halos(atlj_sim *s, cudaStream_t st) {
-  MgState &m = s->mg;
-  const Geom &g = s->g;
-  const int *n_dev = m.cnt_dev + 1;
-  halo_cs_kernel<<<1, 1024, 0, st>>>(g, 0, m.halo_recv[0], nullptr, n_dev, s->cb.cell_start, (long long)s->cap,
-                                     (int)m.halo_cap, s->cb.err);
+  Timer::begin(s, 5);
+  halo_pack_kernel<<<dim3(148, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
+                                                    peer_recv(m, 1, 1, par), (int)m.halo_cap, stamp, m.cnt_dev + 8,
+                                                    s->cb.err, m.cnt_dev + 1, rec);
   ATLJ_LAUNCHED();
-  halo_cs_kernel<<<1, 1024, 0, st>>>(g, g.nxl - 1, m.halo_recv[1], m.halo_recv[0], n_dev, s->cb.cell_start,
-                                     (long long)s->cap, (int)m.halo_cap, s->cb.err);
-  ATLJ_LAUNCHED();
-  halo_copy_kernel<<<148, 256, 0, st>>>(g, m.halo_recv[0], nullptr, n_dev, (int)m.halo_cap, (long long)s->cap,
-                                        s->r[1 - s->cur]);
-  ATLJ_LAUNCHED();
-  halo_copy_kernel<<<148, 256, 0, st>>>(g, m.halo_recv[1], m.halo_recv[0], n_dev, (int)m.halo_cap, (long long)s->cap,
-                                        s->r[1 - s->cur]);
-  ATLJ_LAUNCHED();
+  Timer::end(s);
   return ATLJ_OK;
-}
-
-// emulation path: phase 2c has already swapped the buffers, so "alt" of unpack_halos is the current one
-static int unpack_halos_current(atlj_sim *s) {
-  s->cur = 1 - s->cur;
-  int rc = unpack_halos(s, s->st);
-  s->cur = 1 - s->cur;
-  return rc;
 }
 
 static PairArgs pair_args(atlj_sim *s) {
@@ -372,25 +318,42 @@ static PairArgs pair_args(atlj_sim *s) {
   return a;
 }
 
-// pair kernel over the owned rows (the halos are in place) + kick + local sums
-static int phase3(atlj_sim *s, double dt, double *rec) {
-  int rc;
+// phase 3: the received layers become the halo layers 0 and nxl-1 of the local grid, behind the owned atoms; pair
+// kernel over the owned rows.  -> rows of partials written (the record is finished by the next phase 1 or by tail())
+static int phase3(atlj_sim *s) {
   MgState &m = s->mg;
-  ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));
+  const Geom &g = s->g;
+  const int par = (int)(m.step & 1), stamp = (int)(m.step + 1);
+  const int *n_dev = m.cnt_dev + 1;
+  const unsigned char *hl = my_recv(m, 1, 0, par), *hr = my_recv(m, 1, 1, par);
+  Timer::begin(s, 6);
+  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(hl), reinterpret_cast<const int *>(hr), stamp);
+  ATLJ_LAUNCHED();
+  Timer::end(s);
+  Timer::begin(s, 3);
+  halo_cs_kernel<<<2, 1024, 0, s->st>>>(g, hl, hr, n_dev, s->cb.cell_start, (long long)s->cap, (int)m.halo_cap,
+                                        s->cb.err);
+  ATLJ_LAUNCHED();
+  halo_copy_kernel<<<dim3(148, 2), 256, 0, s->st>>>(g, hl, hr, n_dev, (int)m.halo_cap, (long long)s->cap, s->r[s->cur]);
+  ATLJ_LAUNCHED();
+  Timer::end(s);
   const PairArgs a = pair_args(s);
   Timer::begin(s, 0);
   const int nb = (s->pair_kernel == 0 && a.p.model == ATLJ_MODEL_LJ) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
                                                                    : launch_pair_tile(s->st, a, false);
   Timer::end(s);
-  if (nb < 0) return nb;
-  if ((rc = launch_finalize(s->st, s->partials, nb, a.p.model, false, rec, s->cb.err + 2))) return rc;
+  m.step++;
+  return nb;
+}
+
+// the record of the last step of a run: pair totals, trailing half kick, sum v^2, sum f^2
+static int tail(atlj_sim *s, double dt, double *rec, int nb) {
+  int rc;
+  if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2))) return rc;
   Timer::begin(s, 2);
-  if ((rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, m.cnt_dev + 1)))
-    return rc;
-  set_nown_kernel<<<1, 1, 0, s->st>>>(rec, m.cnt_dev + 1);
-  ATLJ_LAUNCHED();
+  rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->mg.cnt_dev + 1);
   Timer::end(s);
-  return ATLJ_OK;
+  return rc;
 }
 
 // host copy of the owned count <-> device
@@ -408,16 +371,16 @@ static int pull_n(atlj_sim *s) {
 
 static void mg_free(atlj_sim *s) {
   MgState &m = s->mg;
-  for (int k = 0; k < 2; k++) {
-    cudaFree(m.mig_send[k]), cudaFree(m.mig_recv[k]), cudaFree(m.halo_send[k]), cudaFree(m.halo_recv[k]);
-    m.mig_send[k] = m.mig_recv[k] = m.halo_send[k] = m.halo_recv[k] = nullptr;
+  for (int d = 0; d < 2; d++) {
+    if (m.peer_ipc[d]) cudaIpcCloseMemHandle(m.peer_arena[d]);
+    m.peer_arena[d] = nullptr, m.peer_ipc[d] = false;
   }
+  cudaFree(m.arena);
+  m.arena = nullptr;
   cudaFree(m.cnt_dev);
   m.cnt_dev = nullptr;
   if (m.cnt_host) cudaFreeHost(m.cnt_host);
   m.cnt_host = nullptr;
-  if (m.st2) cudaStreamDestroy(m.st2), cudaEventDestroy(m.e1), cudaEventDestroy(m.e2);
-  m.st2 = nullptr;
   if (m.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m.comm);
   m.comm = nullptr;
   m.on = false;
@@ -442,71 +405,87 @@ int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap) {
   mg_free(s);
   MgState &m = s->mg;
   m.mig_cap = mig_cap, m.halo_cap = halo_cap;
-  m.mig_bytes = sizeof(int) * HDR_INTS + sizeof(double) * 7 * (size_t)mig_cap;
-  m.halo_bytes = sizeof(int) * (HDR_INTS + halo_counts_ints(s->g.sc)) + sizeof(double) * 3 * (size_t)halo_cap;
-  for (int k = 0; k < 2; k++) {
-    ATLJ_CUDA(cudaMalloc((void **)&m.mig_send[k], m.mig_bytes));
-    ATLJ_CUDA(cudaMalloc((void **)&m.mig_recv[k], m.mig_bytes));
-    ATLJ_CUDA(cudaMalloc((void **)&m.halo_send[k], m.halo_bytes));
-    ATLJ_CUDA(cudaMalloc((void **)&m.halo_recv[k], m.halo_bytes));
-    ATLJ_CUDA(cudaMemsetAsync(m.mig_send[k], 0, m.mig_bytes, s->st));
-    ATLJ_CUDA(cudaMemsetAsync(m.mig_recv[k], 0, m.mig_bytes, s->st));
-    ATLJ_CUDA(cudaMemsetAsync(m.halo_send[k], 0, m.halo_bytes, s->st));
-    ATLJ_CUDA(cudaMemsetAsync(m.halo_recv[k], 0, m.halo_bytes, s->st));
-  }
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  m.mig_bytes = up(sizeof(int) * HDR_INTS + sizeof(double) * 7 * (size_t)mig_cap);
+  m.halo_bytes = up(sizeof(int) * (HDR_INTS + halo_counts_ints(s->g.sc)) + sizeof(double) * 3 * (size_t)halo_cap);
+  m.arena_bytes = 4 * m.mig_bytes + 4 * m.halo_bytes;
+  ATLJ_CUDA(cudaMalloc((void **)&m.arena, m.arena_bytes));
+  ATLJ_CUDA(cudaMemsetAsync(m.arena, 0, m.arena_bytes, s->st));
   ATLJ_CUDA(cudaMalloc((void **)&m.cnt_dev, 16 * sizeof(int)));
   ATLJ_CUDA(cudaMemsetAsync(m.cnt_dev, 0, 16 * sizeof(int), s->st));
   ATLJ_CUDA(cudaHostAlloc((void **)&m.cnt_host, 16 * sizeof(int), cudaHostAllocDefault));
-  {
-    int lo = 0, hi = 0;
-    ATLJ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    ATLJ_CUDA(cudaStreamCreateWithPriority(&m.st2, cudaStreamNonBlocking, hi));  // exchanges get SM slots first
-  }
-  ATLJ_CUDA(cudaEventCreateWithFlags(&m.e1, cudaEventDisableTiming));
-  ATLJ_CUDA(cudaEventCreateWithFlags(&m.e2, cudaEventDisableTiming));
+  m.step = 0;
   m.on = true;
-  return push_n(s);
-}
-
-/* which: 0/1 migration send left/right, 2/3 migration recv from left/right, 4/5 halo send left/right,
- * 6/7 halo recv from left/right */
-void *atlj_sim_mg_buffer(atlj_sim *s, int which) {
-  if (!s || !s->mg.on || which < 0 || which > 7) return nullptr;
-  MgState &m = s->mg;
-  unsigned char *t[8] = {m.mig_send[0], m.mig_send[1], m.mig_recv[0], m.mig_recv[1],
-                         m.halo_send[0], m.halo_send[1], m.halo_recv[0], m.halo_recv[1]};
-  return t[which];
-}
-int64_t atlj_sim_mg_buffer_bytes(atlj_sim *s, int which) {
-  if (!s || !s->mg.on || which < 0 || which > 7) return -1;
-  return (int64_t)(which < 4 ? s->mg.mig_bytes : s->mg.halo_bytes);
-}
-int atlj_device_copy(void *dst, const void *src, int64_t bytes) {
-  ATLJ_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+  int rc = push_n(s);
+  if (rc) return rc;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
   return ATLJ_OK;
 }
+
 void atlj_sim_set_total(atlj_sim *s, int64_t n_total) {
   if (s) s->n_total = n_total;
 }
 
+/* receive arena of this rank: device pointer (same-process peers) and size */
+void *atlj_sim_mg_arena(atlj_sim *s) { return (s && s->mg.on) ? s->mg.arena : nullptr; }
+int64_t atlj_sim_mg_arena_bytes(atlj_sim *s) { return (s && s->mg.on) ? (int64_t)s->mg.arena_bytes : -1; }
+
+/* peers living in the same process (several ranks emulated on one GPU): plain device pointers */
+int atlj_sim_mg_set_peers(atlj_sim *s, void *left_arena, void *right_arena) {
+  if (!s || !s->mg.on || !left_arena || !right_arena) return ATLJ_ERR_ARG;
+  s->mg.peer_arena[0] = (unsigned char *)left_arena, s->mg.peer_arena[1] = (unsigned char *)right_arena;
+  s->mg.peer_ipc[0] = s->mg.peer_ipc[1] = false;
+  return ATLJ_OK;
+}
+
+/* peers in other processes (one process per GPU): CUDA IPC handle of the arena, 64 bytes */
+int atlj_sim_mg_ipc_handle(atlj_sim *s, char *out64) {
+  if (!s || !s->mg.on || !out64) return ATLJ_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  ATLJ_CUDA(cudaIpcGetMemHandle(&h, s->mg.arena));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &h, 64);
+  return ATLJ_OK;
+}
+int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left64, const char *right64) {
+  if (!s || !s->mg.on || !left64 || !right64) return ATLJ_ERR_ARG;
+  MgState &m = s->mg;
+  const bool same = memcmp(left64, right64, 64) == 0;  // two ranks: both neighbours are the one peer
+  for (int d = 0; d < 2; d++) {
+    if (d == 1 && same) {
+      m.peer_arena[1] = m.peer_arena[0], m.peer_ipc[1] = false;
+      break;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, d == 0 ? left64 : right64, 64);
+    void *p = nullptr;
+    ATLJ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    m.peer_arena[d] = (unsigned char *)p, m.peer_ipc[d] = true;
+  }
+  return ATLJ_OK;
+}
+
 int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
-  if (!s || !s->mg.on) return ATLJ_ERR_ARG;
-  int rc = push_n(s);
-  if (rc || (rc = phase1(s, dt))) return rc;
+  if (!s || !s->mg.on || !s->mg.peer_arena[0]) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, 1);
+  if (rc || (rc = push_n(s))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if ((rc = phase1(s, dt, false, nullptr, 0))) return rc;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
   return ATLJ_OK;
 }
 int atlj_sim_mg_phase2(atlj_sim *s) {
   if (!s || !s->mg.on) return ATLJ_ERR_ARG;
-  int rc = phase2a(s);
-  if (rc || (rc = phase2b(s)) || (rc = phase2c(s)) || (rc = pull_n(s))) return rc;
+  int rc = phase2(s, s->rec_dev);
+  if (rc || (rc = pull_n(s))) return rc;
   return sim_check_flags(s);
 }
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
   if (!s || !s->mg.on) return ATLJ_ERR_ARG;
-  int rc = sim_ensure_rec(s, 1);
+  const int nb = phase3(s);
+  if (nb < 0) return nb;
+  int rc = tail(s, dt, s->rec_dev, nb);
   if (rc) return rc;
-  if ((rc = unpack_halos_current(s)) || (rc = phase3(s, dt, s->rec_dev))) return rc;
   return sim_copy_rec(s, rec_host, 1);
 }
 
@@ -529,50 +508,28 @@ int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128) {
   ATLJ_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
   MgState &m = s->mg;
   m.comm = comm, m.rank = rank, m.world = world;
-  m.left = (rank + world - 1) % world, m.right = (rank + 1) % world;
   return ATLJ_OK;
 }
 
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
-  if (!s || !s->mg.on || !s->mg.comm || nsteps < 0) {
-    set_error("run_nve_mg: enable and connect the slab first");
+  if (!s || !s->mg.on || !s->mg.comm || !s->mg.peer_arena[0] || !s->mg.peer_arena[1] || nsteps < 0) {
+    set_error("run_nve_mg: enable the slab, map the neighbours' buffers and connect first");
     return ATLJ_ERR_ARG;
   }
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
   if (rc) return rc;
   MgState &m = s->mg;
   if ((rc = push_n(s))) return rc;
-  // Per step, main stream | second (high-priority) stream:
-  //   kick, drift, pack leavers        |
-  //   assign the atoms already held    | migration exchange
-  //   append + assign arrivals, scan, sort boundary blocks, pack halos
-  //   sort interior blocks             | halo exchange, unpack
-  //   pair kernel, finalize, kick      |
-  // The NCCL kernels need a few free SM slots, which the saturating pair kernel never leaves, so the exchanges are
-  // hidden behind the short-lived cell-build kernels instead (measured: behind the pair kernel they simply wait).
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)nsteps, s->st));
+  int nb = 0;
+  double *rec_prev = nullptr;
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
-    if ((rc = phase1(s, dt))) return rc;
-    ATLJ_CUDA(cudaEventRecord(m.e1, s->st));
-    ATLJ_CUDA(cudaStreamWaitEvent(m.st2, m.e1, 0));
-    Timer::begin(s, 4, m.st2, true);
-    if ((rc = exchange(s, m.st2, m.mig_send, m.mig_recv, m.mig_bytes))) return rc;
-    Timer::end(s, m.st2, true);
-    ATLJ_CUDA(cudaEventRecord(m.e2, m.st2));
-    if ((rc = phase2a(s))) return rc;
-    ATLJ_CUDA(cudaStreamWaitEvent(s->st, m.e2, 0));
-    if ((rc = phase2b(s))) return rc;
-    ATLJ_CUDA(cudaEventRecord(m.e1, s->st));
-    ATLJ_CUDA(cudaStreamWaitEvent(m.st2, m.e1, 0));
-    Timer::begin(s, 6, m.st2, true);
-    if ((rc = exchange(s, m.st2, m.halo_send, m.halo_recv, m.halo_bytes))) return rc;
-    if ((rc = unpack_halos(s, m.st2))) return rc;  // writes behind the owned atoms of r[alt]; 2c swaps cur
-    Timer::end(s, m.st2, true);
-    ATLJ_CUDA(cudaEventRecord(m.e2, m.st2));
-    if ((rc = phase2c(s))) return rc;
-    ATLJ_CUDA(cudaStreamWaitEvent(s->st, m.e2, 0));
-    if ((rc = phase3(s, dt, rec))) return rc;
+    if ((rc = phase1(s, dt, k > 0, rec_prev, nb)) || (rc = phase2(s, rec))) return rc;
+    if ((nb = phase3(s)) < 0) return nb;
+    rec_prev = rec;
   }
+  if (nsteps > 0 && (rc = tail(s, dt, rec_prev, nb))) return rc;
   // the records are read on the host only now: ONE all-reduce for all steps
   if (nsteps > 0) {
     Timer::begin(s, 3);

@@ -7,16 +7,17 @@
 // slab decomposition state (mg.cu)
 struct MgState {
   bool on = false;
-  int rank = 0, world = 1, left = 0, right = 0;
+  int rank = 0, world = 1;
   int64_t mig_cap = 0, halo_cap = 0;  // atoms per message
-  size_t mig_bytes = 0, halo_bytes = 0;
-  unsigned char *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};    // [0] left, [1] right
-  unsigned char *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // recv[0] = from the left
-  int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended, [1] owned atoms (after the sort)
+  size_t mig_bytes = 0, halo_bytes = 0, arena_bytes = 0;
+  unsigned char *arena = nullptr;                       // my receive buffers: [migration|halo][from left|right][parity]
+  unsigned char *peer_arena[2] = {nullptr, nullptr};    // the left / right neighbour's arena, mapped into this process
+  bool peer_ipc[2] = {false, false};                    // mapped with cudaIpcOpenMemHandle (to be closed)
+  long long step = 0;                                   // exchange counter: parity selects the buffer, step+1 = stamp
+  int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended, [1] owned atoms (after the sort),
+                            // [4..6] migration slot counters + CTAs done, [8], [9] halo pack CTAs done
   int *cnt_host = nullptr;  // pinned mirror of cnt_dev[1]
-  void *comm = nullptr;     // ncclComm_t
-  cudaStream_t st2 = nullptr;  // halo exchange + boundary layers, concurrent with the interior pair kernel
-  cudaEvent_t e1 = nullptr, e2 = nullptr;
+  void *comm = nullptr;     // ncclComm_t (all-reduce of the step records)
 };
 
 struct atlj_sim {

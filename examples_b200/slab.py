@@ -3,10 +3,11 @@
 No reference counterpart: the reference's only distributed program is replica exchange.  The cell grid is
 the reference's (sc = floor(box/r_cut), md_lj_ll_module.py:106); rank k owns the contiguous x layers
 [x_lo, x_hi) = partition(sc, world)[k] and keeps one halo layer on each side.  The per-step exchange (migration,
-halo, all-reduce of the step record) runs inside libatlj on the sim's stream through NCCL send/recv
-(csrc/mg.cu); this module holds the host-side logic: the partition, the initial scatter of a configuration, capacity
-sizing, the NCCL bootstrap over torch.distributed, and a single-GPU emulation of several ranks (device copies in place
-of NCCL) used by the GPU tests.
+halo) runs inside libatlj on the sim's stream: the pack kernels write straight into the neighbours' receive buffers
+over NVLink (csrc/mg.cu); the step records are all-reduced once per run with NCCL.  This module holds the host-side
+logic: the partition, the initial scatter of a configuration, capacity sizing, the bootstrap over torch.distributed
+(CUDA IPC handles of the receive buffers, NCCL unique id), and a single-GPU emulation of several ranks in one process
+used by the GPU tests.
 """
 import ctypes as C
 import math
@@ -87,11 +88,22 @@ class SlabRank(Simulation):
         _lib.check(_lib.lib().atlj_sim_mg_phase3(self._h, float(dt), rec.ctypes.data))
         return rec
 
-    def buffer(self, which):
-        L = _lib.lib()
-        return L.atlj_sim_mg_buffer(self._h, which), L.atlj_sim_mg_buffer_bytes(self._h, which)
+    def arena(self):
+        """Device pointer of this rank's receive buffers (neighbours in the same process write into it directly)."""
+        return _lib.lib().atlj_sim_mg_arena(self._h)
 
-    # ---- NCCL path ------------------------------------------------------------------------------------------------
+    def set_peers(self, left, right):
+        _lib.check(_lib.lib().atlj_sim_mg_set_peers(self._h, left.arena(), right.arena()))
+
+    # ---- one process per GPU ----------------------------------------------------------------------------------------
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        _lib.check(_lib.lib().atlj_sim_mg_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def ipc_open(self, left_handle, right_handle):
+        _lib.check(_lib.lib().atlj_sim_mg_ipc_open(self._h, left_handle, right_handle))
+
     def connect(self, unique_id):
         _lib.check(_lib.lib().atlj_sim_mg_connect(self._h, self.rank, self.world, unique_id))
 
@@ -120,38 +132,31 @@ class SlabSimulation(SlabRank):
     def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0):
         import torch.distributed as dist
         super().__init__(box, r_cut, r_all, v_all, rank, world, model=model, stream=stream)
+        handles = [None] * world
+        dist.all_gather_object(handles, self.ipc_handle())   # map the neighbours' receive buffers (CUDA IPC)
+        self.ipc_open(handles[(rank - 1) % world], handles[(rank + 1) % world])
         ids = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         self.connect(ids[0])
+        dist.barrier()
 
 
 class EmulatedSlabs:
-    """`world` ranks on ONE GPU in one process: the two exchanges of a step are device-to-device copies and the
-    all-reduce is a host sum.  Same kernels, same message formats, same ordering as the NCCL path."""
+    """`world` ranks on ONE GPU in one process, driven in lockstep: every rank finishes a phase before any rank
+    starts the next, so the messages a phase waits for have always been published already.  Same kernels, same
+    peer-memory writes and stamps as the multi-process path; the all-reduce is a host sum."""
 
     def __init__(self, box, r_cut, r, v, world, model="lj"):
         self.world = world
         self.ranks = [SlabRank(box, r_cut, r, v, k, world, model=model) for k in range(world)]
-
-    def _exchange(self, send_left, send_right, recv_left, recv_right):
-        L = _lib.lib()
-        w = self.world
-        for k, me in enumerate(self.ranks):
-            left, right = self.ranks[(k - 1) % w], self.ranks[(k + 1) % w]
-            src, nb = me.buffer(send_left)
-            dst, _ = left.buffer(recv_right)      # my message to the left arrives "from the right" there
-            _lib.check(L.atlj_device_copy(dst, src, nb))
-            src, nb = me.buffer(send_right)
-            dst, _ = right.buffer(recv_left)
-            _lib.check(L.atlj_device_copy(dst, src, nb))
+        for k, s in enumerate(self.ranks):
+            s.set_peers(self.ranks[(k - 1) % world], self.ranks[(k + 1) % world])
 
     def step(self, dt):
         for s in self.ranks:
             s.phase1(dt)
-        self._exchange(0, 1, 2, 3)
         for s in self.ranks:
             s.phase2()
-        self._exchange(4, 5, 6, 7)
         rec = sum(s.phase3(dt) for s in self.ranks)
         rec[7] = 1.0 if rec[7] > 0 else 0.0
         return rec

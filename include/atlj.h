@@ -139,30 +139,33 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
 int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double o_decay, double o_noise, const double *noise_host,
                              int nsteps, double *rec_host);
 
-/* ---- slab domain decomposition over the GPUs of one box (one rank per GPU; no reference counterpart, the yardstick is
- * the single-domain result).  A rank is a sim configured with a proper sub-range [x_lo, x_hi) of x cell layers.
- * mig_cap / halo_cap = atoms per migration / halo message (fixed-size messages, no size handshake). ----------- */
+/* ---- slab domain decomposition over the GPUs of one box (one rank per GPU; no reference counterpart, the yardstick
+ * is the single-domain result).  A rank is a sim configured with a proper sub-range [x_lo, x_hi) of x cell layers.
+ * Migrating atoms and halo layers are written by the pack kernels straight into the neighbours' receive buffers over
+ * NVLink (peer memory mapped once with CUDA IPC) and published with a system-scope step stamp; the per-step records
+ * are all-reduced once per run through NCCL.  mig_cap / halo_cap = atoms per migration / halo message. ---------- */
 int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap);
 void atlj_sim_set_total(atlj_sim *s, int64_t n_total); /* atoms of the whole system (RNG / noise indexing) */
+/* This rank's receive arena: CUDA IPC handle (64 bytes) for neighbours in other processes ... */
+int atlj_sim_mg_ipc_handle(atlj_sim *s, char *out64);
+int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left64, const char *right64);
+/* ... or plain device pointers for neighbours living in the same process (ranks emulated on one GPU). */
+void *atlj_sim_mg_arena(atlj_sim *s);
+int64_t atlj_sim_mg_arena_bytes(atlj_sim *s);
+int atlj_sim_mg_set_peers(atlj_sim *s, void *left_arena, void *right_arena);
 /* NCCL communicator over all ranks: rank 0 obtains the id, the caller broadcasts the 128 bytes by any means. */
 int atlj_nccl_unique_id(char *out128);
 int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
-/* nsteps velocity-Verlet steps (md_nve_lj.py:178-192) of the whole system: per step two NCCL send/recv exchanges
- * with the slab neighbours (migrating atoms; one halo layer of positions) and one all-reduce of the step record,
- * all on the sim's stream.  rec_host (nsteps, ATLJ_NREC) holds the GLOBAL sums on every rank.  dt = 0 gives a plain
- * force evaluation. */
+/* nsteps velocity-Verlet steps (md_nve_lj.py:178-192) of the whole system, no host synchronisation per step.
+ * rec_host (nsteps, ATLJ_NREC) holds the GLOBAL sums on every rank.  dt = 0 gives a plain force evaluation. */
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host);
-/* The same step cut into its three device phases, for emulating several ranks on one GPU with device copies in
- * place of NCCL (tests): phase1 = kick, drift, pack leavers; [exchange migration buffers]; phase2 = append arrivals,
- * bin + sort, pack boundary layers; [exchange halo buffers]; phase3 = unpack halos, pair kernel, kick, LOCAL sums.
- * Buffers: which = 0/1 migration send to left/right, 2/3 migration received from left/right, 4/5 halo send to
- * left/right, 6/7 halo received from left/right. */
+/* The same step cut into its three device phases, for driving several ranks of one process in lockstep (tests):
+ * phase1 = kick, drift, leavers written to the neighbours; phase2 = append arrivals, bin + sort, boundary layers
+ * written to the neighbours; phase3 = unpack halos, pair kernel, kick, LOCAL sums.  Every rank must finish a phase
+ * before any rank starts the next one. */
 int atlj_sim_mg_phase1(atlj_sim *s, double dt);
 int atlj_sim_mg_phase2(atlj_sim *s);
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host);
-void *atlj_sim_mg_buffer(atlj_sim *s, int which);
-int64_t atlj_sim_mg_buffer_bytes(atlj_sim *s, int which);
-int atlj_device_copy(void *dst_dev, const void *src_dev, int64_t bytes);
 
 /* ---- host-buffer step (the end-to-end path of bench.py) --------------------------------------
  * One velocity-Verlet step (md_nve_lj.py:178-192) whose state lives in HOST memory, as it does in the
