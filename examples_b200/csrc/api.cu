@@ -166,10 +166,14 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
 
 // read back and clear the device error flags; maps to the reference's assertion codes
 int sim_check_flags(atlj_sim *s) {
-  int h[4] = {0, 0, 0, 0};
+  int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [0] index error, [1] capacity, [2..4] work / done counters, [5] peer timeout
   ATLJ_CUDA(cudaMemcpyAsync(h, s->cb.err, sizeof(h), cudaMemcpyDeviceToHost, s->st));
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
-  if (h[0] || h[1]) ATLJ_CUDA(cudaMemsetAsync(s->cb.err, 0, sizeof(h), s->st));
+  if (h[0] || h[1] || h[5]) ATLJ_CUDA(cudaMemsetAsync(s->cb.err, 0, sizeof(h), s->st));
+  if (h[5]) {
+    set_error("timed out waiting for a neighbour rank's message (slab exchange)");
+    return ATLJ_ERR_CUDA;
+  }
   if (h[0]) {
     set_error("Index error");
     return ATLJ_ERR_INDEX;

@@ -43,13 +43,20 @@ __device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
 }
 
 // the consumer side: spins until the producer (another GPU) has published the message of this step
-__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp) {
+// (gives up after ~4e9 clocks, about 2 s, and raises err[5]: a neighbour that died must not hang this GPU)
+__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp, int *err) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long t0 = clock64();
   for (const int *h : {hdr_a, hdr_b}) {
     int v;
-    do {
+    for (;;) {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(h + 1) : "memory");
-    } while (v != stamp);
+      if (v == stamp) break;
+      if (clock64() - t0 > 4000000000ll) {
+        atomicOr(&err[5], 1);
+        return;
+      }
+    }
   }
 }
 
@@ -283,7 +290,8 @@ static int phase2(atlj_sim *s, double *rec) {
   const int cur = s->cur, alt = 1 - cur;
   Timer::begin(s, 4);
   const unsigned char *ml = my_recv(m, 0, 0, par), *mr = my_recv(m, 0, 1, par);
-  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(ml), reinterpret_cast<const int *>(mr), stamp);
+  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(ml), reinterpret_cast<const int *>(mr), stamp,
+                                         s->cb.err);
   ATLJ_LAUNCHED();
   Timer::end(s);
   Timer::begin(s, 3);
@@ -327,7 +335,8 @@ static int phase3(atlj_sim *s) {
   const int *n_dev = m.cnt_dev + 1;
   const unsigned char *hl = my_recv(m, 1, 0, par), *hr = my_recv(m, 1, 1, par);
   Timer::begin(s, 6);
-  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(hl), reinterpret_cast<const int *>(hr), stamp);
+  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(hl), reinterpret_cast<const int *>(hr), stamp,
+                                         s->cb.err);
   ATLJ_LAUNCHED();
   Timer::end(s);
   Timer::begin(s, 3);
@@ -408,9 +417,18 @@ int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap) {
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };
   m.mig_bytes = up(sizeof(int) * HDR_INTS + sizeof(double) * 7 * (size_t)mig_cap);
   m.halo_bytes = up(sizeof(int) * (HDR_INTS + halo_counts_ints(s->g.sc)) + sizeof(double) * 3 * (size_t)halo_cap);
-  m.arena_bytes = 4 * m.mig_bytes + 4 * m.halo_bytes;
-  ATLJ_CUDA(cudaMalloc((void **)&m.arena, m.arena_bytes));
-  ATLJ_CUDA(cudaMemsetAsync(m.arena, 0, m.arena_bytes, s->st));
+  // 256 B tail holds a magic word the neighbours verify after mapping.  At least 8 MB and a multiple of 2 MB, so that
+  // the arena is an allocation of its own: cudaIpcGetMemHandle exports the whole underlying allocation, and small
+  // cudaMalloc blocks are carved out of shared 2 MB pages.
+  m.arena_bytes = 4 * m.mig_bytes + 4 * m.halo_bytes + 256;
+  const size_t alloc = ((m.arena_bytes > (8u << 20) ? m.arena_bytes : (8u << 20)) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  ATLJ_CUDA(cudaMalloc((void **)&m.arena, alloc));
+  ATLJ_CUDA(cudaMemsetAsync(m.arena, 0, alloc, s->st));
+  {
+    const unsigned long long magic = 0x61746c6a6d670001ull;  // "atljmg" 1
+    ATLJ_CUDA(cudaMemcpyAsync(m.arena + m.arena_bytes - 256, &magic, sizeof(magic), cudaMemcpyHostToDevice, s->st));
+    ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  }
   ATLJ_CUDA(cudaMalloc((void **)&m.cnt_dev, 16 * sizeof(int)));
   ATLJ_CUDA(cudaMemsetAsync(m.cnt_dev, 0, 16 * sizeof(int), s->st));
   ATLJ_CUDA(cudaHostAlloc((void **)&m.cnt_host, 16 * sizeof(int), cudaHostAllocDefault));
@@ -461,6 +479,12 @@ int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left64, const char *right64) {
     void *p = nullptr;
     ATLJ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     m.peer_arena[d] = (unsigned char *)p, m.peer_ipc[d] = true;
+    unsigned long long magic = 0;  // the mapping must show the neighbour's arena, not some other part of its memory
+    ATLJ_CUDA(cudaMemcpy(&magic, m.peer_arena[d] + m.arena_bytes - 256, sizeof(magic), cudaMemcpyDeviceToHost));
+    if (magic != 0x61746c6a6d670001ull) {
+      set_error("mg_ipc_open: the mapped peer buffer does not carry the arena signature (IPC mapping offset)");
+      return ATLJ_ERR_CUDA;
+    }
   }
   return ATLJ_OK;
 }

@@ -51,7 +51,9 @@ def capacities(n_total, sc, nx_own, slack=1.5):
     """Per-rank buffer sizes (atoms): owned + halo capacity, migration message, halo message."""
     per_layer = n_total / sc
     halo_cap = int(per_layer * slack) + 1024
-    mig_cap = max(4096, int(per_layer * 0.05))
+    # migration message: in a liquid ~1e-3 of a layer crosses a face per step, but a run that starts from the lattice
+    # can have a whole atomic plane sitting on a slab boundary, half of which crosses at once
+    mig_cap = max(4096, int(per_layer * 0.6))
     cap = int(per_layer * nx_own * 1.25) + 2 * halo_cap + 2 * mig_cap + 1024
     return cap, mig_cap, halo_cap
 
