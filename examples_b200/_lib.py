@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libatlj.so")
+LIB_PATH = os.environ.get("ATLJ_LIB", os.path.join(_HERE, "libatlj.so"))  # ATLJ_LIB: A/B runs of another build
 
 OK, ERR_DIM, ERR_SMALL, ERR_INDEX, ERR_MISMATCH, ERR_CUDA, ERR_ARG = 0, -1, -2, -3, -4, -100, -101
 MODEL_LJ, MODEL_WCA = 0, 1

@@ -63,6 +63,16 @@ static int dev_alloc(T **p, size_t count) {
   return ATLJ_OK;
 }
 
+static int ensure_tile_tab(atlj_sim *s, int ints) {
+  if (ints <= s->tile_tab_ints) return ATLJ_OK;
+  cudaFree(s->tile_tab);
+  s->tile_tab = nullptr;
+  int rc = dev_alloc(&s->tile_tab, (size_t)ints);
+  if (rc) return rc;
+  s->tile_tab_ints = ints;
+  return ATLJ_OK;
+}
+
 static int ensure_cells(atlj_sim *s, int ncell) {
   if (ncell <= s->ncell_alloc) return ATLJ_OK;
   cudaFree(s->cb.cell_count);
@@ -126,17 +136,22 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.cell_count = s->cb.cell_count;
     a.f = s->f;
     a.partials = s->partials;
+    a.tile_tab = s->tile_tab;
+    a.natoms = (int)s->n;
     a.g = s->g;
     a.p = p;
     Timer::begin(s, 0);
     int nb;
-    if (s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ)
+    const bool tile2 = s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
+    if (tile2)
       nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
     else
       nb = launch_pair_tile(s->st, a, false);
     Timer::end(s);
     if (nb < 0) return nb;
-    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2))) return rc;
+    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2, nullptr, 0,
+                              tile2 ? s->cb.err + 6 : nullptr)))
+      return rc;
     if (with_hessian) {
       a.fin = s->f;
       a.f = nullptr;
@@ -263,7 +278,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   for (int k = 0; k < 2; k++) cudaFree(s->r[k]), cudaFree(s->v[k]), cudaFree(s->id[k]);
   cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
-  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials);
+  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials), cudaFree(s->tile_tab);
   if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
@@ -312,6 +327,7 @@ int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, 
   if (pair_tile2_items(g) > rows) rows = pair_tile2_items(g);
   int rc = ensure_partials(s, rows);
   if (rc) return rc;
+  if ((rc = ensure_tile_tab(s, pair_tile2_tab_ints(g)))) return rc;
   return ensure_cells(s, g.ncell());
 }
 
@@ -387,7 +403,8 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       const int cur = s->cur, alt = 1 - cur;
       Timer::begin(s, 2);
       const int nvf = launch_kdk_assign(s->st, s->g, n, s->r[cur], s->v[cur], s->f, half_dt, dt, p.box, k > 0, s->cb,
-                                        s->vf_partials, rec_prev, s->partials, nb_prev, p.model);
+                                        s->vf_partials, rec_prev, s->partials, nb_prev, p.model, nullptr,
+                                        tile2 ? s->cb.err + 6 : nullptr);
       if (nvf < 0) return nvf;
       Timer::end(s);
       Timer::begin(s, 1);
@@ -399,7 +416,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       s->cur = alt;
       PairArgs a;
       a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
-      a.f = s->f, a.partials = s->partials, a.g = s->g, a.p = p;
+      a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
       Timer::begin(s, 0);
       nb_prev = tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false);
       Timer::end(s);
@@ -407,7 +424,9 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       rec_prev = rec;
     }
     Timer::begin(s, 2);
-    if ((rc = launch_finalize(s->st, s->partials, nb_prev, p.model, false, rec_prev, s->cb.err + 2))) return rc;
+    if ((rc = launch_finalize(s->st, s->partials, nb_prev, p.model, false, rec_prev, s->cb.err + 2, nullptr, 0,
+                              tile2 ? s->cb.err + 6 : nullptr)))
+      return rc;
     if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_prev + 4))) return rc;
     Timer::end(s);
     s->step_count += nsteps;
@@ -609,6 +628,8 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.cell_count = s->cb.cell_count;
     a.f = nullptr;
     a.partials = s->partials;
+    a.tile_tab = s->tile_tab;
+    a.natoms = (int)s->n;
     a.g = s->g;
     a.p = p;
     nb = launch_pair_tile(s->st, a, true);

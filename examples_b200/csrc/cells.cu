@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
                                                         int *__restrict__ err, double *__restrict__ partials,
                                                         double *__restrict__ rec_vf,
                                                         const double *__restrict__ pair_partials, int pair_rows,
-                                                        int model, SlabArgs sl) {
+                                                        int model, SlabArgs sl, const int *__restrict__ pair_rows_dev) {
+  if (pair_rows_dev) pair_rows = min(pair_rows, *pair_rows_dev);
   // tiles of IT atoms: the 3*IT components are streamed with perfectly coalesced accesses (one component per thread
   // and pass), the wrapped coordinates (and, on a slab, the velocities) are parked in shared memory, then one thread
   // per atom does the integer part
@@ -248,13 +249,15 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
 // -> number of CTAs (= rows of vf partials written when first_kick)
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
-                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab) {
+                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab,
+                      const int *pair_rows_dev) {
   ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   const int nb = integ_blocks(n);
   SlabArgs sl = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
   if (slab) sl = *slab;
   kdk_assign_kernel<<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, first_kick ? 1 : 0, b.cellid, b.rank,
-                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model, sl);
+                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model, sl,
+                                       pair_rows_dev);
   ATLJ_LAUNCHED();
   return nb;
 }

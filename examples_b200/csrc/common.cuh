@@ -149,7 +149,8 @@ struct SlabArgs {
 // is given, the pair kernel's totals (per-item rows reduced in fixed order) are written by the kernel's last CTA
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
-                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab = nullptr);
+                      const double *pair_partials, int pair_rows, int model, const SlabArgs *slab = nullptr,
+                      const int *pair_rows_dev = nullptr);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
@@ -163,7 +164,9 @@ struct PairArgs {
   const int *cell_start;
   const int *cell_count;
   double *f;             // sorted forces out (force mode)
-  double *partials;      // [grid][8]
+  double *partials;      // [rows][8]
+  int *tile_tab;         // work-item table of pair_tile2 (pair_tile2_tab_ints)
+  int natoms;            // owned atoms (a hint for the work-item size; 0 = unknown)
   Geom g;
   Phys p;
 };
@@ -173,16 +176,18 @@ int launch_pair_tile(cudaStream_t st, const PairArgs &a, bool hessian);  // -> C
 int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the second-generation LJ kernel
 // -> items (= rows of partials written) or a negative status; *work_counter must be 0 on entry (launch_finalize and
 // the fused integration kernel reset it)
-// xo_count < 0: all owned x layers; otherwise layers xo_first + k*xo_step, k < xo_count, rows written from row0 on
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int xo_first = 0, int xo_step = 1,
-                      int xo_count = -1, int parts = 0, int row0 = 0);
-int pair_tile2_max_parts(const Geom &g);
+// The number of rows actually written is stored by the kernel in work_counter[4] (device); the reducers take that
+// pointer (rows_dev) next to the upper bound returned here.
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);
+int pair_tile2_tab_ints(const Geom &g);  // ints of PairArgs::tile_tab for this geometry
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)
-// (also zeroes *reset_counter, the work counter of the tiled kernel, when it is not null)
+// (also zeroes *reset_counter, the work counter of the tiled kernel, when it is not null; rows_dev, when not null,
+// holds the number of rows on the device and nblocks is only an upper bound)
 // vf_partials (may be null): [nvf][4] partial {sum v^2, sum f^2} of the integration kernel, reduced into rec[4], rec[5]
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
-                    int *reset_counter = nullptr, const double *vf_partials = nullptr, int nvf = 0);
+                    int *reset_counter = nullptr, const double *vf_partials = nullptr, int nvf = 0,
+                    const int *rows_dev = nullptr);
 
 }  // namespace atlj

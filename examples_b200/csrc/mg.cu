@@ -262,6 +262,11 @@ static inline unsigned char *peer_recv(const MgState &m, int kind, int dir, int 
   return m.peer_arena[dir] + arena_off(m, kind, 1 - dir, parity);
 }
 
+// device-side row count of the tiled LJ kernel's partials (null for the other pair kernels)
+static const int *tile2_rows(atlj_sim *s) {
+  return (s->pair_kernel == 0 && s->p.model == ATLJ_MODEL_LJ) ? s->cb.err + 6 : nullptr;
+}
+
 // ---- the phases -----------------------------------------------------------------------------------------------------------
 // The number of owned atoms changes every step and lives on the device (cnt_dev[1]); kernels are launched over the
 // capacity and read it, so a step needs no host synchronisation.  The host copy s->n is refreshed at the end of a run.
@@ -277,7 +282,8 @@ static int phase1(atlj_sim *s, double dt, bool first_kick, double *rec_prev, int
   sl.mig_cap = (int)m.mig_cap, sl.stamp = (int)(m.step + 1), sl.mig_cnt = m.cnt_dev + 4;
   Timer::begin(s, 2);
   const int nb = launch_kdk_assign(s->st, s->g, (int)s->cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
-                                   first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev, s->p.model, &sl);
+                                   first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev, s->p.model, &sl,
+                                   tile2_rows(s));
   Timer::end(s);
   return nb < 0 ? nb : ATLJ_OK;
 }
@@ -321,7 +327,7 @@ static int phase2(atlj_sim *s, double *rec) {
 static PairArgs pair_args(atlj_sim *s) {
   PairArgs a;
   a.r = s->r[s->cur], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
-  a.f = s->f, a.partials = s->partials, a.g = s->g, a.p = s->p;
+  a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = s->p;
   a.p.strain = 0.0, a.p.shift = 0;
   return a;
 }
@@ -358,7 +364,8 @@ static int phase3(atlj_sim *s) {
 // the record of the last step of a run: pair totals, trailing half kick, sum v^2, sum f^2
 static int tail(atlj_sim *s, double dt, double *rec, int nb) {
   int rc;
-  if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2))) return rc;
+  if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s))))
+    return rc;
   Timer::begin(s, 2);
   rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->mg.cnt_dev + 1);
   Timer::end(s);

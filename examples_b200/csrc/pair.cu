@@ -99,7 +99,9 @@ constexpr int FIN_T = 1024;
 __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,
                                                          int hessian, double *__restrict__ rec,
                                                          int *__restrict__ reset_counter,
-                                                         const double *__restrict__ vf_partials, int nvf) {
+                                                         const double *__restrict__ vf_partials, int nvf,
+                                                         const int *__restrict__ rows_dev) {
+  if (rows_dev) nblocks = min(nblocks, *rows_dev);
   if (threadIdx.x == 0 && reset_counter) *reset_counter = 0;
   __shared__ double sm[FIN_T / 32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -133,8 +135,9 @@ __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restric
 }
 
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
-                    int *reset_counter, const double *vf_partials, int nvf) {
-  finalize_kernel<<<1, FIN_T, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter, vf_partials, nvf);
+                    int *reset_counter, const double *vf_partials, int nvf, const int *rows_dev) {
+  finalize_kernel<<<1, FIN_T, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter, vf_partials, nvf,
+                                       rows_dev);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -19,9 +19,13 @@
 
 namespace atlj {
 
-constexpr int U_NT = 128;               // threads per CTA = i atoms per batch
-constexpr int U_CAP = 1280;             // staged candidates per chunk
-constexpr int U_MAXC = 24;              // logical cells per chunk, including one halo cell at each end
+#ifndef ATLJ_U_NT
+#define ATLJ_U_NT 128
+#endif
+constexpr int U_NT = ATLJ_U_NT;         // threads per CTA = i atoms per batch
+constexpr int U_CTAS = U_NT == 128 ? 4 : 2;                // resident CTAs per SM (registers: 128 per thread)
+constexpr int U_CAP = U_NT == 128 ? 1280 : 2304;           // staged candidates per chunk
+constexpr int U_MAXC = U_NT == 128 ? 24 : 32;              // logical cells per chunk, incl. one halo cell at each end
 constexpr int U_K = 12;                 // staged rows per z cell: 4 y-offsets (outer) x 3 x-offsets (inner)
 constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
 constexpr int U_WW = 6;                 // mask words per window (<= 191 candidates per window)
@@ -31,21 +35,52 @@ static inline size_t tile2_smem_bytes() {
   return sizeof(double) * 3 * U_CAP + sizeof(float4) * (U_CAP + 2) + sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
 }
 
-int pair_tile2_parts(const Geom &g) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char *e = getenv("ATLJ_TILE_PARTS");
-    forced = e ? atoi(e) : 0;
-  }
-  int maxp = g.sc / 4 < 1 ? 1 : g.sc / 4;
-  if (forced > 0) return forced > maxp ? maxp : forced;
-  int rows2 = g.nx_own * ((g.sc + 1) / 2);
-  int want = (148 * 4 * 8 + rows2 - 1) / rows2;  // ~8 items per resident CTA (measured best at 2 M atoms)
-  return want < 1 ? 1 : (want > maxp ? maxp : want);
+constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps every SM busy) .. 4
+
+// Work items.  A row pair (two adjacent y rows of one x layer) is cut greedily into chunks of whole cells holding
+// <= U_NT atoms; gk consecutive chunks are one work item.  tile2_table_kernel records where every item starts
+// (tab layout: [0] = largest number of items of any row pair, [16 .. 16+nrp) = items per row pair, then
+// [nrp][gstride] start cells), so that items are handed out chunk-exact: no partly filled chunk except the last one of
+// a row pair, and the tail of the grid is at most gk chunks long.  Item t = (group t / nrp, row pair t % nrp).
+static inline int tile2_gstride(const Geom &g) { return g.sc + 2; }  // gk = 1: at most one item per cell
+int pair_tile2_tab_ints(const Geom &g) {
+  const int nrp = g.nx_own * ((g.sc + 1) / 2);
+  return 16 + nrp + nrp * tile2_gstride(g);
 }
-int pair_tile2_max_parts(const Geom &g) { return g.sc / 4 < 1 ? 1 : g.sc / 4; }
-// upper bound of the partial rows any combination of launches over this geometry writes
-int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * pair_tile2_max_parts(g); }
+// upper bound of the partial rows a launch over this geometry writes
+int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * (tile2_gstride(g) - 1); }
+
+__global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__restrict__ cs, int nyb, int nrp,
+                                                          int gstride, int gk, int *__restrict__ tab) {
+  __shared__ int cnt[4][1024];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int rp = blockIdx.x * 4 + w;
+  if (rp >= nrp) return;
+  const int sc = g.sc;
+  const int xo = rp / nyb, yb = rp - xo * nyb;
+  const int lx = g.h + xo, y0 = 2 * yb;
+  const bool two = (y0 + 1 < sc);
+  const int ownA0 = g.cs_idx((lx * sc + y0) * sc), ownB0 = ownA0 + sc;
+  for (int c = lane; c < sc; c += 32)
+    cnt[w][c] = (cs[ownA0 + c + 1] - cs[ownA0 + c]) + (two ? cs[ownB0 + c + 1] - cs[ownB0 + c] : 0);
+  __syncwarp();
+  if (lane != 0) return;
+  int *zb = tab + 16 + nrp + (size_t)rp * gstride;
+  int z = 0, nch = 0, ng = 0;
+  while (z < sc) {
+    if (nch % gk == 0) zb[ng++] = z;
+    // same rule as the kernel's chunk extent: as many whole cells as hold <= U_NT atoms, at least one, at most
+    // U_MAXC - 2
+    int acc = 0, ncz = 0;
+    while (z + ncz < sc && ncz < U_MAXC - 2 && acc + cnt[w][z + ncz] <= U_NT) acc += cnt[w][z + ncz], ncz++;
+    if (ncz == 0) ncz = 1;
+    z += ncz;
+    nch++;
+  }
+  zb[ng] = sc;
+  tab[16 + rp] = ng;
+  atomicMax(&tab[0], ng);
+}
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
@@ -103,9 +138,9 @@ __device__ __forceinline__ double rcp46(double s) {
     }                                                                                  \
   } while (0)
 
-__global__ void __launch_bounds__(U_NT, 4)
-    pair_tile2_kernel(PairArgs a, int parts, int nyb, int nitems, int *__restrict__ work_counter, int xo_first,
-                      int xo_step, int row0) {
+__global__ void __launch_bounds__(U_NT, U_CTAS)
+    pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, const int *__restrict__ tab,
+                      int *__restrict__ work_counter, int *__restrict__ rows_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
   double *uy = ux + U_CAP;
@@ -137,12 +172,18 @@ __global__ void __launch_bounds__(U_NT, 4)
     if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u, s_maxwin = 0;
     __syncthreads();
     const int item = s_item;
+    const int nitems = tab[0] * nrp;
+    if (item == 0 && tid == 0) *rows_out = nitems;
     if (item >= nitems) break;
-    const int part = item % parts, t2 = item / parts;
-    const int yb = t2 % nyb, xo = xo_first + (t2 / nyb) * xo_step;  // owned x layer of this item
+    const int grp = item / nrp, rp = item - grp * nrp;
+    if (grp >= tab[16 + rp]) {  // this row pair has fewer items than the longest one: an all-zero row of partials
+      if (tid < 8) a.partials[8 * (size_t)item + tid] = 0.0;
+      continue;
+    }
+    const int xo = rp / nyb, yb = rp - xo * nyb;  // owned x layer, row pair of this item
     const int lx = g.h + xo, y0 = 2 * yb;
     const bool two = (y0 + 1 < sc);
-    const int zA = (int)((long long)sc * part / parts), zB = (int)((long long)sc * (part + 1) / parts);
+    const int zA = tab[16 + nrp + (size_t)rp * gstride + grp], zB = tab[16 + nrp + (size_t)rp * gstride + grp + 1];
     const int ownA0 = g.cs_idx((lx * sc + y0) * sc), ownB0 = ownA0 + sc;  // rows in the padded cell_start
     if (tid < U_K) {
       // row k = yi*3 + xi holds cells (lx-1+xi, y0-1+yi); yi = 0..2 are the dy = -1,0,1 neighbours of row y0 and
@@ -207,7 +248,9 @@ __global__ void __launch_bounds__(U_NT, 4)
 #pragma unroll
         for (int w = 0; w < U_NT / 32; w++)
           if (w < warp) off += wsum[w];
-        total = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+        total = 0;
+#pragma unroll
+        for (int w = 0; w < U_NT / 32; w++) total += wsum[w];
 #pragma unroll
         for (int u = 0; u < 3; u++) {
           const int e = 3 * tid + u;
@@ -455,15 +498,13 @@ __global__ void __launch_bounds__(U_NT, 4)
       acc.np = npf;
       acc.ovr = ovr;
     }
-    block_store_partials<U_NT / 32>(acc, a.partials + 8 * (size_t)(row0 + item));
+    block_store_partials<U_NT / 32>(acc, a.partials + 8 * (size_t)item);
   }
 }
 
-// The owned x layers xo_first, xo_first + xo_step, ... (xo_count of them; default = all) are processed; partial rows
-// are written from row0 on.  A slab rank launches its interior layers while the halo is still in flight and the two
-// boundary layers afterwards.  parts <= 0 selects the default split of the rows along z.
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int xo_first, int xo_step, int xo_count,
-                      int parts, int row0) {
+// -> upper bound of the partial rows written, or a negative status.  The exact number of rows (items) is known on
+// the device only: the kernel stores it in *rows_out (work_counter + 4), which the reducers read.
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
   static int grid = 0;
   const size_t smem = tile2_smem_bytes();
   if (grid == 0) {
@@ -474,15 +515,23 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
     ATLJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     grid = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  if (xo_count < 0) xo_first = 0, xo_step = 1, xo_count = a.g.nx_own;
-  if (xo_count == 0) return 0;
-  if (parts <= 0) parts = pair_tile2_parts(a.g);
-  const int nyb = (a.g.sc + 1) / 2;
-  const int nitems = xo_count * nyb * parts;
-  pair_tile2_kernel<<<grid < nitems ? grid : nitems, U_NT, smem, st>>>(a, parts, nyb, nitems, work_counter, xo_first,
-                                                                     xo_step, row0);
+  if (a.g.sc > 1024 || !a.tile_tab) {
+    set_error("pair_tile2: sc = %d exceeds 1024 cells per edge or the item table is missing", a.g.sc);
+    return ATLJ_ERR_ARG;
+  }
+  const int nyb = (a.g.sc + 1) / 2, nrp = a.g.nx_own * nyb, gstride = tile2_gstride(a.g);
+  // chunks per item: about 8 items per resident CTA, at least 1 (small systems), at most U_GK_MAX
+  const long long chunks = (a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells()) / (U_NT - U_NT / 8) + nrp;
+  int gk = (int)(chunks / (8ll * grid));
+  gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
+  ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
+  tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, a.tile_tab);
   ATLJ_LAUNCHED();
-  return nitems;
+  const int bound = nrp * (gstride - 1);
+  pair_tile2_kernel<<<grid < bound ? grid : bound, U_NT, smem, st>>>(a, nyb, nrp, gstride, a.tile_tab, work_counter,
+                                                                    work_counter + 4);
+  ATLJ_LAUNCHED();
+  return bound;
 }
 
 }  // namespace atlj
