@@ -9,8 +9,10 @@ Workloads (BASELINE.json configs; --workload):
   c5 (default)  NVE LJ weak scaling, fcc nc=80 -> 2,048,000 atoms per GPU (nc=101/127/160 at 2/4/8 GPUs), rho=0.75,
                 r_cut=2.5, dt=0.005, melted before timing.  This is the configuration the metric
                 ("atom-steps/s at 1/2/4/8 B200") is quoted on; its state (~350 MB) exceeds the 126 MB L2.
-  c2            md_nve_lj + md_lj_ll_module, N=32,000 (launch-latency bound on a B200; reported under "other").
+  c2            md_nve_lj + md_lj_ll_module, N=32,000 (launch-latency bound on a B200).
   c4            N=1,000,188.
+The default line also carries "other_workloads": short runs of c1 (N=256 all pairs), c2, c3 (SLLOD, WCA, N=256,000) and
+c4 (BAOAB, N=1,000,188) for information.
 A "step" is one velocity-Verlet step of md_nve_lj.py:178-192: kick, drift+wrap, cell build, pair force, kick, sums.
 
 `value`    atoms * steps / device time of the device-resident loop (CUDA events on the launching stream, max over
@@ -156,6 +158,50 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_workloads():
+    """Short device-resident runs of the other BASELINE.json configurations (information only, not the headline):
+    c1 N=256 all pairs, c2 N=32,000 NVE, c3 N=256,000 WCA Lees-Edwards SLLOD at strain rate 0.01, c4 N=1,000,188
+    BAOAB with the device Gaussian RNG.  -> {name: {atom_steps_per_s, ms_per_step, n}}"""
+    from examples_b200.device import Simulation
+    from examples_b200.lattice import fcc_positions, ran_velocities
+    out = {}
+
+    def timed(tag, sim, n, fn, steps):
+        sim.sync()
+        sim.timer_start()
+        fn(steps)
+        ms = sim.timer_stop()
+        out[tag] = {"n": n, "ms_per_step": ms / steps, "atom_steps_per_s": n * steps / (ms * 1e-3)}
+
+    for tag, nc, steps in (("c1_nve_n256_allpairs", 4, 2000), ("c2_nve_n32000", 20, 1000)):
+        n, box, r, v = make_system(nc)
+        sim = Simulation(box, R_CUT, r, v)
+        sim.force()
+        sim.run_nve(DT, 1000, record=False)
+        timed(tag, sim, n, lambda k: sim.run_nve(DT, k, record=False), steps)
+        sim.close()
+    n, box, r = fcc_positions(40, DENSITY)
+    r = r + np.random.default_rng(1).normal(0.0, 0.05 / box, size=r.shape)  # the perfect lattice has no WCA pair
+    r = np.ascontiguousarray(r - np.rint(r))
+    sim = Simulation(box, None, r, ran_velocities(n, 1.0), model="wca")
+    sim.force(strain=0.0)
+    st = {"strain": 0.0}
+
+    def sllod(k):
+        _, st["strain"] = sim.run_sllod(DT, 0.01, st["strain"], k)
+
+    sllod(400)
+    timed("c3_sllod_wca_n256000_rate0.01", sim, n, sllod, 200)
+    sim.close()
+    n, box, r, v = make_system(63)
+    sim = Simulation(box, R_CUT, r, v)
+    sim.force()
+    sim.run_baoab(DT, 1.0, 1.0, 500, seed=3)
+    timed("c4_baoab_n1000188", sim, n, lambda k: sim.run_baoab(DT, 1.0, 1.0, k, seed=3), 100)
+    sim.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -269,6 +315,10 @@ def run_ours(args, rank, world, local_rank):
         for a in (pr, pv, pf, pi):
             a.free()
 
+    other = None
+    if world == 1 and not args.no_other:
+        other = other_workloads()
+
     if rank != 0:
         return
     hbm_peak, hbm_src = peaks()
@@ -277,8 +327,13 @@ def run_ours(args, rank, world, local_rank):
     n_rank = n_total / world
     flops = FLOP_PER_PAIR * pairs_per_step / world
     ach = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_pair_traffic.json")
+    if os.path.exists(tp) and wl == "c5" and world == 1:  # dram bytes per launch from the committed ncu capture
+        td = json.load(open(tp))
+        traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
     roofline = {"kernel": "pair_tile2_kernel", "bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12,
-                "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": traffic,
                 "peak_source": "register-resident DFMA probe (atlj_measure_fp64_peak) in this run; "
                                "MEASURED_PEAKS.json has no fp64 figure",
                 "ms_per_launch": pair_ms, "flop_per_launch": flops,
@@ -292,9 +347,9 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         # bounded sample: nc=40 (256,000 atoms) of the same fluid; O(N) algorithm
         t0 = time.perf_counter()
-        cv, threads, cn, cdt = cpu_nve(40, 3, 1)
+        cv, threads, cn, cdt = cpu_nve(40, 150, 2)
         cpu = {"value": cv, "unit": "atom-steps/s", "cores": threads, "kind": "port",
-               "sample": "3 velocity-Verlet steps of N=%d (fcc nc=40 + Gaussian displacement), C restatement of the "
+               "sample": "150 velocity-Verlet steps of N=%d (fcc nc=40 + Gaussian displacement), C restatement of the "
                          "reference with OpenMP over cells, %.1f s" % (cn, time.perf_counter() - t0)}
 
     line = {
@@ -310,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
                    "temperature": temp, "pot_per_atom": epot, "pairs_per_atom": pairs_per_step / n_total,
                    "overlap": ovr, "melt_s": t_melt, "parallelism": "slab%d" % world if world > 1 else "single"},
         "e2e": e2e, "gpu_launches": int(l1 - l0), "clocks": clocks, "roofline": roofline,
-        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "other_workloads": other,
         "kernel_ms_per_step": {k: cat[k] / args.steps for k in cat},
     }
     print(json.dumps(line), flush=True)
@@ -328,6 +383,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c4"])
     ap.add_argument("--melt", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -8,7 +8,7 @@
 //                    arrival rank inside the cell                                  (reads 24 B, writes 8 B / atom)
 //   2. cell_scan   : exclusive scan of the histogram -> cell_start                 (4 B / cell, three small kernels)
 //   3. cell_scatter: key = (atom id << 32 | source index) -> slot cell_start + rank
-//   4. cell_sortgather: per block of 128 cells, keys to shared memory, one thread per cell orders its <= ~30 keys
+//   4. cell_sortgather: per block of 32..128 cells, keys to shared memory, one thread per cell orders its <= ~30 keys
 //                    by atom id (the arrival rank of step 1 is scheduling dependent, the sorted result is not) ->
 //                    "ascending atom index" of the reference; then r (and v, id) are gathered into cell order
 // All HBM-bound; see DESIGN.md for bytes per atom.
@@ -439,15 +439,18 @@ __device__ __forceinline__ void sort_cell_keys(unsigned long long *k, int n) {
 }
 
 // ---- 4+5. order each cell by atom id and gather r, v, id into cell order ----------------------------------------
-// One CTA takes SG_CELLS consecutive owned cells: their keys are one contiguous run of slots, which is loaded into
+// One CTA takes cpb (32..128) consecutive owned cells: their keys are one contiguous run of slots, which is loaded into
 // shared memory with coalesced reads, sorted there (one thread per cell; the arrival rank of step 1 is scheduling
 // dependent, the sorted result is not -> "ascending atom index" of md_lj_ll_module.py:118-119), and then drives the
 // gather: one thread per (atom, component), so the writes of r, v in cell order are perfectly coalesced.  A run that
 // does not fit (crowded cells) is sorted in global memory instead.
-constexpr int SG_CELLS = 128;
+constexpr int SG_T = 256;      // most threads per CTA: the first `cpb` of them sort one cell each, all of them gather
 constexpr int SG_KEYS = 3072;  // 24 KB of keys per CTA
 
-__global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int base, int block0,
+// cells per CTA: 128 on large grids; fewer on small ones so that the gather still spreads over every SM
+static inline int sg_cells_per_block(int ncells) { return ncells >= 148 * 2 * 128 ? 128 : (ncells >= 148 * 2 * 64 ? 64 : 32); }
+
+__global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base, int block0, int cpb,
                                                                     const int *__restrict__ cell_start,
                                                                     const int *__restrict__ cell_count,
                                                                     unsigned long long *__restrict__ keys,
@@ -459,27 +462,27 @@ __global__ void __launch_bounds__(SG_CELLS) cell_sortgather_kernel(Geom g, int b
   __shared__ unsigned long long sk[SG_KEYS];
   __shared__ int s_lo, s_hi;
   const int nown = g.n_own_cells(), first = g.first_own_cell();
-  const int c0 = (block0 + blockIdx.x) * SG_CELLS;
+  const int c0 = (block0 + blockIdx.x) * cpb;
   const int c = c0 + threadIdx.x;
   int mystart = 0, mycnt = 0;
-  if (c < nown) {
+  if (threadIdx.x < cpb && c < nown) {
     mystart = cell_start[g.cs_idx(first + c)] - base;
     mycnt = cell_count[first + c];
   }
   if (threadIdx.x == 0) s_lo = mystart;
-  const int clast = min(c0 + SG_CELLS, nown) - 1;
-  if (c == clast) s_hi = mystart + mycnt;
+  const int clast = min(c0 + cpb, nown) - 1;
+  if (threadIdx.x < cpb && c == clast) s_hi = mystart + mycnt;
   __syncthreads();
   const int lo = s_lo, tot = s_hi - s_lo;
   const bool fits = tot <= SG_KEYS;
   unsigned long long *kbase = fits ? sk : keys + lo;
   if (fits) {
-    for (int s = threadIdx.x; s < tot; s += SG_CELLS) sk[s] = keys[lo + s];
+    for (int s = threadIdx.x; s < tot; s += blockDim.x) sk[s] = keys[lo + s];
     __syncthreads();
   }
   sort_cell_keys(kbase + (mystart - lo), mycnt);
   __syncthreads();
-  for (int e = threadIdx.x; e < 3 * tot; e += SG_CELLS) {
+  for (int e = threadIdx.x; e < 3 * tot; e += blockDim.x) {
     const int s = e / 3, k = e - 3 * s;
     const unsigned long long key = kbase[s];
     const size_t src = (size_t)(key & 0xffffffffull);
@@ -504,17 +507,20 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
     ATLJ_LAUNCHED();
   }
   const int nc = g.n_own_cells(), sc2 = g.sc * g.sc;
-  const int nblk = (nc + SG_CELLS - 1) / SG_CELLS;
+  const int cpb = sg_cells_per_block(nc);
+  const int nblk = (nc + cpb - 1) / cpb;
   int lo = 0, hi = nblk;  // interior blocks [lo, hi)
   if (which != 0) {
-    lo = (sc2 + SG_CELLS - 1) / SG_CELLS;
-    hi = (nc - sc2) / SG_CELLS;
+    lo = (sc2 + cpb - 1) / cpb;
+    hi = (nc - sc2) / cpb;
     if (hi < lo) lo = hi = nblk;  // one or two layers: everything is boundary
   }
   auto run = [&](int b0, int cnt) -> int {
     if (cnt <= 0) return ATLJ_OK;
-    cell_sortgather_kernel<<<cnt, SG_CELLS, 0, st>>>(g, base, b0, b.cell_start, b.cell_count, b.keys, r_in, v_in, r_out,
-                                                     v_out, id_out);
+    // large grids: 128 cells and 128 threads per CTA (measured best at 2 M atoms); small grids: fewer cells per CTA
+    // and twice the threads for the gather
+    cell_sortgather_kernel<<<cnt, cpb == 128 ? 128 : SG_T, 0, st>>>(g, base, b0, cpb, b.cell_start, b.cell_count,
+                                                                    b.keys, r_in, v_in, r_out, v_out, id_out);
     ATLJ_LAUNCHED();
     return ATLJ_OK;
   };
