@@ -322,31 +322,55 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
         continue;
       }
 
-      // ---- stage the candidates: half a warp per (cell,row) entry ----------------------------------------------
+      // ---- stage the candidates: half a warp per (cell,row) entry, two entries in flight ------------------------------
       {
         const double ctrz = (z + 0.5 * ncz) * sci - 0.5;
         const int hw = tid >> 4, hl = tid & 15;
         float q2m = 0.f;
-        for (int e = hw; e < NE; e += U_NT / 16) {
-          const int s0 = S[e], cnt = S[e + 1] - s0;
-          if (cnt == 0) continue;
-          const int c = e / U_K;
-          const int lc = z - 1 + c;
-          const double wz = lc < 0 ? -1.0 : (lc >= sc ? 1.0 : 0.0);
-          const int g0 = egl[e];
-          for (int k = hl; k < cnt; k += 16) {
-            const size_t j = (size_t)(g0 + k);
-            const int s = s0 + k;
-            double x = a.r[3 * j] - ctrx, y = a.r[3 * j + 1] - ctry, zz = (a.r[3 * j + 2] + wz) - ctrz;
-            x -= rint(x);
-            y -= rint(y);
-            x *= box, y *= box, zz *= box;
-            ux[s] = x, uy[s] = y, uz[s] = zz;
-            const float fx = (float)x, fy = (float)y, fz = (float)zz;
-            const float n2 = fx * fx + fy * fy + fz * fz;
-            float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
-            d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
-            q2m = fmaxf(q2m, n2);
+        auto put = [&](int s, double x, double y, double zz, double wz) {
+          x -= ctrx, y -= ctry, zz = (zz + wz) - ctrz;
+          x -= rint(x);
+          y -= rint(y);
+          x *= box, y *= box, zz *= box;
+          ux[s] = x, uy[s] = y, uz[s] = zz;
+          const float fx = (float)x, fy = (float)y, fz = (float)zz;
+          const float n2 = fx * fx + fy * fy + fz * fz;
+          float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
+          d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
+          q2m = fmaxf(q2m, n2);
+        };
+        constexpr int HWS = U_NT / 16;  // half warps per CTA
+        constexpr int SE = 2;           // entries in flight per half warp (4 measured no better)
+        for (int e0 = hw; e0 < NE; e0 += SE * HWS) {
+          // entries e0, e0 + HWS, ...: issue the global loads of all of them before any is converted, so that a half
+          // warp pays one load latency per SE entries (ncu: the staging loop held 13 % of the stall samples)
+          int sE[SE], cE[SE], gE[SE];
+          double xE[SE], yE[SE], zE[SE], wE[SE];
+#pragma unroll
+          for (int u = 0; u < SE; u++) {
+            const int e = e0 + u * HWS;
+            const bool ok = e < NE;
+            sE[u] = ok ? S[e] : 0;
+            cE[u] = ok ? S[e + 1] - sE[u] : 0;
+            gE[u] = ok ? egl[e] : 0;
+            const int lc = z - 1 + e / U_K;
+            wE[u] = lc < 0 ? -1.0 : (lc >= sc ? 1.0 : 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < SE; u++) {
+            xE[u] = yE[u] = zE[u] = 0.0;
+            if (hl < cE[u]) {
+              const size_t j = (size_t)(gE[u] + hl);
+              xE[u] = a.r[3 * j], yE[u] = a.r[3 * j + 1], zE[u] = a.r[3 * j + 2];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SE; u++) {
+            if (hl < cE[u]) put(sE[u] + hl, xE[u], yE[u], zE[u], wE[u]);
+            for (int k = hl + 16; k < cE[u]; k += 16) {  // cells with more than 16 atoms
+              const size_t j = (size_t)(gE[u] + k);
+              put(sE[u] + k, a.r[3 * j], a.r[3 * j + 1], a.r[3 * j + 2], wE[u]);
+            }
           }
         }
         unsigned qb = __reduce_max_sync(FULL, __float_as_uint(q2m));
