@@ -114,7 +114,12 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, const int *__res
   }
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   for (long long c = gt; c < sc2; c += stride) cnt[c] = row[c + 1] - row[c];
-  for (long long e = gt; e < 3ll * total; e += stride) pos[e] = r_sorted[3 * (size_t)start + e];
+  // 16-byte stores towards the neighbour (the destination is 64-byte aligned; the source only 8-byte aligned)
+  const double *src = r_sorted + 3 * (size_t)start;
+  const long long n2 = (3ll * total) >> 1;
+  double2 *pos2 = reinterpret_cast<double2 *>(pos);
+  for (long long e = gt; e < n2; e += stride) pos2[e] = make_double2(src[2 * e], src[2 * e + 1]);
+  if (gt == 0 && ((3ll * total) & 1)) pos[3ll * total - 1] = src[3ll * total - 1];
   __shared__ int s_last;
   __threadfence_system();
   __syncthreads();
@@ -316,7 +321,7 @@ static int phase2(atlj_sim *s, double *rec) {
   Timer::end(s);
   s->cur = alt;
   Timer::begin(s, 5);
-  halo_pack_kernel<<<dim3(148, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
+  halo_pack_kernel<<<dim3(296, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
                                                     peer_recv(m, 1, 1, par), (int)m.halo_cap, stamp, m.cnt_dev + 8,
                                                     s->cb.err, m.cnt_dev + 1, rec);
   ATLJ_LAUNCHED();
@@ -349,7 +354,7 @@ static int phase3(atlj_sim *s) {
   halo_cs_kernel<<<2, 1024, 0, s->st>>>(g, hl, hr, n_dev, s->cb.cell_start, (long long)s->cap, (int)m.halo_cap,
                                         s->cb.err);
   ATLJ_LAUNCHED();
-  halo_copy_kernel<<<dim3(148, 2), 256, 0, s->st>>>(g, hl, hr, n_dev, (int)m.halo_cap, (long long)s->cap, s->r[s->cur]);
+  halo_copy_kernel<<<dim3(444, 2), 256, 0, s->st>>>(g, hl, hr, n_dev, (int)m.halo_cap, (long long)s->cap, s->r[s->cur]);
   ATLJ_LAUNCHED();
   Timer::end(s);
   const PairArgs a = pair_args(s);
