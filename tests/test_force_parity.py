@@ -216,3 +216,36 @@ def test_size_independent_properties_large():
     total4, f4 = md_lj_ll_module.force(box, 2.5, rs)
     for a, b in ((total4.pot, total.pot), (total4.vir, total.vir), (total4.lap, total.lap)):
         assert abs(a - b) < 1e-9 * abs(b)  # translation changes rounding of r, hence a few borderline pairs
+
+
+def test_sparse_gas_and_tiny_systems(oracle):
+    """Ragged inputs: a dilute gas (most cells empty, chunks span many cells), strongly non-uniform density (a slab of
+    liquid in an otherwise empty box), and systems of one or two atoms."""
+    from examples_b200 import md_lj_ll_module, md_lj_module
+    rng = np.random.default_rng(11)
+    # dilute gas: N = 600 in a box of 30 sigma -> sc = 12, 1728 cells, 0.35 atoms per cell
+    box = 30.0
+    r = rng.uniform(-0.5, 0.5, size=(600, 3))
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    t, fo, ovr, npair = oracle.force(r, box, 2.5, cells=True)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.maximum(np.abs(t), 1e-300)) < TOL and total.ovr == ovr
+    assert rel_err(f, fo) < TOL
+    # liquid slab: all atoms in a quarter of the box along y
+    n, b2, rl = liquid_like(12, 0.75, 0.05)
+    rl[:, 1] = rl[:, 1] * 0.25
+    b2 = b2 * 1.0
+    total, f = md_lj_ll_module.force(b2, 2.5, rl)
+    t, fo, ovr, npair = oracle.force(rl, b2, 2.5, cells=True)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert total.ovr == ovr and rel_err(f, fo) < TOL
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL
+    # two atoms, one atom
+    r2 = np.array([[0.0, 0.0, 0.0], [0.1, 0.0, 0.0]])
+    total, f = md_lj_module.force(10.0, 2.5, r2)       # separation 1.0 sigma: pot = 4*(1-1) - shift
+    t, fo, ovr, npair = oracle.force(r2, 10.0, 2.5, cells=False)
+    assert npair == 1 and abs(total.pot - t[1]) <= 1e-12 * abs(t[1]) and rel_err(f, fo) < TOL
+    total, f = md_lj_module.force(10.0, 2.5, r2[:1])
+    assert (total.cut, total.pot, total.vir, total.lap, total.ovr) == (0.0, 0.0, 0.0, 0.0, False) and not f.any()
+    total, f = md_lj_ll_module.force(10.0, 2.5, r2)     # same through the cell route (sc = 4)
+    assert abs(total.pot - t[1]) <= 1e-12 * abs(t[1]) and rel_err(f, fo) < TOL
