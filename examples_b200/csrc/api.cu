@@ -108,6 +108,12 @@ int sim_ensure_rec(atlj_sim *s, int64_t nrec) {
   return ATLJ_OK;
 }
 
+// cells of ~1 atom (WCA cut-off): the direct kernel; ATLJ_PAIR_KERNEL=tile1 keeps the tiled one for A/B runs
+static bool sim_direct(const atlj_sim *s) {
+  const long long cells = s->g.n_own_cells();
+  return s->use_cells && s->pair_kernel == 0 && !s->mg.on && cells > 0 && s->n < 3 * cells;
+}
+
 // ---- one force evaluation on the current positions ----------------------------------------------------------------------
 // Cell route: wrap+assign -> scan -> scatter/sort/gather (atoms re-ordered into cell order, buffers swapped) -> pair
 // kernel -> finalize.  All-pairs route (sc < 4): pair_all on the current order.
@@ -142,8 +148,11 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.p = p;
     Timer::begin(s, 0);
     int nb;
-    const bool tile2 = s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
-    if (tile2)
+    const bool direct = sim_direct(s);
+    const bool tile2 = !direct && s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
+    if (direct)
+      nb = launch_pair_direct(s->st, a, false, n);
+    else if (tile2)
       nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
     else
       nb = launch_pair_tile(s->st, a, false);
@@ -156,7 +165,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       a.fin = s->f;
       a.f = nullptr;
       Timer::begin(s, 3);
-      nb = launch_pair_tile(s->st, a, true);
+      nb = direct ? launch_pair_direct(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
       Timer::end(s);
       if (nb < 0) return nb;
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
@@ -325,6 +334,7 @@ int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, 
   int rows = pair_grid_blocks();
   if (pair_tile_grid(g) > rows) rows = pair_tile_grid(g);
   if (pair_tile2_items(g) > rows) rows = pair_tile2_items(g);
+  if (pair_direct_blocks((int)s->cap) > rows) rows = pair_direct_blocks((int)s->cap);
   int rc = ensure_partials(s, rows);
   if (rc) return rc;
   if ((rc = ensure_tile_tab(s, pair_tile2_tab_ints(g)))) return rc;
@@ -396,7 +406,8 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     p.strain = 0.0, p.shift = 0;
     int nb_prev = 0;
     double *rec_prev = nullptr;
-    const bool tile2 = s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;  // finishes its record inside the kernel
+    const bool direct = sim_direct(s);
+    const bool tile2 = !direct && s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
     for (int k = 0; k < nsteps; k++) {
       double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
       ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));
@@ -418,7 +429,8 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
       a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
       Timer::begin(s, 0);
-      nb_prev = tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false);
+      nb_prev = direct ? launch_pair_direct(s->st, a, false, n)
+                       : (tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false));
       Timer::end(s);
       if (nb_prev < 0) return nb_prev;
       rec_prev = rec;
@@ -632,7 +644,7 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.natoms = (int)s->n;
     a.g = s->g;
     a.p = p;
-    nb = launch_pair_tile(s->st, a, true);
+    nb = sim_direct(s) ? launch_pair_direct(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true);
     if (nb < 0) return nb;
   } else {
     if (check_index)

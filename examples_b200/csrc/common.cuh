@@ -180,6 +180,9 @@ int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the 
 // pointer (rows_dev) next to the upper bound returned here.
 int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);
 int pair_tile2_tab_ints(const Geom &g);  // ints of PairArgs::tile_tab for this geometry
+// direct link-cell kernel (cells of ~1 atom): one thread per owned atom, no staging
+int pair_direct_blocks(int n);
+int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n);
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)

@@ -94,6 +94,101 @@ int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, 
   return ATLJ_OK;
 }
 
+// ---- direct link-cell kernel for cells of ~1 atom (WCA cut-off) --------------------------------------------------------
+// With r_cut = 2^(1/6) the reference's cells hold about one atom and an atom has only ~29 candidates in its 27 (LE: up
+// to 30) neighbour cells.  Staging row segments in shared memory (pair_tile*.cu) buys nothing there; one thread per
+// atom walks the neighbour cells straight from the cell-sorted arrays (L1/L2 hits) with the reference's exact
+// arithmetic for every candidate.  Selected when the grid holds fewer than 3 atoms per cell.
+constexpr int DC_T = 128;
+
+constexpr int DC_LIST = 48;  // candidate slots per atom in shared memory (the mean is ~25 at the WCA cut-off)
+
+template <int MODEL, bool HESS>
+__global__ void __launch_bounds__(DC_T) pair_direct_kernel(PairArgs a, int n) {
+  constexpr bool LE = (MODEL == ATLJ_MODEL_WCA);
+  __shared__ int cand[DC_LIST * DC_T];  // [slot][thread]: conflict-free
+  const Geom g = a.g;
+  const Phys p = a.p;
+  const int i = blockIdx.x * DC_T + threadIdx.x;
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0ull, 0};
+  if (i < n) {
+    const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
+    const double scd = (double)g.sc;
+    // the atom's own cell, with the arithmetic of the cell assignment (md_lj_ll_module.py:108)
+    const int c0 = (int)floor(__dmul_rn(__dadd_rn(rix, 0.5), scd));
+    const int cy = (int)floor(__dmul_rn(__dadd_rn(riy, 0.5), scd));
+    const int cz = (int)floor(__dmul_rn(__dadd_rn(riz, 0.5), scd));
+    const int lx = c0 - g.x_lo + g.h;
+    double fix = 0.0, fiy = 0.0, fiz = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+    if (HESS) fix = a.fin[3 * (size_t)i], fiy = a.fin[3 * (size_t)i + 1], fiz = a.fin[3 * (size_t)i + 2];
+    auto one = [&](int j) {
+      double dx, dy, dz, s;
+      if (pair_sep<LE>(rix, riy, riz, a.r[3 * (size_t)j], a.r[3 * (size_t)j + 1], a.r[3 * (size_t)j + 2], p.strain,
+                       p.r_cut_box_sq, dx, dy, dz, s)) {
+        if (HESS)
+          pair_hess_term(p, dx, dy, dz, s, fix - a.fin[3 * (size_t)j], fiy - a.fin[3 * (size_t)j + 1],
+                         fiz - a.fin[3 * (size_t)j + 2], acc);
+        else
+          pair_force_term<MODEL>(p, dx, dy, dz, s, fx, fy, fz, acc);
+      }
+    };
+    // Pass 1 (cheap, divergent): collect the candidate indices.  The three z neighbours of one (dx, dy) slot are
+    // adjacent cells, i.e. ONE index range of the sorted arrays unless z wraps.
+    int cnt = 0;
+    auto range = [&](int j0, int j1) {
+      for (int j = j0; j < j1; j++) {
+        if (j == i) continue;
+        if (cnt < DC_LIST)
+          cand[(cnt++) * DC_T + threadIdx.x] = j;
+        else
+          one(j);  // list full (denser than expected): evaluate on the spot
+      }
+    };
+    // a slot outside the grid only happens after an index error (reported by the cell build): contribute nothing
+    const bool ok = lx >= g.h && lx < g.h + g.nx_own && cy >= 0 && cy < g.sc && cz >= 0 && cz < g.sc;
+    for (int kk = 0; ok && kk < MAX_NB / 3; kk++) {
+      const int nc = neighbour_cell(g, LE, p.shift, lx, cy, cz, 3 * kk + 1);  // the dz = 0 cell of the slot
+      if (nc < 0) continue;
+      const int idx = g.cs_idx(nc);
+      const int lo = cz > 0 ? idx - 1 : idx, hi = cz < g.sc - 1 ? idx + 2 : idx + 1;
+      range(a.cell_start[lo], a.cell_start[hi]);
+      if (cz == 0 || cz == g.sc - 1) {
+        const int w = cz == 0 ? idx + g.sc - 1 : idx - (g.sc - 1);
+        range(a.cell_start[w], a.cell_start[w + 1]);
+      }
+    }
+    // Pass 2 (expensive, nearly uniform trip count): the reference's arithmetic on every candidate
+    for (int c = 0; c < cnt; c++) one(cand[c * DC_T + threadIdx.x]);
+    if (!HESS) {
+      a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
+      a.f[3 * (size_t)i + 1] = 24.0 * fy;
+      a.f[3 * (size_t)i + 2] = 24.0 * fz;
+    }
+  }
+  block_store_partials<DC_T / 32>(acc, a.partials + 8 * (size_t)blockIdx.x);
+}
+
+int pair_direct_blocks(int n) { return (n + DC_T - 1) / DC_T > 0 ? (n + DC_T - 1) / DC_T : 1; }
+
+// -> CTAs launched (= rows of partials written) or a negative status; n = owned atoms (they come first in a.r)
+int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n) {
+  const int blocks = pair_direct_blocks(n);
+  if (a.p.model == ATLJ_MODEL_LJ) {
+    if (hessian)
+      pair_direct_kernel<ATLJ_MODEL_LJ, true><<<blocks, DC_T, 0, st>>>(a, n);
+    else
+      pair_direct_kernel<ATLJ_MODEL_LJ, false><<<blocks, DC_T, 0, st>>>(a, n);
+  } else {
+    if (hessian) {
+      set_error("hessian is defined for the LJ model only");
+      return ATLJ_ERR_ARG;
+    }
+    pair_direct_kernel<ATLJ_MODEL_WCA, false><<<blocks, DC_T, 0, st>>>(a, n);
+  }
+  ATLJ_LAUNCHED();
+  return blocks;
+}
+
 // ---- fixed-order reduction of the CTA partials + the reference's final scaling ------------------------------------
 constexpr int FIN_T = 1024;
 __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,

@@ -3,12 +3,15 @@ from the reference Python modules, and against the C oracle at sizes the referen
 
 Bars (BASELINE.json north_star): integer cell / neighbour work bit-exact; in-range pair count and overlap flag
 exact; energies, virials, Laplacian, forces <= 1e-10 relative (fp64, summation order differs)."""
+import os
+
 import numpy as np
 import pytest
 
 from conftest import WCA_R_CUT, liquid_like, rel_err
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-10
 LJ_TAGS = ["lj_n256_a0", "lj_n256_a0.1", "lj_n864_a0", "lj_n864_a0.1", "lj_n4000_a0", "lj_n4000_a0.1"]
 
@@ -249,3 +252,65 @@ def test_sparse_gas_and_tiny_systems(oracle):
     assert (total.cut, total.pot, total.vir, total.lap, total.ovr) == (0.0, 0.0, 0.0, 0.0, False) and not f.any()
     total, f = md_lj_ll_module.force(10.0, 2.5, r2)     # same through the cell route (sc = 4)
     assert abs(total.pot - t[1]) <= 1e-12 * abs(t[1]) and rel_err(f, fo) < TOL
+
+
+@pytest.mark.parametrize("n", [600, 1400])
+def test_direct_route_force_and_hessian(oracle, n):
+    """Grids with fewer than 3 atoms per cell take the direct per-atom kernel (csrc/pair.cu): LJ force, exact pair
+    count and hessian against the oracle; n = 1400 (74 candidates per atom) overflows the per-atom candidate list."""
+    import math
+    from examples_b200 import md_lj_ll_module
+    from examples_b200.md_lj_module import _force
+    box = 20.0                                            # sc = 8, 512 cells
+    rng = np.random.default_rng(n)
+    g = np.stack(np.meshgrid(*[np.arange(12)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    r = (g[rng.permutation(len(g))[:n]] + 0.5) / 12.0 - 0.5 + rng.normal(0.0, 0.01, (n, 3))   # no overlaps
+    r = np.ascontiguousarray(r - np.rint(r))
+    t, fo, ovr, npair = oracle.force(r, box, 2.5, cells=True)
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL and total.ovr == ovr
+    assert rel_err(f, fo) < TOL
+    rc, _, _, _, npair_g = _force(box, 2.5, r, math.floor(box / 2.5), 1)
+    assert rc == 0 and npair_g == npair
+    hes = md_lj_ll_module.hessian(box, 2.5, r, f)
+    ho = oracle.hessian(r, f, box, 2.5, cells=True)
+    assert abs(hes - ho) <= TOL * abs(ho)
+
+
+def test_tiled_wca_route_matches_direct(oracle):
+    """The tiled WCA/LE kernel (csrc/pair_tile.cu) is only chosen for >= 3 atoms per cell; ATLJ_PAIR_KERNEL=tile1 forces
+    it at the usual density so that it stays covered.  Runs in a child process because the switch is read at
+    sim creation from the environment."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from examples_b200 import md_lj_llle_module\n"
+        "from examples_b200.lattice import fcc_positions\n"
+        "n, box, r = fcc_positions(10, 0.8442)\n"
+        "r = r + np.random.default_rng(5).normal(0, 0.05 / box, r.shape)\n"
+        "r[:, 0] -= np.rint(r[:, 1]) * 0.31\n"
+        "r = np.ascontiguousarray(r - np.rint(r))\n"
+        "t, f = md_lj_llle_module.force(box, 0.31, r.copy())\n"
+        "np.save(sys.argv[1], np.concatenate([[t.pot, t.vir, t.lap, t.pyx], f.ravel()]))\n"
+    ) % ROOT
+    import os
+    import tempfile
+    out = {}
+    for tag, env in (("direct", {}), ("tile1", {"ATLJ_PAIR_KERNEL": "tile1"})):
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "o.npy")
+            subprocess.run([sys.executable, "-c", code, p], check=True, env={**os.environ, **env}, timeout=300)
+            out[tag] = np.load(p)
+    a, b = out["direct"], out["tile1"]
+    assert np.max(np.abs(a[:4] - b[:4]) / np.abs(a[:4])) < TOL
+    assert rel_err(a[4:].reshape(-1, 3), b[4:].reshape(-1, 3)) < TOL
+    from examples_b200.lattice import fcc_positions
+    n, box, r = fcc_positions(10, 0.8442)
+    r = r + np.random.default_rng(5).normal(0, 0.05 / box, r.shape)
+    r[:, 0] -= np.rint(r[:, 1]) * 0.31
+    r = np.ascontiguousarray(r - np.rint(r))
+    t, fo, ovr, npair = oracle.force(r, box, WCA_R_CUT, cells=True, le=True, strain=0.31)
+    assert np.max(np.abs(a[:4] - t) / np.abs(t)) < TOL and rel_err(a[4:].reshape(-1, 3), fo) < TOL
