@@ -68,6 +68,9 @@ def lib():
     L.atlj_sim_run_baoab.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp]
     L.atlj_sim_run_baoab_noise.argtypes = [_vp, C.c_double, C.c_double, C.c_double, _vp, C.c_int, _vp]
     L.atlj_sim_run_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
+    L.atlj_sim_run_npt.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.c_int, _vp]
     L.atlj_sim_run_sllod.argtypes = [_vp, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, _vp]
     L.atlj_sim_mg_enable.argtypes = [_vp, C.c_int64, C.c_int64]
     L.atlj_sim_set_total.restype = None

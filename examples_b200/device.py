@@ -27,7 +27,7 @@ class Simulation:
     """One GPU's worth of atoms.  `model` is 'lj' (cut-and-shifted LJ, totals cut,pot,vir,lap) or 'wca'
     (WCA + Lees-Edwards, totals pot,vir,lap,pyx)."""
 
-    def __init__(self, box, r_cut, r, v=None, model="lj", ids=None, capacity=None, stream=0, slab=None):
+    def __init__(self, box, r_cut, r, v=None, model="lj", ids=None, capacity=None, stream=0, slab=None, sc=None):
         L = _lib.lib()
         self.model = MODEL_LJ if model == "lj" else MODEL_WCA
         if self.model == MODEL_WCA:
@@ -45,6 +45,9 @@ class Simulation:
         sr6 = sr2 ** 3
         self.pot_cut = sr6 ** 2 - sr6
         self.sc = math.floor(self.box / self.r_cut)
+        if sc is not None:      # a coarser grid than the reference's finds the same pairs (cells wider than r_cut)
+            assert 1 <= sc <= self.sc, "cells must not be narrower than r_cut"
+            self.sc = int(sc)
         x_lo, x_hi = (0, max(self.sc, 1)) if slab is None else slab
         cap = int(capacity if capacity is not None else n + n // 8 + 1024)
         self._h = L.atlj_sim_create(cap, C.c_void_p(stream))
@@ -139,6 +142,28 @@ class Simulation:
         _lib.check(_lib.lib().atlj_sim_run_nhc(self._h, float(dt), float(temperature), float(g), len(q), _ptr(eta),
                                                _ptr(p_eta), _ptr(q), int(nsteps), _ptr(rec)))
         return rec
+
+    def run_npt(self, dt, temperature, pressure, eta, p_eta, q, eta_baro, p_eta_baro, q_baro, w_eps, box0, eps,
+                p_eps, nsteps, g=None):
+        """Constant-NPT steps (md_npt_lj.py:344-366).  The chain arrays are updated in place; returns
+        (records, eps, p_eps).  The box follows box0*exp(eps) (md_npt_lj.py:126): self.box, self.sc and the host
+        scalars are those of the last step on return; rec[:, 9] holds the box length after every step."""
+        rec = np.zeros((nsteps, NREC))
+        for a in (eta, p_eta, q, eta_baro, p_eta_baro, q_baro):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and len(a) == len(q)
+        if g is None:
+            g = 3 * (self.n_total - 1)
+        e, pe = C.c_double(float(eps)), C.c_double(float(p_eps))
+        _lib.check(_lib.lib().atlj_sim_run_npt(self._h, float(dt), float(temperature), float(pressure), self.r_cut,
+                                               float(g), len(q), _ptr(eta), _ptr(p_eta), _ptr(q), _ptr(eta_baro),
+                                               _ptr(p_eta_baro), _ptr(q_baro), float(w_eps), float(box0),
+                                               C.byref(e), C.byref(pe), int(nsteps), _ptr(rec)))
+        if nsteps > 0:
+            self.box = float(box0) * math.exp(e.value)
+            self.box_sq = self.box ** 2
+            self.r_cut_box_sq = (self.r_cut / self.box) ** 2
+            self.sc = math.floor(self.box / self.r_cut)
+        return rec, e.value, pe.value
 
     def run_sllod(self, dt, strain_rate, strain, nsteps):
         """-> records, strain after the last step (md_nvt_lj_le.py:226-240)."""

@@ -131,6 +131,17 @@ int atlj_sim_run_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, u
  * (md_nvt_lj.py:44). */
 int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m, double *eta, double *p_eta,
                      const double *q, int nsteps, double *rec_host);
+/* Constant-NPT steps (md_npt_lj.py:101-214 propagators, :344-366 loop): Nose-Hoover chains on the particles and on
+ * the barostat, chain length m <= 8, box = box0*exp(eps) updated every step (md_npt_lj.py:125-126) - the library
+ * re-derives the force path's scalars and the cell grid sc = floor(box/r_cut) from the new box each step
+ * (md_lj_ll_module.py:106; link_list_module.f90:112-120 regrows its cell array the same way).  eta, p_eta, eta_baro,
+ * p_eta_baro, eps, p_eps host in/out; q, q_baro host in.  The caller has run atlj_sim_force on the start state
+ * (md_npt_lj.py:335).  rec[9] = box after the step, rec[10] = the extended-system part of the conserved quantity
+ * (md_npt_lj.py:44-45).  Single domain, LJ. */
+int atlj_sim_run_npt(atlj_sim *s, double dt, double temperature, double pressure, double r_cut, double g, int m,
+                     double *eta, double *p_eta, const double *q, double *eta_baro, double *p_eta_baro,
+                     const double *q_baro, double w_eps, double box0, double *eps, double *p_eps, int nsteps,
+                     double *rec_host);
 /* Isokinetic SLLOD steps (md_nvt_lj_le.py:84-129,226-240); *strain host in/out. */
 int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strain, int nsteps, double *rec_host);
 

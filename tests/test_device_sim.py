@@ -123,6 +123,46 @@ def test_nhc_trajectory_golden(golden_dyn):
     sim.close()
 
 
+@pytest.mark.parametrize("tag", ["npt256", "npt2048"])
+def test_npt_trajectory_golden(tag):
+    """md_npt_lj.py:344-366 executed from the reference source (oracle/make_golden_npt.py) vs the device loop with
+    host-side chains: N=256 (all pairs, 100 steps) and N=2048, where the expanding box takes the link-cell grid from
+    sc=4 to sc=5 during the 40 steps."""
+    import math
+    from examples_b200.device import Simulation
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_npt.npz"))
+    box0, rec_g = float(g[tag + "_box0"]), g[tag + "_rec"]
+    sim = Simulation(box0, 2.5, g[tag + "_r0"], g[tag + "_v0"])
+    sc0 = sim.sc
+    sim.force()
+    m = len(g[tag + "_q"])
+    eta, p_eta, q = np.zeros(m), g[tag + "_p_eta0"].copy(), g[tag + "_q"].copy()
+    eta_b, p_eta_b, q_b = np.zeros(m), g[tag + "_p_eta_baro0"].copy(), g[tag + "_q_baro"].copy()
+    rec, eps, p_eps = sim.run_npt(0.005, 1.0, float(g[tag + "_pressure"]), eta, p_eta, q, eta_b, p_eta_b, q_b,
+                                  float(g[tag + "_w_eps"]), box0, 0.0, float(g[tag + "_p_eps0"]), rec_g.shape[0])
+    for k in range(6):
+        assert rel_err(rec[:, k], rec_g[:, k]) < 1e-9, k       # cut, pot, vir, lap, sum v^2, sum f^2
+    assert rel_err(rec[:, 9], rec_g[:, 6]) < 1e-12              # box length after every step
+    assert rel_err(rec[:, 10], rec_g[:, 7]) < 1e-9              # extended-system part of the conserved quantity
+    assert abs(eps - float(g[tag + "_eps1"])) < 1e-12 and abs(p_eps / float(g[tag + "_p_eps1"]) - 1) < 1e-9
+    for a, b in ((eta, "_eta1"), (p_eta, "_p_eta1"), (eta_b, "_eta_baro1"), (p_eta_b, "_p_eta_baro1")):
+        assert rel_err(a, g[tag + b]) < 1e-9, b
+    r, v, f = sim.download()
+    assert rel_err(r, g[tag + "_r1"]) < 1e-9 and rel_err(v, g[tag + "_v1"]) < 1e-9
+    assert abs(sim.box - rec_g[-1, 6]) < 1e-12 * sim.box and sim.sc == math.floor(rec_g[-1, 6] / 2.5)
+    if tag == "npt2048":
+        assert (sc0, sim.sc) == (4, 5), "the run must cross a cell-grid change"
+    # conserved quantity (md_npt_lj.py:81-83): kinetic + potential + P*V + extended terms, per atom
+    n = r.shape[0]
+    cons = (0.5 * rec[:, 4] + rec[:, 1] + float(g[tag + "_pressure"]) * rec[:, 9] ** 3 + rec[:, 10]) / n
+    assert np.std(cons) < 2e-3
+    # a second call continues from the stored state (pending thermostat factor flushed)
+    rec2, eps2, _ = sim.run_npt(0.005, 1.0, float(g[tag + "_pressure"]), eta, p_eta, q, eta_b, p_eta_b, q_b,
+                                float(g[tag + "_w_eps"]), box0, eps, p_eps, 5)
+    assert np.all(np.isfinite(rec2)) and abs(rec2[0, 9] / rec[-1, 9] - 1) < 1e-2
+    sim.close()
+
+
 @pytest.mark.parametrize("tag", ["le", "le_fast"])
 def test_sllod_trajectory_golden(golden_dyn, tag):
     """md_nvt_lj_le.py:226-240 executed from the reference source (golden) vs the device loop (WCA, Lees-Edwards

@@ -11,13 +11,15 @@ nc = int(sys.argv[1]) if len(sys.argv) > 1 else 80
 melt = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 n, box, r, v = make_system(nc)
-sim = Simulation(box, R_CUT, r, v)
+sc = int(os.environ["ATLJ_SC"]) if "ATLJ_SC" in os.environ else None   # coarser cell grid (skin experiments)
+sim = Simulation(box, R_CUT, r, v, sc=sc)
 sim.force()
 sim.run_nve(DT, melt, record=False)
 sim.enable_timing(True)
 sim.timing()
 rec = sim.run_nve(DT, steps)
 t = sim.timing()
+print("sc=%d " % sim.sc, end="")
 print("N=%d steps=%d pairs/atom=%.3f T=%.3f ms/step: pair %.4f cells %.4f integrate %.4f"
       % (n, steps, rec[-1, 8] / n, rec[-1, 4] / (3 * n - 3), t["pair"] / steps, t["cells"] / steps,
          t["integrate"] / steps))
