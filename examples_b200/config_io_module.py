@@ -1,0 +1,80 @@
+"""read_cnf_atoms / write_cnf_atoms of the reference's config_io_module.py (:30-48, :74-95) for multi-million-atom
+configurations: same file format, same signatures, same assertion messages; the text body is formatted / parsed on
+the GPU (csrc/cnf.cu), byte-for-byte what np.savetxt(fmt='%15.10f') writes and bit-for-bit what np.loadtxt returns.
+
+np.savetxt / np.loadtxt cost minutes at 16 M atoms (one Python-level format call per row); block-end checkpoints
+(md_nve_lj.py:194-196) would dominate a device-resident run.
+
+Only the fixed layout that write_cnf_atoms produces is accepted by read_cnf_atoms: a file in another notation
+(exponents, other widths, comments) raises - read those with the reference's own reader.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+FIELD = 16                      # '%15.10f' + one separator
+
+
+def _header(nn, box):
+    return ("{:15d}\n{:15.8f}".format(nn, box) + "\n").encode("ascii")     # config_io_module.py:82 + savetxt's newline
+
+
+def write_cnf_atoms(filename, nn, box, *args):
+    """Write out atomic configuration (config_io_module.py:74)."""
+    nargs = len(args)
+    assert nargs == 1 or nargs == 2, "{}{:d}".format('Wrong number of arguments ', nargs)
+    n, d = args[0].shape
+    assert n == nn, "r shape mismatch {:d}{:d}".format(n, nn)
+    assert d == 3, "r shape mismatch {:d}".format(d)
+    r = _lib.as_f64(args[0])
+    v = None
+    if nargs == 2:
+        n, d = args[1].shape
+        assert n == nn, "v shape mismatch {:d}{:d}".format(n, nn)
+        assert d == 3, "v shape mismatch {:d}".format(d)
+        v = _lib.as_f64(args[1])
+    cols = 3 if v is None else 6
+    body = np.empty(nn * cols * FIELD, dtype=np.uint8)
+    _lib.check(_lib.lib().atlj_cnf_format(r.ctypes.data, None if v is None else v.ctypes.data, nn, 1.0,
+                                          body.ctypes.data))
+    with open(filename, "wb") as f:
+        f.write(_header(nn, box))
+        body.tofile(f)
+
+
+def write_cnf_sim(filename, sim, with_v=True):
+    """Checkpoint a device-resident Simulation: write_cnf_atoms(filename, n, box, r*box, v) of md_nve_lj.py:196
+    without bringing r, v to the host as doubles - the un-sort, the scaling by box and the formatting are one kernel."""
+    nn, cols = sim.n_total, 6 if with_v else 3
+    body = np.empty(nn * cols * FIELD, dtype=np.uint8)
+    _lib.check(_lib.lib().atlj_sim_cnf_format(sim._h, 1 if with_v else 0, body.ctypes.data))
+    with open(filename, "wb") as f:
+        f.write(_header(nn, sim.box))
+        body.tofile(f)
+
+
+def read_cnf_atoms(filename, with_v=False):
+    """Read in atomic configuration (config_io_module.py:30)."""
+    with open(filename, "rb") as f:
+        n = int(f.readline())        # Number of atoms
+        box = float(f.readline())    # Simulation box length (assumed cubic)
+        start = f.tell()
+        size = os.fstat(f.fileno()).st_size - start
+        assert n > 0 and size % (n * FIELD) == 0, "{:d}{}{:d}".format(size, ' body bytes are not whole rows of ', n)
+        cols = size // (n * FIELD)
+        rows = n
+        assert rows == n, "{:d}{}{:d}".format(rows, ' rows not equal to ', n)
+        assert cols >= 3, "{:d}{}".format(cols, ' cols less than 3')
+        if with_v:
+            assert cols >= 6, "{:d}{}".format(cols, ' cols less than 6')
+        body = np.fromfile(f, dtype=np.uint8, count=size)
+    r = np.empty((n, 3))
+    v = np.empty((n, 3)) if with_v else None
+    _lib.check(_lib.lib().atlj_cnf_parse(body.ctypes.data, n, int(cols), r.ctypes.data,
+                                         None if v is None else v.ctypes.data))
+    if with_v:
+        return n, box, r, v
+    return n, box, r

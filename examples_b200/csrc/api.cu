@@ -22,7 +22,7 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-static int device_ok() {
+int device_ok() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) {

@@ -10,6 +10,7 @@ namespace atlj {
 
 // ---- error plumbing -----------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
+int device_ok();  // ATLJ_OK, or ATLJ_ERR_CUDA with the message set (the library has no CPU path)
 extern int64_t g_launches;  // kernels launched by this library (atlj_kernel_launches)
 
 #define ATLJ_CUDA(call)                                                                          \

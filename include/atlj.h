@@ -188,6 +188,22 @@ int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_hos
 void *atlj_host_alloc(int64_t bytes); /* page-locked host memory (cudaHostAlloc); NULL on failure */
 void atlj_host_free(void *p);
 
+/* ---- configuration files (config_io_module.py:30-48 read_cnf_atoms, :74-95 write_cnf_atoms) ----------------
+ * The body of a cnf file is np.savetxt(fmt='%15.10f'): n*cols fields of 15 characters + one separator (' ' between
+ * columns, '\n' after the last), cols = 3 (r) or 6 (r, v).  Both directions run on the GPU, one thread per field,
+ * bit-exact: format = glibc's correctly rounded '%.10f' (128-bit integer arithmetic on the exact binary value),
+ * parse = the correctly rounded value of the decimal string (what np.loadtxt returns).  The two header lines
+ * ("{:15d}\n{:15.8f}", n and box) are the caller's.  ATLJ_ERR_ARG (with a message) for values that do not fit a
+ * 15-character field, NaN/Inf, or a body that is not in this fixed layout. */
+/* r_host (n,3) [times scale_r, separately rounded like the drivers' r*box], v_host (n,3) or NULL ->
+ * out_host[n*cols*16] */
+int atlj_cnf_format(const double *r_host, const double *v_host, int64_t n, double scale_r, char *out_host);
+/* text_host[n*cols*16] -> r_host (n,3), v_host (n,3) or NULL (then columns >= 3 are checked but not returned) */
+int atlj_cnf_parse(const char *text_host, int64_t n, int cols, double *r_host, double *v_host);
+/* The device-resident state as a cnf body in the ORIGINAL atom order: positions times box (md_nve_lj.py:196 writes
+ * r*box), velocities if with_v; the un-sort by atom id is fused into the formatting kernel. */
+int atlj_sim_cnf_format(atlj_sim *s, int with_v, char *out_host);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* CUDA-event stopwatch on the sim's stream: start records an event, stop records a second one, waits for it
  * and returns the elapsed device milliseconds. */
