@@ -12,7 +12,7 @@ Workloads (BASELINE.json configs; --workload):
   c2            md_nve_lj + md_lj_ll_module, N=32,000 (launch-latency bound on a B200).
   c4            N=1,000,188.
 The default line also carries "other_workloads": short runs of c1 (N=256 all pairs), c2, c3 (SLLOD, WCA, N=256,000) and
-c4 (BAOAB, N=1,000,188) for information.
+c4 (BAOAB, N=1,000,188; plus the constant-NPT loop on the same system) for information.
 A "step" is one velocity-Verlet step of md_nve_lj.py:178-192: kick, drift+wrap, cell build, pair force, kick, sums.
 
 `value`    atoms * steps / device time of the device-resident loop (CUDA events on the launching stream, max over
@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
                                    "Fortran twin cannot be built" % (args.steps, n, nc)},
         "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def other_workloads():
@@ -198,6 +198,21 @@ def other_workloads():
     sim.force()
     sim.run_baoab(DT, 1.0, 1.0, 500, seed=3)
     timed("c4_baoab_n1000188", sim, n, lambda k: sim.run_baoab(DT, 1.0, 1.0, k, seed=3), 100)
+    sim.run_nve(DT, 500, record=False)
+    # constant-NPT on the same system (md_npt_lj.py defaults: P = 0.99, tau = tau_baro = 2): one host
+    # synchronisation per step, box and cell grid re-derived every step
+    m, g = 3, 3 * (n - 1)
+    q = np.full(m, 4.0)
+    q[0] = g * 4.0
+    st = {"eps": 0.0, "p_eps": 0.0}
+    ch = [np.zeros(m), np.zeros(m), q, np.zeros(m), np.zeros(m), np.full(m, 4.0)]
+
+    def npt(k):
+        _, st["eps"], st["p_eps"] = sim.run_npt(DT, 1.0, 0.99, ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], g * 4.0, box,
+                                                st["eps"], st["p_eps"], k)
+
+    npt(50)
+    timed("npt_n1000188", sim, n, npt, 100)
     sim.close()
     return out
 
@@ -368,13 +383,37 @@ def run_ours(args, rank, world, local_rank):
         "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "other_workloads": other,
         "kernel_ms_per_step": {k: cat[k] / args.steps for k in cat},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     sim.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Libraries below us write to stdout on their own (NCCL prints its version line there): point file descriptor 1
+    at stderr for the run and keep the real stdout for the ONE JSON line."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
