@@ -82,6 +82,11 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
   atomicMax(&tab[0], ng);
 }
 
+#ifdef ATLJ_TILE2_STATS
+// debug build only (make stats): where do the phase-2 iterations go?
+__device__ unsigned long long g_t2stats[8];
+#endif
+
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -414,7 +419,6 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
             if (e <= b) continue;
             const int b0 = b & ~1;
             const int npairs = ((e + 1) >> 1) - (b0 >> 1);
-            const int nw0 = nw;
             const float4 *pp = qp + b0;  // = qp + 2 * (b0 >> 1)
             for (int base = 0; base < npairs; base += 16) {
               const int n = min(16, npairs - base);
@@ -430,18 +434,18 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
                 wd = __funnelshift_l(__float_as_uint(t.y), wd, 1);
               }
               wd <<= 2 * (16 - n);
-              mw[nw] = make_uint2(wd, (unsigned)(b0 + 2 * base + 31));  // bit p <-> candidate (b0 + 2*base + 31) - p
-              nw++;
-            }
-            // candidates outside [b, e) that rode along in the first / last pair, and the atom itself
-            if (b & 1) mw[nw0].x &= 0x7fffffffu;
-            if (e & 1) {
-              const int pos = e - b0;
-              mw[nw0 + (pos >> 5)].x &= ~(0x80000000u >> (pos & 31));
-            }
-            if (w == 1) {
-              const int pos = self - b0;
-              mw[nw0 + (pos >> 5)].x &= ~(0x80000000u >> (pos & 31));
+              // bit p <-> candidate c31 - p.  Candidates outside [b, e) that rode along in the first / last pair, and
+              // the atom itself, are cleared here; a word without survivors is not stored at all (ncu/stat build: 4.1
+              // of the 10.7 words per atom were empty and cost a full phase-2 iteration each)
+              const int c31 = b0 + 2 * base + 31;
+              if (base == 0 && (b & 1)) wd &= 0x7fffffffu;
+              const unsigned pe = (unsigned)(c31 - e), ps = (unsigned)(c31 - self);
+              if (pe < 32u) wd &= ~(1u << pe);
+              if (w == 1 && ps < 32u) wd &= ~(1u << ps);
+              if (wd != 0u) {
+                mw[nw] = make_uint2(wd, (unsigned)c31);
+                nw++;
+              }
             }
           }
         }
@@ -459,7 +463,27 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
         uint2 cur = make_uint2(0u, 0u), nxt = make_uint2(0u, 0u);  // (mask, staged index of bit 0's candidate + 31)
         if (nw > 0) cur = mw[0];
         if (nw > 1) nxt = mw[1];
+#ifdef ATLJ_TILE2_STATS
+        {
+          int pc = 0, emp = 0, half = 0;
+          for (int q = 0; q < nw; q++) {
+            const int c = __popc(mw[q].x);
+            pc += c, emp += c == 0, half += (c + 1) >> 1;
+          }
+          const int mx = __reduce_max_sync(FULL, half + emp), mxh = __reduce_max_sync(FULL, (pc + 1) >> 1);
+          atomicAdd(&g_t2stats[1], (unsigned long long)pc);
+          atomicAdd(&g_t2stats[2], (unsigned long long)nw);
+          atomicAdd(&g_t2stats[3], (unsigned long long)emp);
+          atomicAdd(&g_t2stats[4], (unsigned long long)half);
+          if (lane == 0) atomicAdd(&g_t2stats[5], 1ull), atomicAdd(&g_t2stats[6], (unsigned long long)mx),
+              atomicAdd(&g_t2stats[7], (unsigned long long)mxh);
+        }
+        int iters = 0;
+#endif
         while (ww < nw) {
+#ifdef ATLJ_TILE2_STATS
+          iters++;
+#endif
           const bool adv = cur.x == 0u;
           if (adv) ww++;
           const uint2 ld = mw[min(ww + 1, U_NWORDS - 1)];
@@ -499,6 +523,12 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           npf += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
           if (adv) nxt = (ww + 1 < nw) ? ld : make_uint2(0u, 0u);
         }
+#ifdef ATLJ_TILE2_STATS
+        {
+          const int mi = __reduce_max_sync(FULL, iters);
+          if (lane == 0) atomicAdd(&g_t2stats[0], (unsigned long long)mi);
+        }
+#endif
         for (int k = 0; k < nd; k++) U_EXACT(defer[k]);
         if (act) {
           a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
@@ -559,3 +589,13 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
 }
 
 }  // namespace atlj
+
+#ifdef ATLJ_TILE2_STATS
+extern "C" int atlj_debug_tile2_stats(unsigned long long out[8]) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, atlj::g_t2stats, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(atlj::g_t2stats, z, sizeof(z));
+  return 0;
+}
+#endif
