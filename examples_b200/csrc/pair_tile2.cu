@@ -37,12 +37,15 @@ static inline size_t tile2_smem_bytes() {
 
 constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps every SM busy) .. 4
 
-// Work items.  A row pair (two adjacent y rows of one x layer) is cut greedily into chunks of whole cells holding
-// <= U_NT atoms; gk consecutive chunks are one work item.  tile2_table_kernel records where every item starts
-// (tab layout: [0] = largest number of items of any row pair, [16 .. 16+nrp) = items per row pair, then
-// [nrp][gstride] start cells), so that items are handed out chunk-exact: no partly filled chunk except the last one of
-// a row pair, and the tail of the grid is at most gk chunks long.  Item t = (group t / nrp, row pair t % nrp).
-static inline int tile2_gstride(const Geom &g) { return g.sc + 2; }  // gk = 1: at most one item per cell
+// Work items.  The atoms of a row pair (two adjacent y rows of one x layer) are taken in "interleaved" order: for each
+// z cell, its row-A atoms then its row-B atoms.  A chunk is the next <= U_NT atoms of that order, cut short only where
+// it would span more than ncz_max cells (the staged candidate set must fit U_CAP) - chunks are NOT cell-aligned, so
+// every chunk but the last of a row pair is (nearly) full: 99 % of the lanes carry an atom instead of 89.5 % with
+// whole-cell chunks.  gk consecutive chunks are one work item; tile2_table_kernel replays the cutting rule and records
+// where every item starts (tab layout: [0] = largest number of items of any row pair, [16 .. 16+nrp) = items per row
+// pair, then [nrp][gstride] start positions in interleaved order, closed by the row pair's atom count).
+// Item t = (group t / nrp, row pair t % nrp).
+static inline int tile2_gstride(const Geom &g) { return g.sc + 2; }
 int pair_tile2_tab_ints(const Geom &g) {
   const int nrp = g.nx_own * ((g.sc + 1) / 2);
   return 16 + nrp + nrp * tile2_gstride(g);
@@ -51,7 +54,7 @@ int pair_tile2_tab_ints(const Geom &g) {
 int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * (tile2_gstride(g) - 1); }
 
 __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__restrict__ cs, int nyb, int nrp,
-                                                          int gstride, int gk, int *__restrict__ tab) {
+                                                          int gstride, int gk, int ncz_max, int *__restrict__ tab) {
   __shared__ int cnt[4][1024];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int rp = blockIdx.x * 4 + w;
@@ -66,18 +69,18 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
   __syncwarp();
   if (lane != 0) return;
   int *zb = tab + 16 + nrp + (size_t)rp * gstride;
-  int z = 0, nch = 0, ng = 0;
-  while (z < sc) {
-    if (nch % gk == 0) zb[ng++] = z;
-    // same rule as the kernel's chunk extent: as many whole cells as hold <= U_NT atoms, at least one, at most
-    // U_MAXC - 2
-    int acc = 0, ncz = 0;
-    while (z + ncz < sc && ncz < U_MAXC - 2 && acc + cnt[w][z + ncz] <= U_NT) acc += cnt[w][z + ncz], ncz++;
-    if (ncz == 0) ncz = 1;
-    z += ncz;
+  const int T = (cs[ownA0 + sc] - cs[ownA0]) + (two ? cs[ownB0 + sc] - cs[ownB0] : 0);
+  int z0 = 0, cum0 = 0, gpos = 0, nch = 0, ng = 0;
+  while (gpos < T) {
+    // past gstride - 1 items (only a pathologically crowded row pair gets there) the last item takes all the rest
+    if (nch % gk == 0 && ng < gstride - 1) zb[ng++] = gpos;
+    while (cum0 + cnt[w][z0] <= gpos) cum0 += cnt[w][z0], z0++;  // the cell that holds atom gpos
+    int lim = cum0;
+    for (int c = 0; c < ncz_max && z0 + c < sc; c++) lim += cnt[w][z0 + c];
+    gpos = min(gpos + U_NT, lim);  // same rule as the kernel's chunk extent
     nch++;
   }
-  zb[ng] = sc;
+  zb[ng] = T;
   tab[16 + rp] = ng;
   atomicMax(&tab[0], ng);
 }
@@ -144,7 +147,7 @@ __device__ __forceinline__ double rcp46(double s) {
   } while (0)
 
 __global__ void __launch_bounds__(U_NT, U_CTAS)
-    pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, const int *__restrict__ tab,
+    pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, int ncz_max, const int *__restrict__ tab,
                       int *__restrict__ work_counter, int *__restrict__ rows_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
   int *S = reinterpret_cast<int *>(qp + U_CAP + 2);      // [U_NE + 4] staged offset of entry e = cell*12 + row
   int *egl = S + U_NE + 4;                               // [U_NE] global index of the first atom of entry e
   __shared__ int rowcell0[U_K];
+  __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
   __shared__ int wsum[U_NT / 32];
   __shared__ unsigned s_q2max;
   __shared__ int s_maxwin, s_item;
@@ -188,8 +192,12 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
     const int xo = rp / nyb, yb = rp - xo * nyb;  // owned x layer, row pair of this item
     const int lx = g.h + xo, y0 = 2 * yb;
     const bool two = (y0 + 1 < sc);
-    const int zA = tab[16 + nrp + (size_t)rp * gstride + grp], zB = tab[16 + nrp + (size_t)rp * gstride + grp + 1];
+    // atoms [gA, gB) of the row pair's interleaved order
+    const int gA = tab[16 + nrp + (size_t)rp * gstride + grp], gB = tab[16 + nrp + (size_t)rp * gstride + grp + 1];
     const int ownA0 = g.cs_idx((lx * sc + y0) * sc), ownB0 = ownA0 + sc;  // rows in the padded cell_start
+    const int csA0 = cs[ownA0], csB0 = two ? cs[ownB0] : 0;
+    // atoms of the row pair in cells [0, zz)
+    auto cumf = [&](int zz) { return (cs[ownA0 + zz] - csA0) + (two ? cs[ownB0 + zz] - csB0 : 0); };
     if (tid < U_K) {
       // row k = yi*3 + xi holds cells (lx-1+xi, y0-1+yi); yi = 0..2 are the dy = -1,0,1 neighbours of row y0 and
       // yi = 1..3 those of row y0+1; the ids come from the stencil function the bit-exact tests cover
@@ -209,14 +217,22 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
     unsigned npf = 0u;
     int ovr = 0;
 
-    for (int z = zA; z < zB;) {
-      // ---- chunk extent: whole cells of both rows holding <= U_NT atoms ---------------------------------------
-      const int sA = cs[ownA0 + z], sB = two ? cs[ownB0 + z] : 0;
-      int ok = 0;
-      if (tid < U_MAXC - 2 && z + tid < zB)
-        ok = ((cs[ownA0 + z + tid + 1] - sA) + (two ? cs[ownB0 + z + tid + 1] - sB : 0)) <= U_NT;
-      int ncz = __syncthreads_count(ok);  // barrier: previous chunk is done with shared memory
-      if (ncz == 0) ncz = 1;
+    int z = 0;  // the cell that holds atom g0: cumf(z) <= g0 < cumf(z + 1)
+    for (int step = 512; step >= 1; step >>= 1)
+      if (z + step < sc && cumf(z + step) <= gA) z += step;
+    for (int g0 = gA; g0 < gB;) {
+      // ---- chunk extent: the next <= U_NT atoms, over at most ncz_max cells ----------------------------------
+      __syncthreads();  // the previous chunk is done with shared memory
+      if (tid < U_MAXC) {
+        const int zz = min(z + tid, sc);
+        cumloc[tid] = cumf(zz);
+        sAloc[tid] = cs[ownA0 + zz];
+        sBloc[tid] = two ? cs[ownB0 + zz] : 0;
+      }
+      __syncthreads();
+      int g1 = min(min(g0 + U_NT, gB), cumloc[min(ncz_max, U_MAXC - 2)]);
+      int ncz = 1;  // cells that hold atoms [g0, g1)
+      while (cumloc[ncz] < g1) ncz++;
 
       int total, NE;
       for (;;) {
@@ -232,9 +248,9 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
             int zc = z - 1 + c;
             zc = zc < 0 ? zc + sc : (zc >= sc ? zc - sc : zc);
             if (rc0 >= 0) {
-              const int g0 = cs[rc0 + zc];
-              cnt[u] = cs[rc0 + zc + 1] - g0;
-              egl[e] = g0;
+              const int gs = cs[rc0 + zc];
+              cnt[u] = cs[rc0 + zc + 1] - gs;
+              egl[e] = gs;
             } else {
               egl[e] = 0;
             }
@@ -266,12 +282,21 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
         if (total <= U_CAP || ncz == 1) break;
         ncz = max(1, min(ncz - 1, (int)((long long)ncz * U_CAP / total)));
       }
-      const int nA = cs[ownA0 + z + ncz] - sA, nB = two ? cs[ownB0 + z + ncz] - sB : 0;
-      const int ni = nA + nB;
-      if (ni == 0) {
-        z += ncz;
-        continue;
-      }
+      g1 = min(g1, cumloc[ncz]);  // ncz may have been cut to fit U_CAP
+      const int ni = g1 - g0;
+      // atom il of the chunk -> (cell myc of the chunk, row, global index i, offset in its cell row)
+      auto locate = [&](int il, int &myc, int &i, int &k0, int &off) {
+        const int gp = g0 + il;
+        myc = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (myc + step < ncz && cumloc[myc + step] <= gp) myc += step;
+        const int idx = gp - cumloc[myc], nAc = sAloc[myc + 1] - sAloc[myc];
+        const bool inA = idx < nAc;
+        off = inA ? idx : idx - nAc;
+        i = (inA ? sAloc[myc] : sBloc[myc]) + off;
+        k0 = inA ? 0 : 3;
+      };
       // longest window (9 consecutive entries of 3 consecutive cells are three windows; check each)
       {
         int mw = 0;
@@ -288,13 +313,8 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
       if (slow) {
         // ---- crowded neighbourhood (does not occur in a fluid): exact arithmetic straight from global memory ----
         for (int il = tid; il < ni; il += U_NT) {
-          const bool inA = il < nA;
-          const int own0 = inA ? ownA0 : ownB0;
-          const int i = inA ? sA + il : sB + (il - nA);
-          const int k0 = inA ? 0 : 3;
-          int c = 0;
-          for (int step = 16; step >= 1; step >>= 1)
-            if (c + step < ncz && cs[own0 + z + c + step] <= i) c += step;
+          int c, i, k0, off;
+          locate(il, c, i, k0, off);
           const int zi = z + c;
           const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
           double fx = 0, fy = 0, fz = 0;
@@ -323,7 +343,9 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
         }
         __syncthreads();
         if (tid == 0) s_maxwin = 0;
-        z += ncz;
+        g0 = g1;
+        z += ncz - 1;
+        while (z < sc - 1 && cumf(z + 1) <= g0) z++;
         continue;
       }
 
@@ -389,16 +411,11 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
       for (int ib = 0; ib < ni; ib += U_NT) {
         const int il = ib + tid;
         const bool act = il < ni;
-        const bool inA = il < nA;
-        const int own0 = inA ? ownA0 : ownB0;
-        const int i = act ? (inA ? sA + il : sB + (il - nA)) : 0;
-        const int k0 = inA ? 0 : 3;
-        int myc = 0, self = 0;
+        int myc = 0, self = 0, i = 0, k0 = 0;
         if (act) {
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1)
-            if (myc + step < ncz && cs[own0 + z + myc + step] <= i) myc += step;
-          self = S[(myc + 1) * U_K + k0 + 4] + (i - cs[own0 + z + myc]);
+          int off;
+          locate(il, myc, i, k0, off);
+          self = S[(myc + 1) * U_K + k0 + 4] + off;
         }
         const double uix = ux[self], uiy = uy[self], uiz = uz[self];
         const float *qs = qf + 8 * (self >> 1) + (self & 1);
@@ -538,7 +555,9 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
       }
       __syncthreads();
       if (tid == 0) s_q2max = 0u, s_maxwin = 0;
-      z += ncz;
+      g0 = g1;
+      z += ncz - 1;  // the cell that holds the next chunk's first atom (skipping empty cells)
+      while (z < sc - 1 && cumf(z + 1) <= g0) z++;
     }
     // cut = sr12 - sr6, pot = cut - pot_cut, vir = cut + sr12, lap = (22 sr12 - 5 sr6) sr2 (md_lj_module.py:104-108)
     Acc acc;
@@ -575,15 +594,20 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
   }
   const int nyb = (a.g.sc + 1) / 2, nrp = a.g.nx_own * nyb, gstride = tile2_gstride(a.g);
   // chunks per item: about 8 items per resident CTA, at least 1 (small systems), at most U_GK_MAX
-  const long long chunks = (a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells()) / (U_NT - U_NT / 8) + nrp;
+  const long long natoms = a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells();
+  const long long chunks = natoms / (U_NT - U_NT / 16) + nrp;
   int gk = (int)(chunks / (8ll * grid));
   gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
+  // cells a chunk may span: the staged cross-section (12 rows per cell, one halo cell at each end) has to fit U_CAP
+  const double per_cell = (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
+  int ncz_max = (int)(0.96 * U_CAP / (U_K * (per_cell > 0.05 ? per_cell : 0.05))) - 2;
+  ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
   ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
-  tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, a.tile_tab);
+  tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, a.tile_tab);
   ATLJ_LAUNCHED();
   const int bound = nrp * (gstride - 1);
-  pair_tile2_kernel<<<grid < bound ? grid : bound, U_NT, smem, st>>>(a, nyb, nrp, gstride, a.tile_tab, work_counter,
-                                                                    work_counter + 4);
+  pair_tile2_kernel<<<grid < bound ? grid : bound, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab,
+                                                                    work_counter, work_counter + 4);
   ATLJ_LAUNCHED();
   return bound;
 }
