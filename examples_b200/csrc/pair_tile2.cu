@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
         }
         int iters = 0;
 #endif
-        while (ww < nw) {
+        // (the loop ends with the last bit of the last word: testing ww < nw alone costs every warp one dead iteration)
+        while (cur.x != 0u || ww + 1 < nw) {
 #ifdef ATLJ_TILE2_STATS
           iters++;
 #endif
