@@ -117,7 +117,8 @@ static bool sim_direct(const atlj_sim *s) {
 // ---- one force evaluation on the current positions ----------------------------------------------------------------------
 // Cell route: wrap+assign -> scan -> scatter/sort/gather (atoms re-ordered into cell order, buffers swapped) -> pair
 // kernel -> finalize.  All-pairs route (sc < 4): pair_all on the current order.
-int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs) {
+int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs,
+              cudaEvent_t after_sort) {
   int rc;
   const int n = (int)s->n;
   Phys p = s->p;
@@ -135,6 +136,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       return rc;
     Timer::end(s);
     s->cur = alt;
+    if (after_sort) ATLJ_CUDA(cudaEventRecord(after_sort, s->st));
     PairArgs a;
     a.r = s->r[alt];
     a.fin = nullptr;
@@ -171,6 +173,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
     }
   } else {
+    if (after_sort) ATLJ_CUDA(cudaEventRecord(after_sort, s->st));
     if (check_index_allpairs) {  // honour md_lj_ll_module.py:107-109 even though sc < 4 is served by all pairs
       Geom g = s->g;
       if ((rc = launch_cell_assign(s->st, g, s->r[s->cur], nullptr, n, false, strain, s->cb, nullptr))) return rc;
@@ -289,6 +292,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
   cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials), cudaFree(s->tile_tab);
   if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
+  if (s->st_copy) cudaStreamDestroy(s->st_copy), cudaEventDestroy(s->ev_sorted), cudaEventDestroy(s->ev_copied);
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
   for (auto &t : s->ev_open) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
@@ -475,13 +479,23 @@ int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_hos
   ATLJ_CUDA(cudaMemcpyAsync(s->id[0], id_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->st));
   const long long n3 = 3 * n;
   const double half_dt = 0.5 * dt;
+  if (!s->st_copy) {
+    ATLJ_CUDA(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming));
+    ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+  }
   if ((rc = launch_kick_drift(s->st, n3, s->r[0], s->v[0], s->f, half_dt, dt, s->p.box, nullptr))) return rc;
-  if ((rc = sim_force(s, 0.0, false, s->rec_dev, false))) return rc;
+  if ((rc = sim_force(s, 0.0, false, s->rec_dev, false, s->ev_sorted))) return rc;
+  // positions and ids are final once the cell sort is done: they travel home on the copy stream while the pair
+  // kernel runs; v and f follow on the main stream
+  ATLJ_CUDA(cudaStreamWaitEvent(s->st_copy, s->ev_sorted, 0));
+  ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st_copy));
+  ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st_copy));
+  ATLJ_CUDA(cudaEventRecord(s->ev_copied, s->st_copy));
   if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, s->rec_dev + 4))) return rc;
-  ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st));
   ATLJ_CUDA(cudaMemcpyAsync(v_host, s->v[s->cur], b, cudaMemcpyDeviceToHost, s->st));
   ATLJ_CUDA(cudaMemcpyAsync(f_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
-  ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamWaitEvent(s->st, s->ev_copied, 0));
   return sim_copy_rec(s, rec_host, 1);  // synchronises
 }
 

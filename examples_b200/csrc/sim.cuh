@@ -51,6 +51,9 @@ struct atlj_sim {
   double *noise_dev = nullptr;  // injected noise (tests)
   int64_t noise_cap = 0;
   MgState mg;
+  // host-buffer step: copy engine stream + events so that r, id go home while the pair kernel runs
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_sorted = nullptr, ev_copied = nullptr;
   // timing
   cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // stopwatch (atlj_sim_timer_*)
   bool timing = false;
@@ -70,7 +73,9 @@ struct Timer {
   static void begin(atlj_sim *s, int cat, cudaStream_t st = nullptr, bool other_stream = false);
   static void end(atlj_sim *s, cudaStream_t st = nullptr, bool other_stream = false);
 };
-int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs);
+// after_sort (may be null): recorded on the sim's stream when the sorted r, v, id of this evaluation are final
+int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs,
+              cudaEvent_t after_sort = nullptr);
 int sim_check_flags(atlj_sim *s);
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
 int sim_ensure_rec(atlj_sim *s, int64_t nrec);
