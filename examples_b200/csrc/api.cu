@@ -108,6 +108,18 @@ int sim_ensure_rec(atlj_sim *s, int64_t nrec) {
   return ATLJ_OK;
 }
 
+static int ensure_masks(atlj_sim *s) {
+  if (s->masks) return ATLJ_OK;
+  const size_t bytes = pair_tile2_mask_bytes(s->cap);
+  cudaError_t e = cudaMalloc((void **)&s->masks, bytes);
+  if (e != cudaSuccess) {
+    s->masks = nullptr;
+    set_error("cudaMalloc(%zu) for the mask words -> %s", bytes, cudaGetErrorString(e));
+    return ATLJ_ERR_CUDA;
+  }
+  return ATLJ_OK;
+}
+
 // cells of ~1 atom (WCA cut-off): the direct kernel; ATLJ_PAIR_KERNEL=tile1 keeps the tiled one for A/B runs
 static bool sim_direct(const atlj_sim *s) {
   const long long cells = s->g.n_own_cells();
@@ -145,6 +157,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.f = s->f;
     a.partials = s->partials;
     a.tile_tab = s->tile_tab;
+    a.masks = nullptr;
     a.natoms = (int)s->n;
     a.g = s->g;
     a.p = p;
@@ -152,10 +165,16 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     int nb;
     const bool direct = sim_direct(s);
     const bool tile2 = !direct && s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
+    // hessian after the tile2 force kernel: that kernel keeps its mask words, the hessian kernel walks them
+    const bool hess2 = with_hessian && tile2;
+    if (hess2) {
+      if ((rc = ensure_masks(s))) return rc;
+      a.masks = s->masks;
+    }
     if (direct)
       nb = launch_pair_direct(s->st, a, false, n);
     else if (tile2)
-      nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
+      nb = launch_pair_tile2(s->st, a, s->cb.err + 2, hess2 ? 1 : 0);
     else
       nb = launch_pair_tile(s->st, a, false);
     Timer::end(s);
@@ -167,10 +186,15 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       a.fin = s->f;
       a.f = nullptr;
       Timer::begin(s, 3);
-      nb = direct ? launch_pair_direct(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
+      if (hess2)
+        nb = launch_pair_tile2(s->st, a, s->cb.err + 2, 2);
+      else
+        nb = direct ? launch_pair_direct(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
       Timer::end(s);
       if (nb < 0) return nb;
-      if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
+      if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev, hess2 ? s->cb.err + 2 : nullptr, nullptr,
+                                0, hess2 ? s->cb.err + 6 : nullptr)))
+        return rc;
     }
   } else {
     if (after_sort) ATLJ_CUDA(cudaEventRecord(after_sort, s->st));
@@ -290,7 +314,7 @@ void atlj_sim_destroy(atlj_sim *s) {
   for (int k = 0; k < 2; k++) cudaFree(s->r[k]), cudaFree(s->v[k]), cudaFree(s->id[k]);
   cudaFree(s->f), cudaFree(s->cb.cellid), cudaFree(s->cb.rank), cudaFree(s->cb.keys), cudaFree(s->cb.block_sums);
   cudaFree(s->cb.err), cudaFree(s->cb.cell_count), cudaFree(s->cb.cell_start), cudaFree(s->partials);
-  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials), cudaFree(s->tile_tab);
+  cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials), cudaFree(s->tile_tab), cudaFree(s->masks);
   if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
   if (s->st_copy) cudaStreamDestroy(s->st_copy), cudaEventDestroy(s->ev_sorted), cudaEventDestroy(s->ev_copied);
   for (auto e : s->ev_free) cudaEventDestroy(e);
@@ -432,6 +456,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       PairArgs a;
       a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
       a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
+      a.masks = nullptr;
       Timer::begin(s, 0);
       nb_prev = direct ? launch_pair_direct(s->st, a, false, n)
                        : (tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false));
@@ -655,6 +680,7 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.f = nullptr;
     a.partials = s->partials;
     a.tile_tab = s->tile_tab;
+    a.masks = nullptr;
     a.natoms = (int)s->n;
     a.g = s->g;
     a.p = p;

@@ -167,6 +167,7 @@ struct PairArgs {
   double *f;             // sorted forces out (force mode)
   double *partials;      // [rows][8]
   int *tile_tab;         // work-item table of pair_tile2 (pair_tile2_tab_ints)
+  uint2 *masks;          // pair_tile2: per-atom mask words kept between the force and the hessian kernel, or nullptr
   int natoms;            // owned atoms (a hint for the work-item size; 0 = unknown)
   Geom g;
   Phys p;
@@ -179,7 +180,10 @@ int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the 
 // the fused integration kernel reset it)
 // The number of rows actually written is stored by the kernel in work_counter[4] (device); the reducers take that
 // pointer (rows_dev) next to the upper bound returned here.
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter);
+// mode 0: forces; 1: forces, and a.masks receives every atom's mask words; 2: hessian sum from a.fin and the masks of a
+// mode-1 launch on the same cell table
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode = 0);
+size_t pair_tile2_mask_bytes(long long natoms);
 int pair_tile2_tab_ints(const Geom &g);  // ints of PairArgs::tile_tab for this geometry
 // direct link-cell kernel (cells of ~1 atom): one thread per owned atom, no staging
 int pair_direct_blocks(int n);

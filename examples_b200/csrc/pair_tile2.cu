@@ -31,9 +31,19 @@ constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
 constexpr int U_WW = 6;                 // mask words per window (<= 191 candidates per window)
 constexpr int U_NWORDS = 3 * U_WW;
 
-static inline size_t tile2_smem_bytes() {
-  return sizeof(double) * 3 * U_CAP + sizeof(float4) * (U_CAP + 2) + sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
+// Kernel modes.  T2_FORCE: forces + totals.  T2_FORCE_SAVE: the same, and every atom's mask words (the filter's
+// survivors) are kept in global memory.  T2_HESS: the hessian sum (md_lj_module.py:176-191) from those mask words - no
+// filter pass; the chunk boundaries and staged indices are the same because they depend on the cell table only, so a
+// mask word means the same candidates in both kernels.  The forces of the candidates take the place of the fp32 copy in
+// shared memory (48 B per candidate instead of 40: 3 CTAs per SM).
+enum { T2_FORCE = 0, T2_FORCE_SAVE = 1, T2_HESS = 2 };
+
+static inline size_t tile2_smem_bytes(int mode) {
+  const size_t tab = sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
+  if (mode == T2_HESS) return sizeof(double) * 6 * U_CAP + tab;
+  return sizeof(double) * 3 * U_CAP + sizeof(float4) * (U_CAP + 2) + tab;
 }
+size_t pair_tile2_mask_bytes(long long natoms) { return sizeof(uint2) * (size_t)U_NWORDS * (size_t)natoms; }
 
 constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps every SM busy) .. 4
 
@@ -146,15 +156,40 @@ __device__ __forceinline__ double rcp46(double s) {
     }                                                                                  \
   } while (0)
 
-__global__ void __launch_bounds__(U_NT, U_CTAS)
+// hessian term of one in-range pair (md_lj_module.py:176-191): rij in sigma units, fij = f_i - f_j
+#define U_HESS(dx_, dy_, dz_, s_, gx_, gy_, gz_)                                       \
+  do {                                                                                 \
+    const double sr2_ = rcp46(s_);                                                     \
+    const double sr6_ = sr2_ * sr2_ * sr2_;                                            \
+    const double sr8_ = sr6_ * sr2_, sr10_ = sr8_ * sr2_;                              \
+    const double ff_ = fma(gz_, gz_, fma(gy_, gy_, gx_ * gx_));                        \
+    const double rf_ = fma(dz_, gz_, fma(dy_, gy_, dx_ * gx_));                        \
+    const double v1_ = 24.0 * fma(-2.0, sr6_, 1.0) * sr8_;                             \
+    const double v2_ = 96.0 * fma(7.0, sr6_, -2.0) * sr10_;                            \
+    hs = fma(v1_, ff_, fma(v2_, rf_ * rf_, hs));                                       \
+  } while (0)
+#define U_EXACT_H(jj)                                                                  \
+  do {                                                                                 \
+    const ExactOut o_ = exact_pair(a.r, p, S, egl, NE, i, (jj));                       \
+    if (o_.in) {                                                                       \
+      const double ex_ = fix - gx[(jj)], ey_ = fiy - gy[(jj)], ez_ = fiz - gz[(jj)];   \
+      U_HESS(o_.dx, o_.dy, o_.dz, o_.s, ex_, ey_, ez_);                                \
+      npf++;                                                                           \
+    }                                                                                  \
+  } while (0)
+
+template <int MODE>
+__global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
     pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, int ncz_max, const int *__restrict__ tab,
                       int *__restrict__ work_counter, int *__restrict__ rows_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
   double *uy = ux + U_CAP;
   double *uz = uy + U_CAP;
+  double *gx = uz + U_CAP, *gy = gx + U_CAP, *gz = gy + U_CAP;  // T2_HESS only: forces of the staged candidates
   float4 *qp = reinterpret_cast<float4 *>(uz + U_CAP);  // pair p: qp[2p] = (x0,x1,y0,y1), qp[2p+1] = (z0,z1,n0,n1)
-  int *S = reinterpret_cast<int *>(qp + U_CAP + 2);      // [U_NE + 4] staged offset of entry e = cell*12 + row
+  // [U_NE + 4] staged offset of entry e = cell*12 + row
+  int *S = MODE == T2_HESS ? reinterpret_cast<int *>(gz + U_CAP) : reinterpret_cast<int *>(qp + U_CAP + 2);
   int *egl = S + U_NE + 4;                               // [U_NE] global index of the first atom of entry e
   __shared__ int rowcell0[U_K];
   __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
@@ -213,7 +248,7 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
     const double ctry = (y0 + (two ? 1.0 : 0.5)) * sci - 0.5;
 
     // sums of sr^6, sr^12, sr^8, sr^14 over this thread's pairs; cut, vir, lap follow at the end of the item
-    double a6 = 0.0, a12 = 0.0, a8 = 0.0, a14 = 0.0;
+    double a6 = 0.0, a12 = 0.0, a8 = 0.0, a14 = 0.0, hs = 0.0;
     unsigned npf = 0u;
     int ovr = 0;
 
@@ -317,7 +352,8 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           locate(il, c, i, k0, off);
           const int zi = z + c;
           const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
-          double fx = 0, fy = 0, fz = 0;
+          double fx = 0, fy = 0, fz = 0, fix = 0, fiy = 0, fiz = 0;
+          if (MODE == T2_HESS) fix = a.fin[3 * (size_t)i], fiy = a.fin[3 * (size_t)i + 1], fiz = a.fin[3 * (size_t)i + 2];
           for (int k = k0; k < k0 + 9; k++) {
             const int rc0 = rowcell0[k];
             if (rc0 < 0) continue;
@@ -330,16 +366,24 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
                 if (pair_sep<false>(rix, riy, riz, a.r[3 * (size_t)j], a.r[3 * (size_t)j + 1],
                                     a.r[3 * (size_t)j + 2], 0.0, p.r_cut_box_sq, dx, dy, dzz, s)) {
                   const double s2 = __dmul_rn(s, p.box_sq);
-                  if (__drcp_rn(s2) > 1.77) ovr = 1;  // md_lj_module.py:103
-                  U_ACCUM(dx * box, dy * box, dzz * box, s2);
+                  if (MODE == T2_HESS) {
+                    const double ex = fix - a.fin[3 * (size_t)j], ey = fiy - a.fin[3 * (size_t)j + 1],
+                                 ez = fiz - a.fin[3 * (size_t)j + 2];
+                    U_HESS(dx * box, dy * box, dzz * box, s2, ex, ey, ez);
+                  } else {
+                    if (__drcp_rn(s2) > 1.77) ovr = 1;  // md_lj_module.py:103
+                    U_ACCUM(dx * box, dy * box, dzz * box, s2);
+                  }
                   npf++;
                 }
               }
             }
           }
-          a.f[3 * (size_t)i] = 24.0 * fx;
-          a.f[3 * (size_t)i + 1] = 24.0 * fy;
-          a.f[3 * (size_t)i + 2] = 24.0 * fz;
+          if (MODE != T2_HESS) {
+            a.f[3 * (size_t)i] = 24.0 * fx;
+            a.f[3 * (size_t)i + 1] = 24.0 * fy;
+            a.f[3 * (size_t)i + 2] = 24.0 * fz;
+          }
         }
         __syncthreads();
         if (tid == 0) s_maxwin = 0;
@@ -360,11 +404,16 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           y -= rint(y);
           x *= box, y *= box, zz *= box;
           ux[s] = x, uy[s] = y, uz[s] = zz;
-          const float fx = (float)x, fy = (float)y, fz = (float)zz;
-          const float n2 = fx * fx + fy * fy + fz * fz;
-          float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
-          d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
-          q2m = fmaxf(q2m, n2);
+          if (MODE != T2_HESS) {
+            const float fx = (float)x, fy = (float)y, fz = (float)zz;
+            const float n2 = fx * fx + fy * fy + fz * fz;
+            float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
+            d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
+            q2m = fmaxf(q2m, n2);
+          }
+        };
+        auto putf = [&](int s, size_t j) {  // T2_HESS: the candidate's force next to its position
+          gx[s] = a.fin[3 * j], gy[s] = a.fin[3 * j + 1], gz[s] = a.fin[3 * j + 2];
         };
         constexpr int HWS = U_NT / 16;  // half warps per CTA
         constexpr int SE = 2;           // entries in flight per half warp (4 measured no better)
@@ -372,7 +421,7 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           // entries e0, e0 + HWS, ...: issue the global loads of all of them before any is converted, so that a half
           // warp pays one load latency per SE entries (ncu: the staging loop held 13 % of the stall samples)
           int sE[SE], cE[SE], gE[SE];
-          double xE[SE], yE[SE], zE[SE], wE[SE];
+          double xE[SE], yE[SE], zE[SE], wE[SE], fxE[SE], fyE[SE], fzE[SE];
 #pragma unroll
           for (int u = 0; u < SE; u++) {
             const int e = e0 + u * HWS;
@@ -389,19 +438,26 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
             if (hl < cE[u]) {
               const size_t j = (size_t)(gE[u] + hl);
               xE[u] = a.r[3 * j], yE[u] = a.r[3 * j + 1], zE[u] = a.r[3 * j + 2];
+              if (MODE == T2_HESS) fxE[u] = a.fin[3 * j], fyE[u] = a.fin[3 * j + 1], fzE[u] = a.fin[3 * j + 2];
             }
           }
 #pragma unroll
           for (int u = 0; u < SE; u++) {
-            if (hl < cE[u]) put(sE[u] + hl, xE[u], yE[u], zE[u], wE[u]);
+            if (hl < cE[u]) {
+              put(sE[u] + hl, xE[u], yE[u], zE[u], wE[u]);
+              if (MODE == T2_HESS) gx[sE[u] + hl] = fxE[u], gy[sE[u] + hl] = fyE[u], gz[sE[u] + hl] = fzE[u];
+            }
             for (int k = hl + 16; k < cE[u]; k += 16) {  // cells with more than 16 atoms
               const size_t j = (size_t)(gE[u] + k);
               put(sE[u] + k, a.r[3 * j], a.r[3 * j + 1], a.r[3 * j + 2], wE[u]);
+              if (MODE == T2_HESS) putf(sE[u] + k, j);
             }
           }
         }
-        unsigned qb = __reduce_max_sync(FULL, __float_as_uint(q2m));
-        if (lane == 0) atomicMax(&s_q2max, qb);
+        if (MODE != T2_HESS) {
+          unsigned qb = __reduce_max_sync(FULL, __float_as_uint(q2m));
+          if (lane == 0) atomicMax(&s_q2max, qb);
+        }
       }
       __syncthreads();
       // filter threshold (see pair_tile.cu): rounding of the filter <= ~2e-6 Q^2; 6e-6 Q^2 is used
@@ -418,52 +474,72 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           self = S[(myc + 1) * U_K + k0 + 4] + off;
         }
         const double uix = ux[self], uiy = uy[self], uiz = uz[self];
-        const float *qs = qf + 8 * (self >> 1) + (self & 1);
-        const float qix = qs[0], qiy = qs[2], qiz = qs[4], qin = qs[6];
-        const float2 m2x = make_float2(-2.f * qix, -2.f * qix), m2y = make_float2(-2.f * qiy, -2.f * qiy),
-                     m2z = make_float2(-2.f * qiz, -2.f * qiz);
-        const float nt = qin - thr;
-        const float2 nti = make_float2(nt, nt);
-
         // ---- phase 1: packed fp32 filter -> left-aligned mask words --------------------------------------------
         uint2 mw[U_NWORDS];  // (mask word, staged index of the candidate of its bit 0 ... i.e. of bit 31, plus 31)
         int nw = 0;
-        if (act) {
+        double fix = 0.0, fiy = 0.0, fiz = 0.0;  // T2_HESS: this atom's force
+        if constexpr (MODE == T2_HESS) {
+          fix = gx[self], fiy = gy[self], fiz = gz[self];
+          if (act) {  // the survivors of the force kernel's filter, same staged indices
+            const uint2 *mp = a.masks + (size_t)i * U_NWORDS;
 #pragma unroll 1
-          for (int w = 0; w < 3; w++) {
-            const int eb = (myc + w) * U_K + k0;
-            const int b = S[eb], e = S[eb + 9];
-            if (e <= b) continue;
-            const int b0 = b & ~1;
-            const int npairs = ((e + 1) >> 1) - (b0 >> 1);
-            const float4 *pp = qp + b0;  // = qp + 2 * (b0 >> 1)
-            for (int base = 0; base < npairs; base += 16) {
-              const int n = min(16, npairs - base);
-              unsigned wd = 0u;
-#pragma unroll 4
-              for (int k = 0; k < n; k++) {
-                const float4 A = pp[2 * (base + k)], B = pp[2 * (base + k) + 1];
-                float2 t = __fadd2_rn(make_float2(B.z, B.w), nti);
-                t = __ffma2_rn(m2z, make_float2(B.x, B.y), t);
-                t = __ffma2_rn(m2y, make_float2(A.z, A.w), t);
-                t = __ffma2_rn(m2x, make_float2(A.x, A.y), t);
-                wd = __funnelshift_l(__float_as_uint(t.x), wd, 1);
-                wd = __funnelshift_l(__float_as_uint(t.y), wd, 1);
-              }
-              wd <<= 2 * (16 - n);
-              // bit p <-> candidate c31 - p.  Candidates outside [b, e) that rode along in the first / last pair, and
-              // the atom itself, are cleared here; a word without survivors is not stored at all (ncu/stat build: 4.1
-              // of the 10.7 words per atom were empty and cost a full phase-2 iteration each)
-              const int c31 = b0 + 2 * base + 31;
-              if (base == 0 && (b & 1)) wd &= 0x7fffffffu;
-              const unsigned pe = (unsigned)(c31 - e), ps = (unsigned)(c31 - self);
-              if (pe < 32u) wd &= ~(1u << pe);
-              if (w == 1 && ps < 32u) wd &= ~(1u << ps);
-              if (wd != 0u) {
-                mw[nw] = make_uint2(wd, (unsigned)c31);
-                nw++;
+            for (; nw < U_NWORDS; nw++) {
+              const uint2 m = mp[nw];
+              if (m.x == 0u) break;
+              mw[nw] = m;
+            }
+          }
+        } else {
+          const float *qs = qf + 8 * (self >> 1) + (self & 1);
+          const float qix = qs[0], qiy = qs[2], qiz = qs[4], qin = qs[6];
+          const float2 m2x = make_float2(-2.f * qix, -2.f * qix), m2y = make_float2(-2.f * qiy, -2.f * qiy),
+                       m2z = make_float2(-2.f * qiz, -2.f * qiz);
+          const float nt = qin - thr;
+          const float2 nti = make_float2(nt, nt);
+
+          if (act) {
+  #pragma unroll 1
+            for (int w = 0; w < 3; w++) {
+              const int eb = (myc + w) * U_K + k0;
+              const int b = S[eb], e = S[eb + 9];
+              if (e <= b) continue;
+              const int b0 = b & ~1;
+              const int npairs = ((e + 1) >> 1) - (b0 >> 1);
+              const float4 *pp = qp + b0;  // = qp + 2 * (b0 >> 1)
+              for (int base = 0; base < npairs; base += 16) {
+                const int n = min(16, npairs - base);
+                unsigned wd = 0u;
+  #pragma unroll 4
+                for (int k = 0; k < n; k++) {
+                  const float4 A = pp[2 * (base + k)], B = pp[2 * (base + k) + 1];
+                  float2 t = __fadd2_rn(make_float2(B.z, B.w), nti);
+                  t = __ffma2_rn(m2z, make_float2(B.x, B.y), t);
+                  t = __ffma2_rn(m2y, make_float2(A.z, A.w), t);
+                  t = __ffma2_rn(m2x, make_float2(A.x, A.y), t);
+                  wd = __funnelshift_l(__float_as_uint(t.x), wd, 1);
+                  wd = __funnelshift_l(__float_as_uint(t.y), wd, 1);
+                }
+                wd <<= 2 * (16 - n);
+                // bit p <-> candidate c31 - p.  Candidates outside [b, e) that rode along in the first / last pair, and
+                // the atom itself, are cleared here; a word without survivors is not stored at all (ncu/stat build: 4.1
+                // of the 10.7 words per atom were empty and cost a full phase-2 iteration each)
+                const int c31 = b0 + 2 * base + 31;
+                if (base == 0 && (b & 1)) wd &= 0x7fffffffu;
+                const unsigned pe = (unsigned)(c31 - e), ps = (unsigned)(c31 - self);
+                if (pe < 32u) wd &= ~(1u << pe);
+                if (w == 1 && ps < 32u) wd &= ~(1u << ps);
+                if (wd != 0u) {
+                  mw[nw] = make_uint2(wd, (unsigned)c31);
+                  nw++;
+                }
               }
             }
+          }
+
+          if (MODE == T2_FORCE_SAVE && act) {  // kept for the hessian kernel (a zero word ends the list)
+            uint2 *mp = a.masks + (size_t)i * U_NWORDS;
+            for (int k = 0; k < nw; k++) mp[k] = mw[k];
+            if (nw < U_NWORDS) mp[nw] = make_uint2(0u, 0u);
           }
         }
 
@@ -529,15 +605,27 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
             if (b0) defer[nd++] = j0;
             if (b1) defer[nd++] = j1;
             if (nd >= 3) {
-              for (int k = 0; k < nd; k++) U_EXACT(defer[k]);
+              for (int k = 0; k < nd; k++) {
+                if constexpr (MODE == T2_HESS)
+                  U_EXACT_H(defer[k]);
+                else
+                  U_EXACT(defer[k]);
+              }
               nd = 0;
             }
           }
           const bool v0 = live0 & !b0 & (e0 < 0), v1 = live1 & !b1 & (e1 < 0);  // e < 0 <=> s < rc2s
           s0 = v0 ? s0 : 1e300;
           s1 = v1 ? s1 : 1e300;
-          U_ACCUM(dx0, dy0, dz0, s0);
-          U_ACCUM(dx1, dy1, dz1, s1);
+          if constexpr (MODE == T2_HESS) {
+            const double ex0 = fix - gx[j0], ey0 = fiy - gy[j0], ez0 = fiz - gz[j0];
+            const double ex1 = fix - gx[j1], ey1 = fiy - gy[j1], ez1 = fiz - gz[j1];
+            U_HESS(dx0, dy0, dz0, s0, ex0, ey0, ez0);
+            U_HESS(dx1, dy1, dz1, s1, ex1, ey1, ez1);
+          } else {
+            U_ACCUM(dx0, dy0, dz0, s0);
+            U_ACCUM(dx1, dy1, dz1, s1);
+          }
           npf += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
           if (adv) nxt = (ww + 1 < nw) ? ld : make_uint2(0u, 0u);
         }
@@ -547,8 +635,13 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
           if (lane == 0) atomicAdd(&g_t2stats[0], (unsigned long long)mi);
         }
 #endif
-        for (int k = 0; k < nd; k++) U_EXACT(defer[k]);
-        if (act) {
+        for (int k = 0; k < nd; k++) {
+          if constexpr (MODE == T2_HESS)
+            U_EXACT_H(defer[k]);
+          else
+            U_EXACT(defer[k]);
+        }
+        if (MODE != T2_HESS && act) {
           a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
           a.f[3 * (size_t)i + 1] = 24.0 * fy;
           a.f[3 * (size_t)i + 2] = 24.0 * fz;
@@ -568,7 +661,7 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
       acc.a = cutacc;
       acc.vir = cutacc + a12;
       acc.lap = 22.0 * a14 - 5.0 * a8;
-      acc.hes = 0.0;
+      acc.hes = hs;
       acc.np = npf;
       acc.ovr = ovr;
     }
@@ -576,39 +669,68 @@ __global__ void __launch_bounds__(U_NT, U_CTAS)
   }
 }
 
-// -> upper bound of the partial rows written, or a negative status.  The exact number of rows (items) is known on
-// the device only: the kernel stores it in *rows_out (work_counter + 4), which the reducers read.
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter) {
+template <int MODE>
+static int tile2_grid() {
   static int grid = 0;
-  const size_t smem = tile2_smem_bytes();
   if (grid == 0) {
-    ATLJ_CUDA(cudaFuncSetAttribute(pair_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = tile2_smem_bytes(MODE);
+    if (cudaFuncSetAttribute(pair_tile2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return -1;
     int per_sm = 0, dev = 0, sms = 0;
-    ATLJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_tile2_kernel, U_NT, smem));
-    ATLJ_CUDA(cudaGetDevice(&dev));
-    ATLJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_tile2_kernel<MODE>, U_NT, smem) != cudaSuccess ||
+        cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return -1;
     grid = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  if (a.g.sc > 1024 || !a.tile_tab) {
-    set_error("pair_tile2: sc = %d exceeds 1024 cells per edge or the item table is missing", a.g.sc);
+  return grid;
+}
+
+// -> upper bound of the partial rows written, or a negative status.  The exact number of rows (items) is known on
+// the device only: the kernel stores it in *rows_out (work_counter + 4), which the reducers read.
+// mode: T2_FORCE, T2_FORCE_SAVE (a.masks receives the mask words) or T2_HESS (a.fin = forces, a.masks from the
+// T2_FORCE_SAVE launch on the same cell table; the item table of that launch is reused).
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode) {
+  const int grid = mode == T2_HESS ? tile2_grid<T2_HESS>()
+                                   : (mode == T2_FORCE_SAVE ? tile2_grid<T2_FORCE_SAVE>() : tile2_grid<T2_FORCE>());
+  if (grid < 0) {
+    set_error("pair_tile2: kernel attributes -> %s", cudaGetErrorString(cudaGetLastError()));
+    return ATLJ_ERR_CUDA;
+  }
+  const size_t smem = tile2_smem_bytes(mode);
+  if (a.g.sc > 1024 || !a.tile_tab || (mode != T2_FORCE && !a.masks) || (mode == T2_HESS && !a.fin)) {
+    set_error("pair_tile2: sc = %d exceeds 1024 cells per edge, or a table / mask / force buffer is missing", a.g.sc);
     return ATLJ_ERR_ARG;
   }
   const int nyb = (a.g.sc + 1) / 2, nrp = a.g.nx_own * nyb, gstride = tile2_gstride(a.g);
-  // chunks per item: about 8 items per resident CTA, at least 1 (small systems), at most U_GK_MAX
+  // chunks per item: about 8 items per resident CTA (of the force kernel, so that both modes cut the same items), at
+  // least 1 (small systems), at most U_GK_MAX
+  const int grid_f = tile2_grid<T2_FORCE>();
   const long long natoms = a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells();
   const long long chunks = natoms / (U_NT - U_NT / 16) + nrp;
-  int gk = (int)(chunks / (8ll * grid));
+  int gk = (int)(chunks / (8ll * (grid_f > 0 ? grid_f : grid)));
   gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
   // cells a chunk may span: the staged cross-section (12 rows per cell, one halo cell at each end) has to fit U_CAP
   const double per_cell = (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
   int ncz_max = (int)(0.96 * U_CAP / (U_K * (per_cell > 0.05 ? per_cell : 0.05))) - 2;
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
-  ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
-  tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, a.tile_tab);
-  ATLJ_LAUNCHED();
+  if (mode != T2_HESS) {
+    ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
+    tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, a.tile_tab);
+    ATLJ_LAUNCHED();
+  }
   const int bound = nrp * (gstride - 1);
-  pair_tile2_kernel<<<grid < bound ? grid : bound, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab,
-                                                                    work_counter, work_counter + 4);
+  const int nblk = grid < bound ? grid : bound;
+  if (mode == T2_HESS)
+    pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
+                                                         work_counter + 4);
+  else if (mode == T2_FORCE_SAVE)
+    pair_tile2_kernel<T2_FORCE_SAVE><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab,
+                                                               work_counter, work_counter + 4);
+  else
+    pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
+                                                          work_counter + 4);
   ATLJ_LAUNCHED();
   return bound;
 }

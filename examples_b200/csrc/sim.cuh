@@ -43,6 +43,7 @@ struct atlj_sim {
   int pair_kernel = 0;  // 0 = tile2 (LJ force) / tile1 (WCA, hessian); 1 = tile1 everywhere
   int *tile_tab = nullptr;     // work-item table of pair_tile2
   int tile_tab_ints = 0;
+  uint2 *masks = nullptr;      // pair_tile2 mask words (allocated with the first hessian request)
   double *vf_partials = nullptr;  // [<= 4096][4] partial {sum v^2, sum f^2} of the integration kernels
   bool unfused = false;
   double *scal = nullptr;      // 64 device scalars (thermostat state, reduction results)

@@ -267,3 +267,43 @@ def test_baseline_sizes_properties():
     _, _, f, ids = sim.download_sorted()
     assert np.array_equal(np.sort(ids), np.arange(n)) and np.max(np.abs(f.sum(axis=0))) < 1e-7 * np.max(np.abs(f))
     sim.close()
+
+
+@pytest.mark.parametrize("nc,sigma", [(20, 0.05), (13, 0.08)])
+def test_hessian_from_kept_masks_vs_oracle(oracle, nc, sigma):
+    """Device-resident hessian (md_lj_module.py:176-191): the force kernel keeps its mask words, the hessian kernel
+    walks them with the forces staged beside the positions (csrc/pair_tile2.cu, T2_HESS).  Against the C oracle on the
+    same positions and the device's own forces; then step by step inside run_nve."""
+    from examples_b200.device import Simulation
+    from examples_b200.lattice import ran_velocities
+    n, box, r = liquid_like(nc, 0.75, sigma)
+    sim = Simulation(box, 2.5, r, ran_velocities(n, 1.0))
+    rec = sim.force(hessian=True)
+    rs, vs, fs, ids = sim.download_sorted()
+    ho = oracle.hessian(rs, fs, box, 2.5, cells=True)
+    assert abs(rec[6] - ho) <= 1e-10 * abs(ho)
+    recs = sim.run_nve(0.005, 5, hessian=True)
+    rs, vs, fs, ids = sim.download_sorted()
+    ho = oracle.hessian(rs, fs, box, 2.5, cells=True)
+    assert abs(recs[-1, 6] - ho) <= 1e-10 * abs(ho)
+    t, fo, ovr, npair = oracle.force(rs, box, 2.5, cells=True)
+    assert rel_err(fs, fo) < 1e-10 and recs[-1, 8] == npair
+    sim.close()
+
+
+def test_hessian_crowded_cell_matches_tiled_kernel(oracle):
+    """A crowded neighbourhood (slow chunk path of both kernels) and overlapping atoms: hessian through the device
+    object equals the oracle's."""
+    from examples_b200.device import Simulation
+    n, box, r = liquid_like(6, 0.75, 0.02)
+    rng = np.random.default_rng(3)
+    g = np.stack(np.meshgrid(*[np.arange(9)] * 3, indexing="ij"), -1).reshape(-1, 3)[:700]
+    extra = (g * 0.9 + 0.3) / box - 0.5 + rng.normal(0, 1e-3, (700, 3))
+    r2 = np.ascontiguousarray(np.concatenate([r, extra]))
+    r2 = r2 - np.rint(r2)
+    sim = Simulation(box, 2.5, r2)
+    rec = sim.force(hessian=True)
+    rs, vs, fs, ids = sim.download_sorted()
+    ho = oracle.hessian(rs, fs, box, 2.5, cells=True)
+    assert abs(rec[6] - ho) <= 1e-10 * abs(ho)
+    sim.close()
