@@ -45,6 +45,15 @@ static inline size_t tile2_smem_bytes(int mode) {
 }
 size_t pair_tile2_mask_bytes(long long natoms) { return sizeof(uint2) * (size_t)U_NWORDS * (size_t)natoms; }
 
+#ifndef ATLJ_U_SE
+#define ATLJ_U_SE 3
+#endif
+#ifndef ATLJ_U_IPC
+#define ATLJ_U_IPC 8  // work items per resident CTA the item size aims at
+#endif
+#ifndef ATLJ_U_P1U
+#define ATLJ_U_P1U 4
+#endif
 constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps every SM busy) .. 4
 
 // Work items.  The atoms of a row pair (two adjacent y rows of one x layer) are taken in "interleaved" order: for each
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           gx[s] = a.fin[3 * j], gy[s] = a.fin[3 * j + 1], gz[s] = a.fin[3 * j + 2];
         };
         constexpr int HWS = U_NT / 16;  // half warps per CTA
-        constexpr int SE = 2;           // entries in flight per half warp (4 measured no better)
+        constexpr int SE = ATLJ_U_SE;   // entries in flight per half warp (3: 0.819 ms, 2: 0.836, 4 no better than 2)
         for (int e0 = hw; e0 < NE; e0 += SE * HWS) {
           // entries e0, e0 + HWS, ...: issue the global loads of all of them before any is converted, so that a half
           // warp pays one load latency per SE entries (ncu: the staging loop held 13 % of the stall samples)
@@ -709,7 +718,7 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   const int grid_f = tile2_grid<T2_FORCE>();
   const long long natoms = a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells();
   const long long chunks = natoms / (U_NT - U_NT / 16) + nrp;
-  int gk = (int)(chunks / (8ll * (grid_f > 0 ? grid_f : grid)));
+  int gk = (int)(chunks / ((long long)ATLJ_U_IPC * (grid_f > 0 ? grid_f : grid)));
   gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
   // cells a chunk may span: the staged cross-section (12 rows per cell, one halo cell at each end) has to fit U_CAP
   const double per_cell = (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
