@@ -314,3 +314,33 @@ def test_tiled_wca_route_matches_direct(oracle):
     r = np.ascontiguousarray(r - np.rint(r))
     t, fo, ovr, npair = oracle.force(r, box, WCA_R_CUT, cells=True, le=True, strain=0.31)
     assert np.max(np.abs(a[:4] - t) / np.abs(t)) < TOL and rel_err(a[4:].reshape(-1, 3), fo) < TOL
+
+
+@pytest.mark.parametrize("n,box", [(2200, 20.0), (5000, 23.0), (900, 10.5)])
+def test_thin_cells_through_the_tiled_kernel(oracle, n, box):
+    """3-6 atoms per cell: the tiled LJ kernel with chunks that span many cells (up to the whole z extent of a row
+    pair, staged planes wrapping around the box), sc = 8, 9 and 4."""
+    import math
+    from examples_b200 import md_lj_ll_module
+    from examples_b200.device import Simulation
+    from examples_b200.md_lj_module import _force
+    rng = np.random.default_rng(n)
+    m = math.ceil(n ** (1.0 / 3.0)) + 1
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    r = (g[rng.permutation(len(g))[:n]] + 0.5) / m - 0.5 + rng.normal(0.0, 0.12 / m, (n, 3))
+    r = np.ascontiguousarray(r - np.rint(r))
+    sc = math.floor(box / 2.5)
+    assert n >= 3 * sc ** 3, "meant for the tiled kernel, not the direct one"
+    t, fo, ovr, npair = oracle.force(r, box, 2.5, cells=True)
+    total, f = md_lj_ll_module.force(box, 2.5, r)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL and total.ovr == ovr
+    assert rel_err(f, fo) < TOL
+    rc, _, _, _, npair_g = _force(box, 2.5, r, sc, 1)
+    assert rc == 0 and npair_g == npair
+    sim = Simulation(box, 2.5, r)
+    rec = sim.force(hessian=True)
+    rs, vs, fs, ids = sim.download_sorted()
+    ho = oracle.hessian(rs, fs, box, 2.5, cells=True)
+    assert abs(rec[6] - ho) <= TOL * abs(ho) and rec[8] == npair
+    sim.close()
