@@ -12,6 +12,8 @@
 //                    by atom id (the arrival rank of step 1 is scheduling dependent, the sorted result is not) ->
 //                    "ascending atom index" of the reference; then r (and v, id) are gathered into cell order
 // All HBM-bound; see DESIGN.md for bytes per atom.
+#include <cstring>
+
 #include "common.cuh"
 #include "integrate.cuh"
 #include "pair_math.cuh"
@@ -96,9 +98,11 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
 // step k, then md_lj_ll_module.py:88,106-109):  v += hdt*f [sum v^2, sum f^2 of the finished step]  ->  v += hdt*f
 // -> r += dt*v/box -> wrap -> cell triplet, histogram, arrival rank.  Same separately-rounded operations as
 // kick_sums_kernel + kick_drift_kernel + cell_assign_kernel, so results are bit-identical to the unfused sequence.
-__global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
+template <bool RCP>
+__global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
                                                         const double *__restrict__ f, double half_dt, double dt,
-                                                        double box, int first_kick, int *__restrict__ cellid,
+                                                        double box, double inv_box, int first_kick,
+                                                        int *__restrict__ cellid,
                                                         int *__restrict__ rank, int *__restrict__ cell_count,
                                                         int *__restrict__ err, double *__restrict__ partials,
                                                         double *__restrict__ rec_vf,
@@ -131,7 +135,18 @@ __global__ void __launch_bounds__(IT) kdk_assign_kernel(Geom g, int n, double *_
           s[1] += ff * ff;
         }
         vv = __dadd_rn(vv, __dmul_rn(half_dt, ff));
-        double x = wrap1(__dadd_rn(r[e], __ddiv_rn(__dmul_rn(dt, vv), box)));
+        // (dt*v)/box, correctly rounded without the division subroutine (and its 64 registers): with y = RN(1/box)
+        // from the host, q = RN(a*y), r = a - q*box (exact in an fma), RN(q + r*y) is RN(a/box) (Markstein); the host
+        // passes inv_box = 0 for the one family of divisors the theorem excludes (significand all ones)
+        const double a = __dmul_rn(dt, vv);
+        double q;
+        if (RCP) {
+          q = __dmul_rn(a, inv_box);
+          q = __fma_rn(__fma_rn(-q, box, a), inv_box, q);
+        } else {
+          q = __ddiv_rn(a, box);
+        }
+        double x = wrap1(__dadd_rn(r[e], q));
         x = __dsub_rn(x, rint(x));  // the force routine wraps again (md_lj_ll_module.py:88); idempotent
         v[e] = vv;
         r[e] = x;
@@ -255,9 +270,20 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   const int nb = integ_blocks(n);
   SlabArgs sl = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
   if (slab) sl = *slab;
-  kdk_assign_kernel<<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, first_kick ? 1 : 0, b.cellid, b.rank,
-                                       b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows, model, sl,
-                                       pair_rows_dev);
+  // y = RN(1/box) for the division-free exact quotient; not for a divisor whose significand is all ones, nor when
+  // the quotient could leave the normal range (never for a box length, but cheap to check)
+  unsigned long long bits;
+  memcpy(&bits, &box, sizeof(bits));
+  const bool ones = (bits & 0xfffffffffffffull) == 0xfffffffffffffull;
+  const double inv_box = (!ones && box > 1e-100 && box < 1e100) ? 1.0 / box : 0.0;
+  if (inv_box != 0.0)
+    kdk_assign_kernel<true><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
+                                               b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
+                                               pair_rows, model, sl, pair_rows_dev);
+  else
+    kdk_assign_kernel<false><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
+                                                b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
+                                                pair_rows, model, sl, pair_rows_dev);
   ATLJ_LAUNCHED();
   return nb;
 }
