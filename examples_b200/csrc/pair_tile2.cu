@@ -161,7 +161,8 @@ __device__ __forceinline__ double rcp46(double s) {
     ovr |= o_.ovr;                                                                     \
     if (o_.in) {                                                                       \
       U_ACCUM(o_.dx, o_.dy, o_.dz, o_.s);                                              \
-      npf++;                                                                           \
+    } else {                                                                           \
+      npf--; /* it was counted with the filter's survivors */                          \
     }                                                                                  \
   } while (0)
 
@@ -183,7 +184,8 @@ __device__ __forceinline__ double rcp46(double s) {
     if (o_.in) {                                                                       \
       const double ex_ = fix - gx[(jj)], ey_ = fiy - gy[(jj)], ez_ = fiz - gz[(jj)];   \
       U_HESS(o_.dx, o_.dy, o_.dz, o_.s, ex_, ey_, ez_);                                \
-      npf++;                                                                           \
+    } else {                                                                           \
+      npf--;                                                                           \
     }                                                                                  \
   } while (0)
 
@@ -484,8 +486,10 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         }
         const double uix = ux[self], uiy = uy[self], uiz = uz[self];
         // ---- phase 1: packed fp32 filter -> left-aligned mask words --------------------------------------------
-        uint2 mw[U_NWORDS];  // (mask word, staged index of the candidate of its bit 0 ... i.e. of bit 31, plus 31)
+        // (mask word, shared-memory address of ux[c] for the candidate c of bit 31); bit p <-> candidate c + 31 - p
+        uint2 mw[U_NWORDS];
         int nw = 0;
+        unsigned pc = 0u;  // survivors of the filter: in-range pairs = pc - (those phase 2 rejects)
         double fix = 0.0, fiy = 0.0, fiz = 0.0;  // T2_HESS: this atom's force
         if constexpr (MODE == T2_HESS) {
           fix = gx[self], fiy = gy[self], fiz = gz[self];
@@ -495,7 +499,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             for (; nw < U_NWORDS; nw++) {
               const uint2 m = mp[nw];
               if (m.x == 0u) break;
-              mw[nw] = m;
+              pc += __popc(m.x);
+              mw[nw] = make_uint2(m.x, ux_s + 8u * m.y);  // kept as staged index of bit 31's candidate
             }
           }
         } else {
@@ -538,8 +543,10 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
                 if (pe < 32u) wd &= ~(1u << pe);
                 if (w == 1 && ps < 32u) wd &= ~(1u << ps);
                 if (wd != 0u) {
-                  mw[nw] = make_uint2(wd, (unsigned)c31);
+                  // second member: shared-memory address of the candidate a leading-zero count of 0 stands for
+                  mw[nw] = make_uint2(wd, ux_s + 8u * (unsigned)(c31 - 31));
                   nw++;
+                  pc += __popc(wd);
                 }
               }
             }
@@ -547,7 +554,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
 
           if (MODE == T2_FORCE_SAVE && act) {  // kept for the hessian kernel (a zero word ends the list)
             uint2 *mp = a.masks + (size_t)i * U_NWORDS;
-            for (int k = 0; k < nw; k++) mp[k] = mw[k];
+            for (int k = 0; k < nw; k++) mp[k] = make_uint2(mw[k].x, (mw[k].y - ux_s) >> 3);
             if (nw < U_NWORDS) mp[nw] = make_uint2(0u, 0u);
           }
         }
@@ -559,10 +566,12 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         // two independent fp64 chains (the kernel is latency-, not fp64-throughput-bound); a dead slot gets
         // s = 1e300, whose sr^6 underflows to exactly 0, so no branch is needed around the arithmetic.
         double fx = 0.0, fy = 0.0, fz = 0.0;
+        const unsigned self_addr = ux_s + 8u * (unsigned)self;
+        npf += pc;
         int nd = 0;
         int defer[4];
         int ww = 0;
-        uint2 cur = make_uint2(0u, 0u), nxt = make_uint2(0u, 0u);  // (mask, staged index of bit 0's candidate + 31)
+        uint2 cur = make_uint2(0u, 0u), nxt = make_uint2(0u, 0u);  // (mask, address of the candidate a leading-zero count of 0 stands for)
         if (nw > 0) cur = mw[0];
         if (nw > 1) nxt = mw[1];
 #ifdef ATLJ_TILE2_STATS
@@ -592,27 +601,44 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           const uint2 ld = mw[min(ww + 1, U_NWORDS - 1)];
           if (adv) cur = nxt;
           unsigned cm = cur.x;
-          const bool live0 = cm != 0u;
-          const int p0 = 31 - __clz(cm | 1u);
-          cm &= ~(1u << p0);
-          const bool live1 = cm != 0u;
-          const int p1 = 31 - __clz(cm | 1u);
-          cm &= ~(1u << p1);
+          bool live0 = cm != 0u;
+          const int z0 = __clz(cm | 1u);
+          cm &= ~(0x80000000u >> z0);
+          bool live1 = cm != 0u;
+          const int z1 = __clz(cm | 1u);
+          cm &= ~(0x80000000u >> z1);
           cur.x = cm;
-          const int j0 = live0 ? (int)cur.y - p0 : 0, j1 = live1 ? (int)cur.y - p1 : 0;
-          const double dx0 = uix - lds_f64(ux_s + 8u * j0), dy0 = uiy - lds_f64(ux_s + 8u * (j0 + U_CAP)),
-                       dz0 = uiz - lds_f64(ux_s + 8u * (j0 + 2 * U_CAP));
-          const double dx1 = uix - lds_f64(ux_s + 8u * j1), dy1 = uiy - lds_f64(ux_s + 8u * (j1 + U_CAP)),
-                       dz1 = uiz - lds_f64(ux_s + 8u * (j1 + 2 * U_CAP));
+          // a dead slot reads the atom's own coordinates (any valid address would do); its s is replaced below
+          const unsigned a0 = live0 ? cur.y + 8u * (unsigned)z0 : self_addr;
+          const unsigned a1 = live1 ? cur.y + 8u * (unsigned)z1 : self_addr;
+          const double dx0 = uix - lds_f64(a0), dy0 = uiy - lds_f64(a0 + 8u * U_CAP),
+                       dz0 = uiz - lds_f64(a0 + 16u * U_CAP);
+          const double dx1 = uix - lds_f64(a1), dy1 = uiy - lds_f64(a1 + 8u * U_CAP),
+                       dz1 = uiz - lds_f64(a1 + 16u * U_CAP);
           double s0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), s1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
           const int e0 = __double2hiint(s0 - rc2s), e1 = __double2hiint(s1 - rc2s);
-          // |s - rc2s| <= band or s < sovr, tested conservatively on the high words (integer pipe, not fp64):
-          // such pairs are set aside and decided with the reference's exact operation sequence
-          const bool b0 = live0 & (((e0 & 0x7fffffff) <= band_hi) | (__double2hiint(s0) <= sovr_hi));
-          const bool b1 = live1 & (((e1 & 0x7fffffff) <= band_hi) | (__double2hiint(s1) <= sovr_hi));
-          if (b0 | b1) {
-            if (b0) defer[nd++] = j0;
-            if (b1) defer[nd++] = j1;
+          // Not plainly in range - outside (a false positive of the fp32 filter), or |s - rc2s| <= band, or s < sovr
+          // (tested conservatively on the high words: integer pipe, not fp64) - is rare and leaves the hot path: the
+          // borderline pairs are set aside and decided with the reference's exact operation sequence, the rest is
+          // dropped.  Survivors were counted in phase 1, so the hot path counts nothing.
+          const bool n0 = ((e0 & 0x7fffffff) <= band_hi) | (__double2hiint(s0) <= sovr_hi);
+          const bool n1 = ((e1 & 0x7fffffff) <= band_hi) | (__double2hiint(s1) <= sovr_hi);
+          const bool r0 = live0 & (n0 | (e0 >= 0)), r1 = live1 & (n1 | (e1 >= 0));
+          if (r0 | r1) {
+            if (r0) {
+              if (n0)
+                defer[nd++] = (int)((a0 - ux_s) >> 3);
+              else
+                npf--;
+              live0 = false;
+            }
+            if (r1) {
+              if (n1)
+                defer[nd++] = (int)((a1 - ux_s) >> 3);
+              else
+                npf--;
+              live1 = false;
+            }
             if (nd >= 3) {
               for (int k = 0; k < nd; k++) {
                 if constexpr (MODE == T2_HESS)
@@ -623,19 +649,19 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
               nd = 0;
             }
           }
-          const bool v0 = live0 & !b0 & (e0 < 0), v1 = live1 & !b1 & (e1 < 0);  // e < 0 <=> s < rc2s
-          s0 = v0 ? s0 : 1e300;
-          s1 = v1 ? s1 : 1e300;
+          s0 = live0 ? s0 : 1e300;
+          s1 = live1 ? s1 : 1e300;
           if constexpr (MODE == T2_HESS) {
-            const double ex0 = fix - gx[j0], ey0 = fiy - gy[j0], ez0 = fiz - gz[j0];
-            const double ex1 = fix - gx[j1], ey1 = fiy - gy[j1], ez1 = fiz - gz[j1];
+            const double ex0 = fix - lds_f64(a0 + 24u * U_CAP), ey0 = fiy - lds_f64(a0 + 32u * U_CAP),
+                         ez0 = fiz - lds_f64(a0 + 40u * U_CAP);
+            const double ex1 = fix - lds_f64(a1 + 24u * U_CAP), ey1 = fiy - lds_f64(a1 + 32u * U_CAP),
+                         ez1 = fiz - lds_f64(a1 + 40u * U_CAP);
             U_HESS(dx0, dy0, dz0, s0, ex0, ey0, ez0);
             U_HESS(dx1, dy1, dz1, s1, ex1, ey1, ez1);
           } else {
             U_ACCUM(dx0, dy0, dz0, s0);
             U_ACCUM(dx1, dy1, dz1, s1);
           }
-          npf += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
           if (adv) nxt = (ww + 1 < nw) ? ld : make_uint2(0u, 0u);
         }
 #ifdef ATLJ_TILE2_STATS
