@@ -14,6 +14,8 @@
 //     straight into left-aligned 32-bit mask words;
 //   * work items (x layer, y row pair, z part) are handed out through an atomic counter so the tail of the grid
 //     stays busy; every item writes its own row of partial sums, so totals stay bitwise reproducible.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "pair_math.cuh"
 
@@ -23,8 +25,14 @@ namespace atlj {
 #define ATLJ_U_NT 128
 #endif
 constexpr int U_NT = ATLJ_U_NT;         // threads per CTA = i atoms per batch
-constexpr int U_CTAS = U_NT == 128 ? 4 : 2;                // resident CTAs per SM (registers: 128 per thread)
-constexpr int U_CAP = U_NT == 128 ? 1280 : 2304;           // staged candidates per chunk
+#ifndef ATLJ_U_CTAS
+#define ATLJ_U_CTAS 5
+#endif
+constexpr int U_CTAS = U_NT == 128 ? ATLJ_U_CTAS : 2;      // resident CTAs per SM (registers: 128 per thread)
+#ifndef ATLJ_U_CAP
+#define ATLJ_U_CAP 1280
+#endif
+constexpr int U_CAP = U_NT == 128 ? ATLJ_U_CAP : 2304;           // staged candidates per chunk (nine cell planes of a liquid)
 constexpr int U_MAXC = U_NT == 128 ? 24 : 32;              // logical cells per chunk, incl. one halo cell at each end
 constexpr int U_K = 12;                 // staged rows per z cell: 4 y-offsets (outer) x 3 x-offsets (inner)
 constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
@@ -41,7 +49,7 @@ enum { T2_FORCE = 0, T2_FORCE_SAVE = 1, T2_HESS = 2 };
 static inline size_t tile2_smem_bytes(int mode) {
   const size_t tab = sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
   if (mode == T2_HESS) return sizeof(double) * 6 * U_CAP + tab;
-  return sizeof(double) * 3 * U_CAP + sizeof(float4) * (U_CAP + 2) + tab;
+  return sizeof(double) * 3 * U_CAP + sizeof(uint4) * (U_CAP / 2 + 1) + tab;
 }
 size_t pair_tile2_mask_bytes(long long natoms) { return sizeof(uint2) * (size_t)U_NWORDS * (size_t)natoms; }
 
@@ -108,6 +116,9 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
 // debug build only (make stats): where do the phase-2 iterations go?
 __device__ unsigned long long g_t2stats[8];
 #endif
+
+__device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
+__device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2 *>(&u); }
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
@@ -198,9 +209,10 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   double *uy = ux + U_CAP;
   double *uz = uy + U_CAP;
   double *gx = uz + U_CAP, *gy = gx + U_CAP, *gz = gy + U_CAP;  // T2_HESS only: forces of the staged candidates
-  float4 *qp = reinterpret_cast<float4 *>(uz + U_CAP);  // pair p: qp[2p] = (x0,x1,y0,y1), qp[2p+1] = (z0,z1,n0,n1)
+  // fp16 copy for the filter: record p holds candidates 2p (low halves) and 2p+1 (high halves): (x, y, z, unused)
+  uint4 *hp = reinterpret_cast<uint4 *>(uz + U_CAP);
   // [U_NE + 4] staged offset of entry e = cell*12 + row
-  int *S = MODE == T2_HESS ? reinterpret_cast<int *>(gz + U_CAP) : reinterpret_cast<int *>(qp + U_CAP + 2);
+  int *S = MODE == T2_HESS ? reinterpret_cast<int *>(gz + U_CAP) : reinterpret_cast<int *>(hp + U_CAP / 2 + 1);
   int *egl = S + U_NE + 4;                               // [U_NE] global index of the first atom of entry e
   __shared__ int rowcell0[U_K];
   __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const double sovr = (1.0 / 1.77) * (1.0 + 1e-6);
   const int band_hi = __double2hiint(band), sovr_hi = __double2hiint(sovr);
   const double sci = 1.0 / (double)sc;
-  const float *qf = reinterpret_cast<const float *>(qp);
+  const __half *hq = reinterpret_cast<const __half *>(hp);
   const unsigned ux_s = (unsigned)__cvta_generic_to_shared(ux);
 
   for (;;) {
@@ -417,10 +429,9 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           ux[s] = x, uy[s] = y, uz[s] = zz;
           if (MODE != T2_HESS) {
             const float fx = (float)x, fy = (float)y, fz = (float)zz;
-            const float n2 = fx * fx + fy * fy + fz * fz;
-            float *d = reinterpret_cast<float *>(qp + 2 * (s >> 1)) + (s & 1);
-            d[0] = fx, d[2] = fy, d[4] = fz, d[6] = n2;
-            q2m = fmaxf(q2m, n2);
+            __half *d = reinterpret_cast<__half *>(hp + (s >> 1)) + (s & 1);
+            d[0] = __float2half_rn(fx), d[2] = __float2half_rn(fy), d[4] = __float2half_rn(fz);
+            q2m = fmaxf(q2m, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));  // largest coordinate of the chunk
           }
         };
         auto putf = [&](int s, size_t j) {  // T2_HESS: the candidate's force next to its position
@@ -471,9 +482,21 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         }
       }
       __syncthreads();
-      // filter threshold (see pair_tile.cu): rounding of the filter <= ~2e-6 Q^2; 6e-6 Q^2 is used
-      const float q2max = __uint_as_float(s_q2max);
-      const float thr = (float)(rc2s * (1.0 + 1e-6) + 6e-6 * (double)q2max) * (1.0f + 2e-7f);
+      // Filter threshold.  The filter evaluates d^2 = dx^2 + dy^2 + dz^2 in fp16 (unit roundoff u = 2^-11) on fp16 copies
+      // of the chunk-centred coordinates, |coordinate| <= Q.  For a pair within the cutoff R: each difference is off by
+      // at most ec = 2uQ (two quantised coordinates) + uR (the subtraction), the sum of squares by at most
+      // 2 sqrt(3) R ec + 3 ec^2, and the three fp16 operations that form it by at most 6 u R^2 more.  With 10 % on
+      // top and rounded up to fp16, no pair with d^2 < R^2 can fail the test; what passes in excess (about 3 % at
+      // Q = 11 sigma) is rejected by the fp64 evaluation.
+      const float Qm = __uint_as_float(s_q2max) * 1.001f;
+      float thr;
+      {
+        const float u = 4.8828125e-4f, R = sqrtf((float)rc2s) * 1.0001f;
+        const float ec = 2.f * u * Qm + u * R;
+        const float E = 3.4642f * R * ec + 3.f * ec * ec + 6.f * u * R * R;
+        thr = (float)rc2s * (1.0f + 1e-5f) + 1.1f * E;
+      }
+      const __half thr_h = __float2half_ru(thr);
 
       for (int ib = 0; ib < ni; ib += U_NT) {
         const int il = ib + tid;
@@ -504,34 +527,31 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             }
           }
         } else {
-          const float *qs = qf + 8 * (self >> 1) + (self & 1);
-          const float qix = qs[0], qiy = qs[2], qiz = qs[4], qin = qs[6];
-          const float2 m2x = make_float2(-2.f * qix, -2.f * qix), m2y = make_float2(-2.f * qiy, -2.f * qiy),
-                       m2z = make_float2(-2.f * qiz, -2.f * qiz);
-          const float nt = qin - thr;
-          const float2 nti = make_float2(nt, nt);
-
+          const __half *qs = hq + 8 * (self >> 1) + (self & 1);
+          const __half2 xi2 = __half2half2(qs[0]), yi2 = __half2half2(qs[2]), zi2 = __half2half2(qs[4]);
+          const __half2 nthr2 = __half2half2(__hneg(thr_h));
           if (act) {
-  #pragma unroll 1
+#pragma unroll 1
             for (int w = 0; w < 3; w++) {
               const int eb = (myc + w) * U_K + k0;
               const int b = S[eb], e = S[eb + 9];
               if (e <= b) continue;
               const int b0 = b & ~1;
               const int npairs = ((e + 1) >> 1) - (b0 >> 1);
-              const float4 *pp = qp + b0;  // = qp + 2 * (b0 >> 1)
+              const uint4 *pp = hp + (b0 >> 1);
               for (int base = 0; base < npairs; base += 16) {
                 const int n = min(16, npairs - base);
                 unsigned wd = 0u;
-  #pragma unroll 4
+#pragma unroll 4
                 for (int k = 0; k < n; k++) {
-                  const float4 A = pp[2 * (base + k)], B = pp[2 * (base + k) + 1];
-                  float2 t = __fadd2_rn(make_float2(B.z, B.w), nti);
-                  t = __ffma2_rn(m2z, make_float2(B.x, B.y), t);
-                  t = __ffma2_rn(m2y, make_float2(A.z, A.w), t);
-                  t = __ffma2_rn(m2x, make_float2(A.x, A.y), t);
-                  wd = __funnelshift_l(__float_as_uint(t.x), wd, 1);
-                  wd = __funnelshift_l(__float_as_uint(t.y), wd, 1);
+                  const uint4 A = pp[base + k];
+                  const __half2 dx = __hsub2(xi2, u2h(A.x)), dy = __hsub2(yi2, u2h(A.y)), dz = __hsub2(zi2, u2h(A.z));
+                  __half2 t = __hfma2(dx, dx, nthr2);
+                  t = __hfma2(dy, dy, t);
+                  t = __hfma2(dz, dz, t);
+                  const unsigned tu = h2u(t);  // sign bits: candidate 2k at bit 15, candidate 2k+1 at bit 31
+                  wd = __funnelshift_l(tu << 16, wd, 1);
+                  wd = __funnelshift_l(tu, wd, 1);
                 }
                 wd <<= 2 * (16 - n);
                 // bit p <-> candidate c31 - p.  Candidates outside [b, e) that rode along in the first / last pair, and
