@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
 
   const Geom g = a.g;
   const Phys p = a.p;
+  const bool save_masks = MODE == T2_FORCE && a.masks != nullptr;  // T2_FORCE_SAVE is T2_FORCE with a mask buffer
   const int sc = g.sc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *__restrict__ cs = a.cell_start;
   const double box = p.box;
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             }
           }
 
-          if (MODE == T2_FORCE_SAVE && act) {  // kept for the hessian kernel (a zero word ends the list)
+          if (save_masks && act) {  // kept for the hessian kernel (a zero word ends the list)
             uint2 *mp = a.masks + (size_t)i * U_NWORDS;
             for (int k = 0; k < nw; k++) mp[k] = make_uint2(mw[k].x, (mw[k].y - ux_s) >> 3);
             if (nw < U_NWORDS) mp[nw] = make_uint2(0u, 0u);
@@ -637,28 +638,20 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
                        dz1 = uiz - lds_f64(a1 + 16u * U_CAP);
           double s0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), s1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
           const int e0 = __double2hiint(s0 - rc2s), e1 = __double2hiint(s1 - rc2s);
-          // Not plainly in range - outside (a false positive of the fp32 filter), or |s - rc2s| <= band, or s < sovr
-          // (tested conservatively on the high words: integer pipe, not fp64) - is rare and leaves the hot path: the
-          // borderline pairs are set aside and decided with the reference's exact operation sequence, the rest is
-          // dropped.  Survivors were counted in phase 1, so the hot path counts nothing.
+          // Survivors of the filter were counted in phase 1; a false positive (about 3 % of them: the fp16 margin) only
+          // takes one off the count and turns the slot into a dead one - no branch, most warp iterations have one.
+          // |s - rc2s| <= band or s < sovr (tested conservatively on the high words: integer pipe, not fp64) is rare
+          // and leaves the hot path: such pairs are set aside and decided with the reference's exact operation sequence.
           const bool n0 = ((e0 & 0x7fffffff) <= band_hi) | (__double2hiint(s0) <= sovr_hi);
           const bool n1 = ((e1 & 0x7fffffff) <= band_hi) | (__double2hiint(s1) <= sovr_hi);
-          const bool r0 = live0 & (n0 | (e0 >= 0)), r1 = live1 & (n1 | (e1 >= 0));
-          if (r0 | r1) {
-            if (r0) {
-              if (n0)
-                defer[nd++] = (int)((a0 - ux_s) >> 3);
-              else
-                npf--;
-              live0 = false;
-            }
-            if (r1) {
-              if (n1)
-                defer[nd++] = (int)((a1 - ux_s) >> 3);
-              else
-                npf--;
-              live1 = false;
-            }
+          const bool b0 = live0 & n0, b1 = live1 & n1;
+          npf -= (live0 & !n0 & (e0 >= 0)) ? 1u : 0u;
+          npf -= (live1 & !n1 & (e1 >= 0)) ? 1u : 0u;
+          live0 = live0 & !n0 & (e0 < 0);
+          live1 = live1 & !n1 & (e1 < 0);
+          if (b0 | b1) {
+            if (b0) defer[nd++] = (int)((a0 - ux_s) >> 3);
+            if (b1) defer[nd++] = (int)((a1 - ux_s) >> 3);
             if (nd >= 3) {
               for (int k = 0; k < nd; k++) {
                 if constexpr (MODE == T2_HESS)
@@ -748,7 +741,7 @@ static int tile2_grid() {
 // T2_FORCE_SAVE launch on the same cell table; the item table of that launch is reused).
 int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode) {
   const int grid = mode == T2_HESS ? tile2_grid<T2_HESS>()
-                                   : (mode == T2_FORCE_SAVE ? tile2_grid<T2_FORCE_SAVE>() : tile2_grid<T2_FORCE>());
+                                   : tile2_grid<T2_FORCE>();
   if (grid < 0) {
     set_error("pair_tile2: kernel attributes -> %s", cudaGetErrorString(cudaGetLastError()));
     return ATLJ_ERR_CUDA;
@@ -780,12 +773,13 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   if (mode == T2_HESS)
     pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
                                                          work_counter + 4);
-  else if (mode == T2_FORCE_SAVE)
-    pair_tile2_kernel<T2_FORCE_SAVE><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab,
-                                                               work_counter, work_counter + 4);
   else
-    pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
+  {
+    PairArgs af = a;
+    if (mode == T2_FORCE) af.masks = nullptr;
+    pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
                                                           work_counter + 4);
+  }
   ATLJ_LAUNCHED();
   return bound;
 }
