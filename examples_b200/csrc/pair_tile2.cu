@@ -60,8 +60,9 @@ size_t pair_tile2_mask_bytes(long long natoms) { return sizeof(uint2) * (size_t)
 #define ATLJ_U_IPC 8  // work items per resident CTA the item size aims at
 #endif
 #ifndef ATLJ_U_P1U
-#define ATLJ_U_P1U 4
+#define ATLJ_U_P1U 16
 #endif
+constexpr int U_P1U = ATLJ_U_P1U;  // unroll of the filter loop
 constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps every SM busy) .. 4
 
 // Work items.  The atoms of a row pair (two adjacent y rows of one x layer) are taken in "interleaved" order: for each
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
               for (int base = 0; base < npairs; base += 16) {
                 const int n = min(16, npairs - base);
                 unsigned wd = 0u;
-#pragma unroll 4
+#pragma unroll U_P1U
                 for (int k = 0; k < n; k++) {
                   const uint4 A = pp[base + k];
                   const __half2 dx = __hsub2(xi2, u2h(A.x)), dy = __hsub2(yi2, u2h(A.y)), dz = __hsub2(zi2, u2h(A.z));
