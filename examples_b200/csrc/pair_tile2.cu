@@ -1,19 +1,21 @@
 // Second-generation tiled LJ pair-force kernel: the hot kernel of the device-resident loop.
 //
 // Reference arithmetic: python_examples/md_lj_ll_module.py:134-165; scaling md_lj_module.py:143-147.
-// Same exactness scheme as pair_tile.cu (fp32 filter that never drops an in-range pair -> fp64 evaluation, the
-// reference's exact operation sequence for every pair within 1e-8 of the cutoff or near the overlap threshold),
-// with the structure chosen from the ncu profile of the first tiled kernel (profiles/r1_pair_tile_v1.md):
+// Exactness scheme: a cheap filter that never drops an in-range pair -> fp64 evaluation of the survivors, which decides;
+// the reference's exact operation sequence for every pair within 1e-8 of the cutoff or near the overlap threshold.
+// Structure, each step chosen from an ncu profile (profiles/r1_pair_kernel_history.md):
 //   * a CTA owns TWO adjacent y rows of cells, so the staged cross-section is 3 x 4 = 12 rows for two i rows
-//     (6 per i row instead of 9): a third less shared memory per atom -> 4 CTAs (16 warps) per SM, and a third
-//     less staging work;
+//     (6 per i row instead of 9): a third less shared memory per atom and a third less staging work;
 //   * staged candidates are laid out CELL-major (for each z cell: 4 y-offsets x 3 x-offsets), so the candidates of
 //     one thread are ONE contiguous run per z cell (3 runs, ~111 candidates each) instead of 9 short windows;
-//   * the fp32 filter runs on packed pairs of candidates with FFMA2/FADD2 (sm_100 f32x2): 2 LDS.128 + 1 FADD2 +
-//     3 FFMA2 + 2 funnel shifts per TWO candidates; the sign bit of (|qj|^2 - 2 qi.qj) - (thr - |qi|^2) is shifted
-//     straight into left-aligned 32-bit mask words;
-//   * work items (x layer, y row pair, z part) are handed out through an atomic counter so the tail of the grid
-//     stays busy; every item writes its own row of partial sums, so totals stay bitwise reproducible.
+//   * the filter is d^2 = dx^2 + dy^2 + dz^2 in packed fp16 (HADD2/HFMA2) on fp16 copies of the chunk-centred
+//     coordinates: one LDS.128 + 6 half2 operations + 3 shifts per TWO candidates, the sign bit of d^2 - thr shifted
+//     straight into left-aligned 32-bit mask words; thr carries a proven bound of the fp16 error (the kernel is bound
+//     by the shared-memory pipe: the fp32 expanded form it replaced needed two LDS.128 per two candidates);
+//   * 43 KB of shared memory and 96 registers per thread: 5 CTAs (20 warps) per SM;
+//   * work items (chunks of <= 128 atoms of a row pair, not cell-aligned) are handed out through an atomic counter so
+//     the tail of the grid stays busy; every item writes its own row of partial sums, so totals stay bitwise
+//     reproducible.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
