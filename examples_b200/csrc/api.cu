@@ -108,6 +108,13 @@ int sim_ensure_rec(atlj_sim *s, int64_t nrec) {
   return ATLJ_OK;
 }
 
+// mean atoms per cell of the whole system (all ranks)
+double sim_per_cell(const atlj_sim *s) {
+  const double cells = (double)s->g.sc * s->g.sc * s->g.sc;
+  const long long nt = s->n_total > 0 ? s->n_total : s->n;
+  return cells > 0 ? (double)nt / cells : 0.0;
+}
+
 static int ensure_masks(atlj_sim *s) {
   if (s->masks) return ATLJ_OK;
   const size_t bytes = pair_tile2_mask_bytes(s->cap);
@@ -159,6 +166,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.tile_tab = s->tile_tab;
     a.masks = nullptr;
     a.natoms = (int)s->n;
+    a.per_cell = sim_per_cell(s);
     a.g = s->g;
     a.p = p;
     Timer::begin(s, 0);
@@ -456,6 +464,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
       PairArgs a;
       a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
       a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
+      a.per_cell = sim_per_cell(s);
       a.masks = nullptr;
       Timer::begin(s, 0);
       nb_prev = direct ? launch_pair_direct(s->st, a, false, n)
@@ -682,6 +691,7 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.tile_tab = s->tile_tab;
     a.masks = nullptr;
     a.natoms = (int)s->n;
+    a.per_cell = sim_per_cell(s);
     a.g = s->g;
     a.p = p;
     nb = sim_direct(s) ? launch_pair_direct(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true);

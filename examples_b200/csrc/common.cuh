@@ -169,6 +169,8 @@ struct PairArgs {
   int *tile_tab;         // work-item table of pair_tile2 (pair_tile2_tab_ints)
   uint2 *masks;          // pair_tile2: per-atom mask words kept between the force and the hessian kernel, or nullptr
   int natoms;            // owned atoms (a hint for the work-item size; 0 = unknown)
+  double per_cell;       // mean atoms per cell of the WHOLE system (0 = unknown): fixes the chunk rule of pair_tile2, so
+                         // that a slab cuts the same chunks - and sums in the same order - as the single domain
   Geom g;
   Phys p;
 };

@@ -333,6 +333,7 @@ static PairArgs pair_args(atlj_sim *s) {
   PairArgs a;
   a.r = s->r[s->cur], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
   a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = s->p;
+  a.per_cell = sim_per_cell(s);
   a.masks = nullptr;
   a.p.strain = 0.0, a.p.shift = 0;
   return a;

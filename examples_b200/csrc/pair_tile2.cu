@@ -763,7 +763,8 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   int gk = (int)(chunks / ((long long)ATLJ_U_IPC * (grid_f > 0 ? grid_f : grid)));
   gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
   // cells a chunk may span: the staged cross-section (12 rows per cell, one halo cell at each end) has to fit U_CAP
-  const double per_cell = (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
+  const double per_cell =
+      a.per_cell > 0.0 ? a.per_cell : (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
   int ncz_max = (int)(0.96 * U_CAP / (U_K * (per_cell > 0.05 ? per_cell : 0.05))) - 2;
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
   if (mode != T2_HESS) {
