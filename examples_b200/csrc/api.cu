@@ -108,6 +108,13 @@ int sim_ensure_rec(atlj_sim *s, int64_t nrec) {
   return ATLJ_OK;
 }
 
+// The second-generation LJ kernel keeps fp16 copies of chunk-centred coordinates (sigma units): its chunks must stay
+// within the fp16 range, which a cell wider than 40 sigma (a cutoff beyond 32 sigma) could break - such systems and the
+// WCA model go through the first tiled kernel.
+bool sim_tile2(const atlj_sim *s) {
+  return s->pair_kernel == 0 && s->p.model == ATLJ_MODEL_LJ && s->p.box <= 40.0 * s->g.sc;
+}
+
 // mean atoms per cell of the whole system (all ranks)
 double sim_per_cell(const atlj_sim *s) {
   const double cells = (double)s->g.sc * s->g.sc * s->g.sc;
@@ -172,7 +179,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     Timer::begin(s, 0);
     int nb;
     const bool direct = sim_direct(s);
-    const bool tile2 = !direct && s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
+    const bool tile2 = !direct && sim_tile2(s);
     // hessian after the tile2 force kernel: that kernel keeps its mask words, the hessian kernel walks them
     const bool hess2 = with_hessian && tile2;
     if (hess2) {
@@ -443,7 +450,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     int nb_prev = 0;
     double *rec_prev = nullptr;
     const bool direct = sim_direct(s);
-    const bool tile2 = !direct && s->pair_kernel == 0 && p.model == ATLJ_MODEL_LJ;
+    const bool tile2 = !direct && sim_tile2(s);
     for (int k = 0; k < nsteps; k++) {
       double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
       ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));

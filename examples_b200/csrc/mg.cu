@@ -269,7 +269,7 @@ static inline unsigned char *peer_recv(const MgState &m, int kind, int dir, int 
 
 // device-side row count of the tiled LJ kernel's partials (null for the other pair kernels)
 static const int *tile2_rows(atlj_sim *s) {
-  return (s->pair_kernel == 0 && s->p.model == ATLJ_MODEL_LJ) ? s->cb.err + 6 : nullptr;
+  return sim_tile2(s) ? s->cb.err + 6 : nullptr;
 }
 
 // ---- the phases -----------------------------------------------------------------------------------------------------------
@@ -361,7 +361,7 @@ static int phase3(atlj_sim *s) {
   Timer::end(s);
   const PairArgs a = pair_args(s);
   Timer::begin(s, 0);
-  const int nb = (s->pair_kernel == 0 && a.p.model == ATLJ_MODEL_LJ) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
+  const int nb = sim_tile2(s) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
                                                                    : launch_pair_tile(s->st, a, false);
   Timer::end(s);
   m.step++;

@@ -766,6 +766,9 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   const double per_cell =
       a.per_cell > 0.0 ? a.per_cell : (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
   int ncz_max = (int)(0.96 * U_CAP / (U_K * (per_cell > 0.05 ? per_cell : 0.05))) - 2;
+  // fp16 range: the chunk-centred z coordinates stay below 100 sigma
+  const double cell = a.p.box / a.g.sc;
+  if (ncz_max > (int)(200.0 / cell) - 2) ncz_max = (int)(200.0 / cell) - 2;
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
   if (mode != T2_HESS) {
     ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));

@@ -79,6 +79,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
               cudaEvent_t after_sort = nullptr);
 int sim_check_flags(atlj_sim *s);
 double sim_per_cell(const atlj_sim *s);
+bool sim_tile2(const atlj_sim *s);
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
 int sim_ensure_rec(atlj_sim *s, int64_t nrec);
 void sim_mg_destroy(atlj_sim *s);

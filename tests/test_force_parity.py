@@ -344,3 +344,26 @@ def test_thin_cells_through_the_tiled_kernel(oracle, n, box):
     ho = oracle.hessian(rs, fs, box, 2.5, cells=True)
     assert abs(rec[6] - ho) <= TOL * abs(ho) and rec[8] == npair
     sim.close()
+
+
+@pytest.mark.parametrize("r_cut,box", [(30.0, 125.0), (42.0, 172.0)])
+def test_long_cutoff_dilute_system(oracle, r_cut, box):
+    """Cells of 31 and 43 sigma: the fp16 filter of the tiled LJ kernel works on chunk-centred coordinates up to ~100
+    sigma (first case); beyond 40 sigma per cell the first tiled kernel takes over (second case)."""
+    import math
+    from examples_b200 import md_lj_ll_module
+    from examples_b200.md_lj_module import _force
+    sc = math.floor(box / r_cut)
+    assert sc == 4
+    n = 420
+    rng = np.random.default_rng(int(r_cut))
+    g = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    r = (g[rng.permutation(len(g))[:n]] + 0.5) / 8.0 - 0.5 + rng.normal(0.0, 0.02, (n, 3))   # spacing >> sigma
+    r = np.ascontiguousarray(r - np.rint(r))
+    t, fo, ovr, npair = oracle.force(r, box, r_cut, cells=True)
+    total, f = md_lj_ll_module.force(box, r_cut, r)
+    tg = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(tg - t) / np.abs(t)) < TOL and total.ovr == ovr
+    assert rel_err(f, fo) < TOL
+    rc, _, _, _, npair_g = _force(box, r_cut, r, sc, 1)
+    assert rc == 0 and npair_g == npair
