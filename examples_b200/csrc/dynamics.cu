@@ -50,7 +50,7 @@ __device__ __forceinline__ void gauss3(unsigned long long seed, unsigned id, uns
 // ---- BAOAB: B(t) A(t) O(2t) A(t) fused, one thread per atom (bd_nvt_lj.py:223-226) ---------------------------------
 __global__ void __launch_bounds__(IT) baoab_kernel(int n, double *__restrict__ r, double *__restrict__ v,
                                                    const double *__restrict__ f, const int *__restrict__ id, double t,
-                                                   double box, double decay, double amp,
+                                                   BoxDiv box, double decay, double amp,
                                                    const double *__restrict__ noise, unsigned long long seed,
                                                    unsigned step) {
   for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(IT) baoab_kernel(int n, double *__restrict__ r
     for (int k = 0; k < 3; k++) {
       const size_t e = 3 * (size_t)i + k;
       double vv = __dadd_rn(v[e], __dmul_rn(t, f[e]));                          // b_propagator, :109
-      double x = wrap1(__dadd_rn(r[e], __ddiv_rn(__dmul_rn(t, vv), box)));      // a_propagator, :100-101
+      double x = wrap1(__dadd_rn(r[e], div_box(__dmul_rn(t, vv), box)));      // a_propagator, :100-101
       vv = __dadd_rn(__dmul_rn(vv, decay), __dmul_rn(amp, g[k]));               // o_propagator, :127
-      x = wrap1(__dadd_rn(x, __ddiv_rn(__dmul_rn(t, vv), box)));                // a_propagator
+      x = wrap1(__dadd_rn(x, div_box(__dmul_rn(t, vv), box)));                // a_propagator
       v[e] = vv;
       r[e] = x;
     }
@@ -145,7 +145,7 @@ __global__ void sllod_b2_coef_kernel(const double *sums /*Sfv, Sff, Svv*/, doubl
 
 // a(t) and b1(t) on one atom; b1_first selects the order (b1 then a at the end of a step, a then b1 at its start)
 __global__ void __launch_bounds__(IT) sllod_ab1_kernel(int n, double *__restrict__ r, double *__restrict__ v, double t,
-                                                       double x, double strain_new, double box,
+                                                       double x, double strain_new, BoxDiv box,
                                                        const double *__restrict__ coef, int b1_first,
                                                        double *__restrict__ partials) {
   const double g = coef[0];
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(IT) sllod_ab1_kernel(int n, double *__restrict
     }
     // a_propagator, :92-98
     rx = __dadd_rn(rx, __dmul_rn(x, ry));
-    rx = __dadd_rn(rx, __ddiv_rn(__dmul_rn(t, vx), box));
-    ry = __dadd_rn(ry, __ddiv_rn(__dmul_rn(t, vy), box));
-    rz = __dadd_rn(rz, __ddiv_rn(__dmul_rn(t, vz), box));
+    rx = __dadd_rn(rx, div_box(__dmul_rn(t, vx), box));
+    ry = __dadd_rn(ry, div_box(__dmul_rn(t, vy), box));
+    rz = __dadd_rn(rz, div_box(__dmul_rn(t, vz), box));
     rx = __dsub_rn(rx, __dmul_rn(rint(ry), strain_new));
     rx = wrap1(rx), ry = wrap1(ry), rz = wrap1(rz);
     if (!b1_first) {
@@ -238,7 +238,7 @@ static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const dou
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     Timer::begin(s, 2);
-    baoab_kernel<<<atom_blocks(n), IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], s->f, s->id[s->cur], t, s->p.box,
+    baoab_kernel<<<atom_blocks(n), IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], s->f, s->id[s->cur], t, make_box_div(s->p.box),
                                                    decay, amp,
                                                    noise_dev ? noise_dev + (size_t)k * 3 * (size_t)s->n_total : nullptr,
                                                    seed, (unsigned)(s->step_count + k));
@@ -361,7 +361,7 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
     sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
     ATLJ_LAUNCHED();
     advance();
-    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, s->p.box, coef, 0, s->partials);
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, make_box_div(s->p.box), coef, 0, s->partials);
     ATLJ_LAUNCHED();
     Timer::end(s);
     if ((rc = sim_force(s, st, false, rec, false))) return rc;
@@ -379,7 +379,7 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
     sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
     ATLJ_LAUNCHED();
     advance();
-    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, s->p.box, coef, 1, s->partials);
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, make_box_div(s->p.box), coef, 1, s->partials);
     ATLJ_LAUNCHED();
     if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
     sllod_rec_kernel<<<1, 32, 0, s->st>>>(sumv, sumf, st, rec);

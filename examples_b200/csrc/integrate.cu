@@ -17,7 +17,7 @@ namespace atlj {
 // vscale (device scalar, may be null) multiplies v first: pending Nose-Hoover U3 factor (md_nvt_lj.py:129).
 __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__restrict__ r, double *__restrict__ v,
                                                         const double *__restrict__ f, double half_dt, double dt,
-                                                        double box, const double *__restrict__ vscale,
+                                                        BoxDiv box, const double *__restrict__ vscale,
                                                         const int *__restrict__ n_dev) {
   if (n_dev) n3 = min(n3, 3ll * *n_dev);  // atom count kept on the device (slab path): n3 is an upper bound
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__
     double vv = v[t];
     if (vscale) vv = __dmul_rn(vv, sc);
     vv = __dadd_rn(vv, __dmul_rn(half_dt, f[t]));
-    double x = __dadd_rn(r[t], __ddiv_rn(__dmul_rn(dt, vv), box));
+    double x = __dadd_rn(r[t], div_box(__dmul_rn(dt, vv), box));
     v[t] = vv;
     r[t] = wrap1(x);
   }
@@ -83,7 +83,7 @@ int integ_blocks(long long n3) {
 int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const double *f, double half_dt, double dt,
                       double box, const double *vscale, const int *n_dev) {
   if (n3 <= 0) return ATLJ_OK;
-  kick_drift_kernel<<<integ_blocks(n3), IT, 0, st>>>(n3, r, v, f, half_dt, dt, box, vscale, n_dev);
+  kick_drift_kernel<<<integ_blocks(n3), IT, 0, st>>>(n3, r, v, f, half_dt, dt, make_box_div(box), vscale, n_dev);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

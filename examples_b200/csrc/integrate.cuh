@@ -1,5 +1,7 @@
 // Launchers of integrate.cu (internal).
 #pragma once
+#include <cstring>
+
 #include "common.cuh"
 
 namespace atlj {
@@ -7,6 +9,29 @@ namespace atlj {
 constexpr int IT = 256;
 
 __device__ __forceinline__ double wrap1(double x) { return __dsub_rn(x, rint(x)); }
+
+// a / box, correctly rounded, without the division subroutine: with inv = RN(1/box) from the host, q = RN(a*inv),
+// r = a - q*box (exact in an fma), RN(q + r*inv) = RN(a/box) (Markstein).  inv = 0 selects the division: the host does
+// that for the one family of divisors the theorem excludes (significand all ones) and outside the normal range.
+struct BoxDiv {
+  double box, inv;
+};
+inline BoxDiv make_box_div(double box) {
+  unsigned long long bits;
+  memcpy(&bits, &box, sizeof(bits));
+  const bool ones = (bits & 0xfffffffffffffull) == 0xfffffffffffffull;
+  BoxDiv b;
+  b.box = box;
+  b.inv = (!ones && box > 1e-100 && box < 1e100) ? 1.0 / box : 0.0;
+  return b;
+}
+__device__ __forceinline__ double div_box(double a, const BoxDiv &b) {
+  if (b.inv != 0.0) {
+    const double q = __dmul_rn(a, b.inv);
+    return __fma_rn(__fma_rn(-q, b.box, a), b.inv, q);
+  }
+  return __ddiv_rn(a, b.box);
+}
 
 // CTA reduction of K values, result row written by thread 0
 template <int K>
@@ -36,7 +61,7 @@ int launch_sums_final(cudaStream_t st, const double *partials, int nblocks, int 
 int integ_blocks(long long n3);
 // n_dev (may be null): the atom count lives on the device and n3 is only an upper bound (slab path)
 int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const double *f, double half_dt, double dt,
-                      double box, const double *vscale, const int *n_dev = nullptr);
+                      double box, const double *vscale, const int *n_dev = nullptr);  // box: plain length
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
                      double *out2, const int *n_dev = nullptr);
 int launch_vf_sums(cudaStream_t st, long long n3, const double *v, const double *f, double *partials, double *out2);

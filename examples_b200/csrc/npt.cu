@@ -21,13 +21,13 @@ namespace atlj {
 
 __global__ void __launch_bounds__(IT) npt_kick_drift_kernel(long long n3, double *__restrict__ r,
                                                             double *__restrict__ v, const double *__restrict__ f,
-                                                            double s3, double e2, double c2t, double c1t, double box) {
+                                                            double s3, double e2, double c2t, double c1t, BoxDiv box) {
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
   const long long stride = (long long)gridDim.x * IT;
   for (; t < n3; t += stride) {
     double vv = __dmul_rn(v[t], s3);                                      // u3, md_npt_lj.py:166 (applied lazily)
     vv = __dadd_rn(__dmul_rn(vv, e2), __dmul_rn(c2t, f[t]));             // u2, :149
-    const double x = __dadd_rn(r[t], __ddiv_rn(__dmul_rn(c1t, vv), box));  // u1, :120
+    const double x = __dadd_rn(r[t], div_box(__dmul_rn(c1t, vv), box));  // u1, :120
     v[t] = vv;
     r[t] = wrap1(x);                                                      // :121
   }
@@ -163,7 +163,7 @@ extern "C" int atlj_sim_run_npt(atlj_sim *s, double dt, double temperature, doub
     const double x1 = dt * z.p_eps / z.w_eps;
     const double c1t = exprel_neg(x1) * dt;
     Timer::begin(s, 2);
-    npt_kick_drift_kernel<<<nb, IT, 0, s->st>>>(n3, s->r[s->cur], s->v[s->cur], s->f, z.pend, e2, c2t, c1t, z.box);
+    npt_kick_drift_kernel<<<nb, IT, 0, s->st>>>(n3, s->r[s->cur], s->v[s->cur], s->f, z.pend, e2, c2t, c1t, make_box_div(z.box));
     ATLJ_LAUNCHED();
     Timer::end(s);
     z.pend = 1.0;
