@@ -212,6 +212,9 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
+#ifndef ATLJ_HALO_PACK_CTAS
+#define ATLJ_HALO_PACK_CTAS 296
+#endif
 static NcclApi g_nccl;
 
 static int nccl_load() {
@@ -321,7 +324,7 @@ static int phase2(atlj_sim *s, double *rec) {
   Timer::end(s);
   s->cur = alt;
   Timer::begin(s, 5);
-  halo_pack_kernel<<<dim3(296, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
+  halo_pack_kernel<<<dim3(ATLJ_HALO_PACK_CTAS, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
                                                     peer_recv(m, 1, 1, par), (int)m.halo_cap, stamp, m.cnt_dev + 8,
                                                     s->cb.err, m.cnt_dev + 1, rec);
   ATLJ_LAUNCHED();

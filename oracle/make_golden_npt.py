@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference):
 
     python oracle/make_golden_npt.py
 
-Two cases: N=256 at rho=0.75 (all-pairs route, 100 steps, the driver's default parameters), and N=2048 compressed to
+Three cases: N=864 whose shrinking box leaves the link-cell regime (sc 4 -> 3) during the run, N=256 at rho=0.75 (all-pairs route, 100 steps, the driver's default parameters), and N=2048 compressed to
 box = 12.49 sigma so that the expanding box crosses box/r_cut = 5 within the run: the cell grid of the link-cell route
 changes from sc=4 to sc=5 on the way (md_lj_ll_module.py:106).
 """
@@ -70,6 +70,9 @@ def main():
     lj = ref_module("md_lj_module")
     run_case("npt256", 4, None, 100, 0.99, 21, out, lj)
     run_case("npt2048", 8, 12.49, 40, 0.99, 22, out, lj)
+    # N=864 at rho=0.75 (box 10.48, sc=4) under a pressure of 8: the shrinking box drops below 4 cells per edge, the
+    # force path switches from link cells to all pairs during the run
+    run_case("npt864", 6, None, 80, 8.0, 23, out, lj)
     path = os.path.join(ROOT, "tests", "golden", "reference_npt.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; numpy", np.__version__)

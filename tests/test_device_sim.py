@@ -123,11 +123,12 @@ def test_nhc_trajectory_golden(golden_dyn):
     sim.close()
 
 
-@pytest.mark.parametrize("tag", ["npt256", "npt2048"])
+@pytest.mark.parametrize("tag", ["npt256", "npt2048", "npt864"])
 def test_npt_trajectory_golden(tag):
     """md_npt_lj.py:344-366 executed from the reference source (oracle/make_golden_npt.py) vs the device loop with
-    host-side chains: N=256 (all pairs, 100 steps) and N=2048, where the expanding box takes the link-cell grid from
-    sc=4 to sc=5 during the 40 steps."""
+    host-side chains: N=256 (all pairs, 100 steps); N=2048, where the expanding box takes the link-cell grid from
+    sc=4 to sc=5 during the 40 steps; N=864 under a pressure of 8, where the shrinking box leaves the link-cell regime
+    (sc 4 -> 3: all pairs) during the 80 steps."""
     import math
     from examples_b200.device import Simulation
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_npt.npz"))
@@ -152,6 +153,8 @@ def test_npt_trajectory_golden(tag):
     assert abs(sim.box - rec_g[-1, 6]) < 1e-12 * sim.box and sim.sc == math.floor(rec_g[-1, 6] / 2.5)
     if tag == "npt2048":
         assert (sc0, sim.sc) == (4, 5), "the run must cross a cell-grid change"
+    if tag == "npt864":
+        assert (sc0, sim.sc) == (4, 3), "the run must leave the link-cell regime (all pairs from then on)"
     # conserved quantity (md_npt_lj.py:81-83): kinetic + potential + P*V + extended terms, per atom
     n = r.shape[0]
     cons = (0.5 * rec[:, 4] + rec[:, 1] + float(g[tag + "_pressure"]) * rec[:, 9] ** 3 + rec[:, 10]) / n
