@@ -69,6 +69,34 @@ def test_baoab_trajectory_golden(golden_dyn):
     sim.close()
 
 
+def test_thermostats_on_the_link_cell_route_golden():
+    """bd_nvt_lj.py and md_nvt_lj.py loops executed from the reference source with md_lj_ll_module.force at N = 864
+    (oracle/make_golden_dynamics_ll.py) vs the device loops, which take the link-cell kernels at sc = 4."""
+    from examples_b200.device import Simulation
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_dynamics_ll.npz"))
+    box = float(g["box"])
+    sim = Simulation(box, 2.5, g["r0"], g["bd_v0"])
+    assert sim.sc == 4
+    sim.force()
+    rec = sim.run_baoab(0.005, 1.0, 1.0, g["bd_rec"].shape[0], noise=g["bd_noise"])
+    for k in range(6):
+        assert rel_err(rec[:, k], g["bd_rec"][:, k]) < 1e-9, k
+    r, v, f = sim.download()
+    assert rel_err(r, g["bd_r1"]) < 1e-9 and rel_err(v, g["bd_v1"]) < 1e-9
+    sim.close()
+    sim = Simulation(box, 2.5, g["r0"], g["nhc_v0"])
+    sim.force()
+    eta, p_eta, q = np.zeros(3), g["nhc_p_eta0"].copy(), g["nhc_q"].copy()
+    rec = sim.run_nhc(0.005, 1.0, eta, p_eta, q, g["nhc_rec"].shape[0], g=float(g["nhc_g"]))
+    for k in range(6):
+        assert rel_err(rec[:, k], g["nhc_rec"][:, k]) < 1e-9, k
+    assert rel_err(rec[:, 10], g["nhc_rec"][:, 6]) < 1e-9
+    assert rel_err(eta, g["nhc_eta1"]) < 1e-9 and rel_err(p_eta, g["nhc_p_eta1"]) < 1e-9
+    r, v, f = sim.download()
+    assert rel_err(r, g["nhc_r1"]) < 1e-9 and rel_err(v, g["nhc_v1"]) < 1e-9
+    sim.close()
+
+
 def test_baoab_device_rng_statistics():
     """Philox + Box-Muller on the device: with a huge friction one O step replaces v by sqrt(T) * N(0,1)."""
     from examples_b200.device import Simulation
