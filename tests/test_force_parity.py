@@ -367,3 +367,30 @@ def test_long_cutoff_dilute_system(oracle, r_cut, box):
     assert rel_err(f, fo) < TOL
     rc, _, _, _, npair_g = _force(box, r_cut, r, sc, 1)
     assert rc == 0 and npair_g == npair
+
+
+@pytest.mark.parametrize("tag,nc,model", [("c3", 40, "wca"), ("c4", 63, "lj"), ("c5", 80, "lj")])
+def test_baseline_sizes_against_the_oracle(oracle, tag, nc, model):
+    """The BASELINE.json configurations at FULL size against the C oracle (OpenMP over cells on the host cores):
+    c3 N = 256,000 WCA with Lees-Edwards cells at strain 0.3, c4 N = 1,000,188 and c5 N = 2,048,000 LJ liquids.
+    Totals and forces to 1e-10, in-range pair count and overlap flag exact."""
+    from examples_b200.device import Simulation
+    n, box, r = liquid_like(nc, 0.75, 0.07)
+    if model == "wca":
+        strain = 0.3
+        r[:, 0] = r[:, 0] - np.rint(r[:, 1]) * strain
+        r = np.ascontiguousarray(r - np.rint(r))
+        t, fo, ovr, npair = oracle.force(r, box, WCA_R_CUT, cells=True, le=True, strain=strain, omp=True)
+        sim = Simulation(box, None, r, model="wca")
+        rec = sim.force(strain=strain)
+    else:
+        t, fo, ovr, npair = oracle.force(r, box, 2.5, cells=True, omp=True)
+        sim = Simulation(box, 2.5, r)
+        rec = sim.force()
+    rs, vs, fs, ids = sim.download_sorted()
+    f = np.empty_like(fs)
+    f[ids] = fs
+    assert rec[8] == npair and bool(rec[7]) == ovr
+    assert np.max(np.abs(rec[:4] - t) / np.abs(t)) < TOL
+    assert rel_err(f, fo) < TOL
+    sim.close()
