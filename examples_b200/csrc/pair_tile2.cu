@@ -41,11 +41,11 @@ constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
 constexpr int U_WW = 6;                 // mask words per window (<= 191 candidates per window)
 constexpr int U_NWORDS = 3 * U_WW;
 
-// Kernel modes.  T2_FORCE: forces + totals.  T2_FORCE_SAVE: the same, and every atom's mask words (the filter's
-// survivors) are kept in global memory.  T2_HESS: the hessian sum (md_lj_module.py:176-191) from those mask words - no
+// Kernel modes.  T2_FORCE: forces + totals.  T2_FORCE_SAVE: the same launch with a mask buffer - every atom's mask
+// words (the filter's survivors) are kept in global memory.  T2_HESS: the hessian sum (md_lj_module.py:176-191) from those mask words - no
 // filter pass; the chunk boundaries and staged indices are the same because they depend on the cell table only, so a
-// mask word means the same candidates in both kernels.  The forces of the candidates take the place of the fp32 copy in
-// shared memory (48 B per candidate instead of 40: 3 CTAs per SM).
+// mask word means the same candidates in both kernels.  The forces of the candidates take the place of the fp16 copy in
+// shared memory (48 B per candidate instead of 32: 3 CTAs per SM).
 enum { T2_FORCE = 0, T2_FORCE_SAVE = 1, T2_HESS = 2 };
 
 static inline size_t tile2_smem_bytes(int mode) {
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           self = S[(myc + 1) * U_K + k0 + 4] + off;
         }
         const double uix = ux[self], uiy = uy[self], uiz = uz[self];
-        // ---- phase 1: packed fp32 filter -> left-aligned mask words --------------------------------------------
+        // ---- phase 1: packed fp16 filter -> left-aligned mask words --------------------------------------------
         // (mask word, shared-memory address of ux[c] for the candidate c of bit 31); bit p <-> candidate c + 31 - p
         uint2 mw[U_NWORDS];
         int nw = 0;
