@@ -354,11 +354,27 @@ __global__ void __launch_bounds__(SCAN_T) scan_tile_offsets_kernel(int *__restri
 
 // phase C: final exclusive scan, cell_start[first + c] = base + prefix; also writes the end sentinel
 // start is the padded table of the whole local grid (Geom::cs_idx); k-th owned cell sits in layer h + k / sc2
+// fold != 0: tile_off holds the raw tile SUMS (not their scan): every CTA adds up the sums of the tiles before it
+// itself - for grids of up to SCAN_T tiles (2 M cells) that saves the one-CTA kernel in between
 __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restrict__ cnt, int n,
                                                             const int *__restrict__ tile_off, int base_off,
-                                                            int *__restrict__ start, int sc2, int h) {
+                                                            int *__restrict__ start, int sc2, int h, int fold) {
   __shared__ int sm[SCAN_T / 32];
   __shared__ int total;
+  __shared__ int s_before;
+  if (fold) {
+    int t = (int)threadIdx.x < (int)blockIdx.x ? tile_off[threadIdx.x] : 0;  // blockIdx.x <= SCAN_T tiles
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int a = 0;
+      for (int w = 0; w < SCAN_T / 32; w++) a += sm[w];
+      s_before = a;
+    }
+    __syncthreads();
+  }
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
@@ -367,7 +383,7 @@ __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restric
     v[k] = base + k < n ? cnt[base + k] : 0;
     s += v[k];
   }
-  int off = block_exclusive_scan(s, sm, &total) + tile_off[blockIdx.x] + base_off;
+  int off = block_exclusive_scan(s, sm, &total) + (fold ? s_before : tile_off[blockIdx.x]) + base_off;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
     const int c = base + k;
@@ -391,10 +407,13 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
   }
   scan_tile_sums_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums);
   ATLJ_LAUNCHED();
-  scan_tile_offsets_kernel<<<1, SCAN_T, 0, st>>>(b.block_sums, ntiles);
-  ATLJ_LAUNCHED();
+  const int fold = ntiles <= SCAN_T ? 1 : 0;
+  if (!fold) {
+    scan_tile_offsets_kernel<<<1, SCAN_T, 0, st>>>(b.block_sums, ntiles);
+    ATLJ_LAUNCHED();
+  }
   scan_final_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums, base, b.cell_start, g.sc * g.sc,
-                                               g.h);
+                                               g.h, fold);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }
