@@ -126,29 +126,63 @@ __global__ void __launch_bounds__(IT) scale_v_kernel(long long n3, double *__res
 __global__ void set_scalar_kernel(double *p, double val) { *p = val; }
 
 // ---- SLLOD (md_nvt_lj_le.py:84-129) ------------------------------------------------------------------------------
-// coef[0] = g of b1, coef[1] = prefactor, coef[2] = dt_factor of b2 (device scalars written by the kernels below)
-__global__ void sllod_b1_coef_kernel(const double *sums /*Sxy, Syy, Svv*/, double x, double *coef) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// The coefficients of b1 (g) and b2 (prefactor, dt_factor) depend on three global sums each.  The kernel that needs a
+// coefficient forms it itself from the per-CTA rows its predecessor left behind (every CTA adds up the same <= 296 rows
+// in the same fixed order, so all CTAs get the same bits): no reduction kernel and no one-thread kernel in between.
+constexpr int SL_CTAS = 296;  // CTAs of the SLLOD kernels = rows of partial sums (2 per SM)
+
+// out[k] = sum over rows of partials[row][k], k < 3; every thread of the CTA returns the same values
+__device__ __forceinline__ void sllod_reduce_rows(const double *__restrict__ partials, int rows, double out[3]) {
+  __shared__ double red[IT / 32][3];
+  __shared__ double tot[3];
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < rows; b += IT) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) a[k] += __ldcg(partials + 4 * (size_t)b + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) red[threadIdx.x >> 5][k] = a[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < IT / 32; w++) t += red[w][threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  out[0] = tot[0], out[1] = tot[1], out[2] = tot[2];
+  __syncthreads();  // red / tot are reused by block_reduce_store below
+}
+// g of b1_propagator from (Sxy, Syy, Svv), :108-111
+__device__ __forceinline__ double sllod_b1_g(const double sums[3], double x) {
   const double c1 = x * sums[0] / sums[2];
   const double c2 = (x * x) * sums[1] / sums[2];
-  coef[0] = 1.0 / sqrt(1.0 - 2.0 * c1 + c2);
+  return 1.0 / sqrt(1.0 - 2.0 * c1 + c2);
 }
-__global__ void sllod_b2_coef_kernel(const double *sums /*Sfv, Sff, Svv*/, double t, double *coef) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// (prefactor, dt_factor) of b2_propagator from (Sfv, Sff, Svv), :120-127
+__device__ __forceinline__ void sllod_b2_pd(const double sums[3], double t, double &pre, double &dtf) {
   const double alpha = sums[0] / sums[2];
   const double beta = sqrt(sums[1] / sums[2]);
   const double h = (alpha + beta) / (alpha - beta);
   const double e = exp(-beta * t);
-  coef[2] = (1.0 + h - e - h / e) / ((1.0 - h) * beta);
-  coef[1] = (1.0 - h) / (e - h / e);
+  dtf = (1.0 + h - e - h / e) / ((1.0 - h) * beta);
+  pre = (1.0 - h) / (e - h / e);
 }
 
 // a(t) and b1(t) on one atom; b1_first selects the order (b1 then a at the end of a step, a then b1 at its start)
 __global__ void __launch_bounds__(IT) sllod_ab1_kernel(int n, double *__restrict__ r, double *__restrict__ v, double t,
                                                        double x, double strain_new, BoxDiv box,
-                                                       const double *__restrict__ coef, int b1_first,
+                                                       const double *__restrict__ rows_in, int nrows, int b1_first,
                                                        double *__restrict__ partials) {
-  const double g = coef[0];
+  double sums[3];
+  sllod_reduce_rows(rows_in, nrows, sums);  // Sxy, Syy, Svv of the current velocities
+  const double g = sllod_b1_g(sums, x);
   double s[3] = {0.0, 0.0, 0.0};  // sum vx*vy, sum vy^2, sum v^2 of the velocities left behind
   for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
     const size_t e = 3 * (size_t)i;
@@ -193,10 +227,18 @@ __global__ void __launch_bounds__(IT) sllod_fv_sums_kernel(long long n3, const d
 }
 
 // b2_propagator, :129: v = prefactor * (v + dt_factor * f); sums sum vx*vy, sum vy^2, sum v^2 of the new v
+// rows_in = the rows of sllod_fv_sums_kernel; nullptr: identity (plain reduction of the current velocities);
+// sums_f_out (CTA 0): the (Sfv, Sff, Svv) the coefficients came from, for the step record
 __global__ void __launch_bounds__(IT) sllod_b2_kernel(int n, double *__restrict__ v, const double *__restrict__ f,
-                                                      const double *__restrict__ coef,
-                                                      double *__restrict__ partials) {
-  const double pre = coef[1], dtf = coef[2];
+                                                      const double *__restrict__ rows_in, int nrows, double t,
+                                                      double *__restrict__ partials, double *__restrict__ sums_f_out) {
+  double pre = 1.0, dtf = 0.0;
+  if (rows_in) {
+    double sums[3];
+    sllod_reduce_rows(rows_in, nrows, sums);
+    sllod_b2_pd(sums, t, pre, dtf);
+    if (blockIdx.x == 0 && threadIdx.x < 3 && sums_f_out) sums_f_out[threadIdx.x] = sums[threadIdx.x];
+  }
   double s[3] = {0.0, 0.0, 0.0};
   for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
     const size_t e = 3 * (size_t)i;
@@ -211,12 +253,15 @@ __global__ void __launch_bounds__(IT) sllod_b2_kernel(int n, double *__restrict_
   block_reduce_store<3>(s, partials + 4 * (size_t)blockIdx.x);
 }
 
-__global__ void sllod_rec_kernel(const double *sums_v /*Sxy,Syy,Svv*/, const double *sums_f /*Sfv,Sff,Svv*/,
-                                 double strain, double *rec) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  rec[4] = sums_v[2];
+__global__ void __launch_bounds__(IT) sllod_rec_kernel(const double *__restrict__ rows_v, int nrows,
+                                                       const double *sums_f /*Sfv,Sff,Svv*/, double strain,
+                                                       double *rec) {
+  double sv[3];
+  sllod_reduce_rows(rows_v, nrows, sv);  // Sxy, Syy, Svv after the closing a(dt/2)
+  if (threadIdx.x != 0) return;
+  rec[4] = sv[2];
   rec[5] = sums_f[1];
-  rec[9] = sums_v[0];
+  rec[9] = sv[0];
   rec[10] = strain;
 }
 
@@ -335,8 +380,11 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
   if (rc) return rc;
   const int n = (int)s->n;
   const long long n3 = 3 * s->n;
-  const int nb = atom_blocks(n), nb3 = integ_blocks(n3);
-  double *sumv = s->scal + SC_SUMV, *sumf = s->scal + SC_SUMF, *coef = s->scal + SC_COEF;
+  const int nb = atom_blocks(n) < SL_CTAS ? atom_blocks(n) : SL_CTAS;
+  const int nb3 = integ_blocks(n3) < SL_CTAS ? integ_blocks(n3) : SL_CTAS;
+  double *sumf = s->scal + SC_SUMF;
+  // two sets of per-CTA rows, used alternately: a kernel reads the rows of its predecessor and writes its own
+  double *rowsA = s->vf_partials, *rowsB = s->vf_partials + 4 * 2048;
   const double t = dt / 2;              // md_nvt_lj_le.py:230
   const double x = t * strain_rate;     // :89,105
   double st = *strain;
@@ -344,45 +392,30 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
     st = st + x;
     st = st - rint(st);
   };
-  // sums of the starting velocities for the first b1
-  {
-    double zero_coef[4] = {1.0, 1.0, 0.0, 0.0};
-    ATLJ_CUDA(cudaMemcpyAsync(coef, zero_coef, sizeof(zero_coef), cudaMemcpyHostToDevice, s->st));
-    ATLJ_CUDA(cudaStreamSynchronize(s->st));
-    // plain reduction of vx*vy, vy^2, v^2 without touching anything: b2 kernel with pre = 1, dtf = 0
-    sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, coef, s->partials);
-    ATLJ_LAUNCHED();
-    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
-  }
+  const BoxDiv bd = make_box_div(s->p.box);
+  // sums of the starting velocities for the first b1: the b2 kernel as an identity -> rowsA
+  sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, nullptr, 0, dt, rowsA, nullptr);
+  ATLJ_LAUNCHED();
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     Timer::begin(s, 2);
-    // a(dt/2) then b1(dt/2)
-    sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
-    ATLJ_LAUNCHED();
+    // a(dt/2) then b1(dt/2); g from rowsA
     advance();
-    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, make_box_div(s->p.box), coef, 0, s->partials);
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, bd, rowsA, nb, 0, rowsB);
     ATLJ_LAUNCHED();
     Timer::end(s);
     if ((rc = sim_force(s, st, false, rec, false))) return rc;
     Timer::begin(s, 2);
-    // b2(dt)
-    sllod_fv_sums_kernel<<<nb3, IT, 0, s->st>>>(n3, s->v[s->cur], s->f, s->partials);
+    // b2(dt): sums of f.v, f^2, v^2 -> rowsA; the kernel that applies b2 forms its coefficients from them
+    sllod_fv_sums_kernel<<<nb3, IT, 0, s->st>>>(n3, s->v[s->cur], s->f, rowsA);
     ATLJ_LAUNCHED();
-    if ((rc = launch_sums_final(s->st, s->partials, nb3, 3, sumf))) return rc;
-    sllod_b2_coef_kernel<<<1, 32, 0, s->st>>>(sumf, dt, coef);
+    sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, rowsA, nb3, dt, rowsB, sumf);
     ATLJ_LAUNCHED();
-    sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, coef, s->partials);
-    ATLJ_LAUNCHED();
-    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
-    // b1(dt/2) then a(dt/2)
-    sllod_b1_coef_kernel<<<1, 32, 0, s->st>>>(sumv, x, coef);
-    ATLJ_LAUNCHED();
+    // b1(dt/2) then a(dt/2); g from rowsB, the sums of the velocities it leaves behind -> rowsA
     advance();
-    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, make_box_div(s->p.box), coef, 1, s->partials);
+    sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, bd, rowsB, nb, 1, rowsA);
     ATLJ_LAUNCHED();
-    if ((rc = launch_sums_final(s->st, s->partials, nb, 3, sumv))) return rc;
-    sllod_rec_kernel<<<1, 32, 0, s->st>>>(sumv, sumf, st, rec);
+    sllod_rec_kernel<<<1, IT, 0, s->st>>>(rowsA, nb, sumf, st, rec);
     ATLJ_LAUNCHED();
     Timer::end(s);
   }
