@@ -484,7 +484,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     if ((rc = launch_finalize(s->st, s->partials, nb_prev, p.model, false, rec_prev, s->cb.err + 2, nullptr, 0,
                               tile2 ? s->cb.err + 6 : nullptr)))
       return rc;
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_prev + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_prev + 4, s->cb.err + 4))) return rc;
     Timer::end(s);
     s->step_count += nsteps;
     return sim_copy_rec(s, rec_host, nsteps);
@@ -497,7 +497,7 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
     Timer::end(s);
     if ((rc = sim_force(s, 0.0, with_hessian != 0, rec, false))) return rc;
     Timer::begin(s, 2);
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4, s->cb.err + 4))) return rc;
     Timer::end(s);
   }
   s->step_count += nsteps;
@@ -533,7 +533,7 @@ int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_hos
   ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st_copy));
   ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st_copy));
   ATLJ_CUDA(cudaEventRecord(s->ev_copied, s->st_copy));
-  if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, s->rec_dev + 4))) return rc;
+  if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, s->rec_dev + 4, s->cb.err + 4))) return rc;
   ATLJ_CUDA(cudaMemcpyAsync(v_host, s->v[s->cur], b, cudaMemcpyDeviceToHost, s->st));
   ATLJ_CUDA(cudaMemcpyAsync(f_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
   ATLJ_CUDA(cudaStreamWaitEvent(s->st, s->ev_copied, 0));

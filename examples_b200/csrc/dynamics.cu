@@ -291,7 +291,7 @@ static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const dou
     Timer::end(s);
     if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
     Timer::begin(s, 2);
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, t, s->partials, rec + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, t, s->partials, rec + 4, s->cb.err + 4))) return rc;
     Timer::end(s);
   }
   s->step_count += nsteps;
@@ -353,7 +353,7 @@ int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m
     Timer::end(s);
     if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
     Timer::begin(s, 2);
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4, s->cb.err + 4))) return rc;
     nhc_chain_kernel<<<1, 32, 0, s->st>>>(st, m, dt, temperature, g, rec + 4, rec);
     ATLJ_LAUNCHED();
     Timer::end(s);

@@ -33,10 +33,12 @@ __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__
   }
 }
 
-// md_nve_lj.py:190 + the sums of :43-45: v = v + 0.5*dt*f ; partial sum v^2, sum f^2
+// md_nve_lj.py:190 + the sums of :43-45: v = v + 0.5*dt*f ; sum v^2, sum f^2.  Two-level fixed-order reduction in ONE
+// launch: every CTA writes its row, the CTA that finishes last adds the rows up (deterministic) and writes out2[0..1].
 __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__restrict__ v,
                                                        const double *__restrict__ f, double half_dt,
-                                                       double *__restrict__ partials, const int *__restrict__ n_dev) {
+                                                       double *__restrict__ partials, const int *__restrict__ n_dev,
+                                                       int *__restrict__ done, double *__restrict__ out2) {
   if (n_dev) n3 = min(n3, 3ll * *n_dev);
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
   long long stride = (long long)gridDim.x * IT;
@@ -49,6 +51,20 @@ __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__r
     s[1] += ff * ff;
   }
   block_reduce_store<2>(s, partials + 4 * (size_t)blockIdx.x);
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a[2] = {0.0, 0.0};
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
+    a[0] += __ldcg(partials + 4 * (size_t)b);
+    a[1] += __ldcg(partials + 4 * (size_t)b + 1);
+  }
+  block_reduce_store<2>(a, out2);
+  if (threadIdx.x == 0) *done = 0;
 }
 
 // generic second stage: out[k] = sum_b partials[b][k], k < K <= 4, fixed order
@@ -89,11 +105,9 @@ int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const
 }
 
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
-                     double *out2, const int *n_dev) {
+                     double *out2, int *done, const int *n_dev) {
   int nb = integ_blocks(n3);
-  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev);
-  ATLJ_LAUNCHED();
-  sums_final_kernel<<<1, 256, 0, st>>>(partials, nb, 2, out2);
+  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev, done, out2);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

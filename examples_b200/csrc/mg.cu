@@ -377,7 +377,7 @@ static int tail(atlj_sim *s, double dt, double *rec, int nb) {
   if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s))))
     return rc;
   Timer::begin(s, 2);
-  rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->mg.cnt_dev + 1);
+  rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->cb.err + 4, s->mg.cnt_dev + 1);
   Timer::end(s);
   return rc;
 }
