@@ -72,6 +72,8 @@ def lib():
                                    _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.c_int, _vp]
     L.atlj_sim_run_sllod.argtypes = [_vp, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, _vp]
+    L.atlj_force_1.argtypes = [_vp, _vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp,
+                               C.POINTER(C.c_int)]
     L.atlj_cnf_format.argtypes = [_vp, _vp, C.c_int64, C.c_double, _vp]
     L.atlj_cnf_parse.argtypes = [_vp, C.c_int64, C.c_int, _vp, _vp]
     L.atlj_sim_cnf_format.argtypes = [_vp, C.c_int, _vp]

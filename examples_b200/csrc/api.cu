@@ -655,6 +655,38 @@ int atlj_force_lj(const double *r_host, int64_t n, double box, double r_cut_box_
                     ovr, npair);
 }
 
+int atlj_force_1(const double *ri_host, const double *r_host, int64_t nj, double box, double r_cut_box_sq,
+                 double box_sq, double pot_cut, double *f_partial_host, double totals[4], int *ovr) {
+  int rc = device_ok();
+  if (rc) return rc;
+  if (!ri_host || !f_partial_host || !totals || !ovr || nj < 0 || (nj > 0 && !r_host)) {
+    set_error("force_1: bad arguments");
+    return ATLJ_ERR_ARG;
+  }
+  for (int k = 0; k < 4; k++) totals[k] = 0.0;
+  *ovr = 0;
+  if (nj == 0) return ATLJ_OK;
+  atlj_sim *s = host_sim(nj);
+  if (!s) return ATLJ_ERR_CUDA;
+  if ((rc = atlj_sim_configure(s, ATLJ_MODEL_LJ, box, r_cut_box_sq, box_sq, pot_cut, 1, 0, 1))) return rc;
+  const size_t b = sizeof(double) * 3 * (size_t)nj;
+  ATLJ_CUDA(cudaMemcpyAsync(s->r[0], r_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if ((rc = ensure_partials(s, (int)((nj + 127) / 128) + 1))) return rc;
+  const int nb = launch_force_1(s->st, ri_host, s->r[0], (int)nj, s->p, s->f, s->partials);
+  if ((rc = launch_finalize(s->st, s->partials, nb, ATLJ_MODEL_LJ, false, s->rec_dev))) return rc;
+  ATLJ_CUDA(cudaMemcpyAsync(f_partial_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
+  double rec[ATLJ_NREC];
+  if ((rc = sim_copy_rec(s, rec, 1))) return rc;
+  *ovr = rec[7] != 0.0;
+  if (*ovr) {  // smc_lj_module.py:146-149: nothing is usable after an overlap
+    memset(f_partial_host, 0, b);
+    return ATLJ_OK;
+  }
+  for (int k = 0; k < 4; k++) totals[k] = rec[k];
+  return ATLJ_OK;
+}
+
 int atlj_force_le(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double strain,
                   int sc, int shift, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair) {
   (void)shift;  // recomputed as floor(strain*sc) on the host side of the library; the argument documents the contract

@@ -190,6 +190,9 @@ int pair_tile2_tab_ints(const Geom &g);  // ints of PairArgs::tile_tab for this 
 // direct link-cell kernel (cells of ~1 atom): one thread per owned atom, no staging
 int pair_direct_blocks(int n);
 int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n);
+// one atom against nj partners (smc_lj_module.force_1): -> rows of partials written
+int launch_force_1(cudaStream_t st, const double ri[3], const double *r, int nj, const Phys &p, double *f_partial,
+                   double *partials);
 int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, const Phys &p, double *f,
                     double *partials, bool hessian, int *nblocks_out);
 // fixed-order reduction of partials -> rec[0..3], rec[7], rec[8] (force) or rec[6] (hessian)

@@ -189,6 +189,37 @@ int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n) 
   return blocks;
 }
 
+// ---- force_1: one atom against a set of partners (smc_lj_module.py:100-191) ---------------------------------------
+// One thread per partner j with the reference's arithmetic; f_partial[j] = force on i due to j (times 24, :190); the
+// per-CTA rows go through the usual fixed-order finalize.  The caller zeroes everything when the overlap flag comes
+// back set (:146-149).
+__global__ void __launch_bounds__(128) force_1_kernel(double rix, double riy, double riz, const double *__restrict__ r,
+                                                      int nj, Phys p, double *__restrict__ f_partial,
+                                                      double *__restrict__ partials) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0ull, 0};
+  if (j < nj) {
+    double dx, dy, dz, s, fx = 0.0, fy = 0.0, fz = 0.0;
+    if (pair_sep<false>(rix, riy, riz, r[3 * (size_t)j], r[3 * (size_t)j + 1], r[3 * (size_t)j + 2], 0.0,
+                        p.r_cut_box_sq, dx, dy, dz, s))
+      pair_force_term<ATLJ_MODEL_LJ>(p, dx, dy, dz, s, fx, fy, fz, acc);
+    f_partial[3 * (size_t)j] = 24.0 * fx;
+    f_partial[3 * (size_t)j + 1] = 24.0 * fy;
+    f_partial[3 * (size_t)j + 2] = 24.0 * fz;
+  }
+  // finalize halves the sums (it serves kernels that visit every pair from both ends): each pair is visited once here
+  acc.a *= 2.0, acc.pot *= 2.0, acc.vir *= 2.0, acc.lap *= 2.0, acc.np *= 2ull;
+  block_store_partials<4>(acc, partials + 8 * (size_t)blockIdx.x);
+}
+
+int launch_force_1(cudaStream_t st, const double ri[3], const double *r, int nj, const Phys &p, double *f_partial,
+                   double *partials) {
+  const int blocks = (nj + 127) / 128 > 0 ? (nj + 127) / 128 : 1;
+  force_1_kernel<<<blocks, 128, 0, st>>>(ri[0], ri[1], ri[2], r, nj, p, f_partial, partials);
+  ATLJ_LAUNCHED();
+  return blocks;
+}
+
 // ---- fixed-order reduction of the CTA partials + the reference's final scaling ------------------------------------
 constexpr int FIN_T = 1024;
 __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restrict__ partials, int nblocks, int model,

@@ -67,6 +67,12 @@ int64_t atlj_kernel_launches(void); /* kernels launched by this library so far (
 int atlj_force_lj(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double pot_cut,
                   int sc, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair);
 
+/* One atom against a set of partners: smc_lj_module.py:100-191 `force_1(ri, box, r_cut, r)` (the single-atom moves of
+ * smc_nvt_lj.py:200-231).  ri[3] and r (nj,3) in box = 1 units; f_partial (nj,3) = force on the atom due to each
+ * partner; totals = cut, pot, vir, lap with the reference's factors (:185-190).  With an overlap (:146-149) ovr = 1,
+ * totals = 0 and f_partial = 0. */
+int atlj_force_1(const double *ri_host, const double *r_host, int64_t nj, double box, double r_cut_box_sq,
+                 double box_sq, double pot_cut, double *f_partial_host, double totals[4], int *ovr);
 /* Replaces md_lj_le_module.force (md_lj_le_module.py:69-150; sc < 4) and md_lj_llle_module.force
  * (md_lj_llle_module.py:70-245; sc >= 4, shift = floor(strain*sc) of :112).  WCA potential,
  * Lees-Edwards image.  totals = {pot, vir, lap, pyx}. */

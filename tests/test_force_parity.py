@@ -394,3 +394,28 @@ def test_baseline_sizes_against_the_oracle(oracle, tag, nc, model):
     assert np.max(np.abs(rec[:4] - t) / np.abs(t)) < TOL
     assert rel_err(f, fo) < TOL
     sim.close()
+
+
+def test_smc_force_1_golden():
+    """smc_lj_module.force_1 / force (the single-atom and multi-atom moves of smc_nvt_lj.py) against values produced
+    by the reference module (oracle/make_golden_smc.py): per-partner forces and totals to 1e-10, the overlap contract
+    (ovr = True, everything zero, smc_lj_module.py:146-149), assertion messages."""
+    from examples_b200 import smc_lj_module
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_smc.npz"))
+    box, r = float(g["box"]), g["r"]
+    for k, i in enumerate(g["idx"]):
+        rj = np.delete(r, i, 0)
+        partial, fp = smc_lj_module.force_1(r[i, :], box, 2.5, rj)
+        t = np.array([partial.cut, partial.pot, partial.vir, partial.lap])
+        assert not partial.ovr and np.max(np.abs(t - g["f1_totals"][k]) / np.abs(g["f1_totals"][k])) < TOL
+        assert fp.shape == rj.shape and rel_err(fp, g["f1_f"][k]) < TOL
+        assert np.array_equal(fp == 0.0, g["f1_f"][k] == 0.0), "the same partners are out of range"
+    partial, fp = smc_lj_module.force_1(g["ovr_ri"], box, 2.5, g["ovr_rj"])
+    assert partial.ovr and not fp.any() and (partial.pot, partial.cut, partial.vir, partial.lap) == (0.0, 0.0, 0.0, 0.0)
+    total, f = smc_lj_module.force(box, 2.5, r)
+    t = np.array([total.cut, total.pot, total.vir, total.lap])
+    assert np.max(np.abs(t - g["force_totals"]) / np.abs(g["force_totals"])) < TOL and rel_err(f, g["force_f"]) < TOL
+    with pytest.raises(AssertionError, match="Dimension error for r in force_1"):
+        smc_lj_module.force_1(r[0], box, 2.5, r[:, :2])
+    with pytest.raises(AssertionError, match="Dimension error for ri in force_1"):
+        smc_lj_module.force_1(r[0, :2], box, 2.5, r)
