@@ -111,10 +111,32 @@ def make_system(nc, seed=20170101):
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the C restatement of md_nve_lj.py + md_lj_ll_module on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_nve(nc, steps, warmup, melt_state=None):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(wl, nc, world):
+    """The descriptor both arms print (nothing run-dependent in it, so the two lines can be compared key by key)."""
+    n = 4 * nc ** 3
+    box = (n / DENSITY) ** (1.0 / 3.0)
+    n_rank = n / world
+    return {"workload": "%s: NVE LJ, N=%d (fcc nc=%d), rho=0.75, r_cut=2.5, dt=0.005, link cells sc=%d"
+                        % (wl, n, nc, int(np.floor(box / R_CUT))),
+            "atoms_per_gpu": n_rank,
+            "l2": ("state %.0f MB per GPU exceeds the 126 MB L2" % (n_rank * 24 * 7 / 1e6)) if n_rank * 24 * 7 > 126e6
+            else "state fits in L2 (device-resident loop)",
+            "parallelism": "slab%d" % world if world > 1 else "single"}
+
+
+def cpu_nve(nc, steps, warmup, melt_state=None, threads=None):
     """-> atom-steps/s, threads, n.  Liquid-like input: melt_state (r, v) if given, else a perturbed lattice."""
     from oracle import oracle as O
     O.build()
+    # explicit team size: torch.distributed.run exports OMP_NUM_THREADS=1 to its children
+    O.set_num_threads(threads if threads else host_cores())
     n, box, r, v = make_system(nc)
     if melt_state is not None:
         r, v = melt_state
@@ -134,25 +156,33 @@ def cpu_nve(nc, steps, warmup, melt_state=None):
     return n * steps / dt, O.num_threads(True), n, dt
 
 
+def workload_nc(wl, world):
+    if wl == "c5":
+        return NC_WEAK[world]
+    return {"c2": 20, "c4": 63}[wl]
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    # bounded sample: nc=40 (256,000 atoms, same density / cutoff / dt) keeps K+W steps within minutes; the
-    # algorithm is O(N) so atom-steps/s does not depend on the sample size
-    nc = 40
+    # the SAME system as our arm at this N (2,048,000 atoms at 1 GPU ... 16,384,000 at 8): every step is one
+    # velocity-Verlet step of the whole system on all host cores; K + W steps stay within minutes (0.4 s per step
+    # and 2 M atoms on 16 threads).  Not melted (2,000 CPU steps would take a quarter of an hour): the lattice is
+    # disordered with Gaussian displacements instead, which gives the liquid's pair count.
+    nc = workload_nc(args.workload, world)
     value, threads, n, dt = cpu_nve(nc, args.steps, args.warmup)
-    nc_w = NC_WEAK.get(world, 80)
     line = {
         "impl": "reference", "metric": "LJ atom-steps/sec (rho=0.75, r_cut=2.5)", "value": value,
         "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic fcc lattice + Gaussian displacement (sigma 0.08), T=1 velocities",
-        "config": {"workload": "c5: NVE LJ weak scaling, 2,048,000 atoms/GPU (fcc nc=%d), rho=0.75, r_cut=2.5, "
-                               "dt=0.005" % nc_w, "sample_atoms": n},
+        "config": workload_config(args.workload, nc, world),
         "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps of N=%d (fcc nc=%d) velocity Verlet + link-cell force, C restatement "
-                                   "of md_nve_lj.py/md_lj_ll_module.py (gcc -O2 -fopenmp); gfortran absent so the "
-                                   "Fortran twin cannot be built" % (args.steps, n, nc)},
+                         "sample": "%d steps of the whole system, N=%d (fcc nc=%d): velocity Verlet + link-cell "
+                                   "force, C restatement of md_nve_lj.py/md_lj_ll_module.py (gcc -O2 -fopenmp, %d "
+                                   "threads set explicitly; like md_lj_omp_module.f90 it keeps a private N x 3 "
+                                   "force array per thread and allocates its cell arrays every call); gfortran "
+                                   "absent so the Fortran twin cannot be built" % (args.steps, n, nc, threads)},
         "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -218,6 +248,80 @@ def other_workloads():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# driver-visible parity records
+# ---------------------------------------------------------------------------------------------------------------------
+def slab_parity(rank, world, dist, nc=20, nsteps=100):
+    """The REAL multi-process slab path (CUDA IPC peer buffers, stamps, NCCL all-reduce) against the single-domain run
+    of the same system on rank 0's GPU: N = 32,000 (BASELINE config 2), 100 velocity-Verlet steps.  Every rank takes
+    part; rank 0 gets the record, the others None.  Forces are per-atom sums in a fixed order, so r, v, f must agree
+    to the last bit; the totals are reduced in a different order (<= 1e-12)."""
+    from examples_b200.device import Simulation
+    from examples_b200.lattice import fcc_positions, ran_velocities
+    from examples_b200.slab import SlabSimulation
+    n, box, r = fcc_positions(nc, DENSITY)
+    r = r + np.random.default_rng(1).normal(0.0, 0.06 / box, size=r.shape)
+    r = np.ascontiguousarray(r - np.rint(r))
+    v = ran_velocities(n, 1.5)
+    sim = SlabSimulation(box, R_CUT, r, v, rank, world)
+    rec0 = sim.force()
+    rec = sim.run_nve(DT, nsteps)
+    parts = [None] * world
+    dist.all_gather_object(parts, sim.download_sorted())
+    sim.close()
+    if rank != 0:
+        return None
+    one = Simulation(box, R_CUT, r, v)
+    ref0 = one.force()
+    ref = one.run_nve(DT, nsteps)
+    r1, v1, f1 = one.download()
+    one.close()
+    rm, vm, fm = np.empty_like(r1), np.empty_like(r1), np.empty_like(r1)
+    seen = np.zeros(n, dtype=np.int64)
+    for a, b, c, i in parts:
+        rm[i], vm[i], fm[i] = a, b, c
+        seen[i] += 1
+    tot = max(float(np.max(np.abs(rec[:, k] - ref[:, k]) / np.maximum(np.abs(ref[:, k]), 1e-300))) for k in range(6))
+    tot = max(tot, float(np.max(np.abs(rec0[:4] - ref0[:4]) / np.abs(ref0[:4]))))
+    return {"world": world, "n": n, "steps": nsteps, "against": "single-domain run of the same system on rank 0",
+            "every_atom_owned_once": bool(np.all(seen == 1)), "owned_count_conserved": bool(np.all(rec[:, 11] == n)),
+            "pair_counts_equal": bool(np.array_equal(rec[:, 8], ref[:, 8]) and rec0[8] == ref0[8]),
+            "max_abs_diff_r": float(np.max(np.abs(rm - r1))), "max_abs_diff_v": float(np.max(np.abs(vm - v1))),
+            "max_abs_diff_f": float(np.max(np.abs(fm - f1))), "max_rel_diff_step_records": tot}
+
+
+def melted_parity(sim, box, n):
+    """The state the bench times (melted liquid), checked against the CPU restatement of the reference
+    (oracle/, OpenMP): forces, totals, in-range pair count, overlap flag.  oracle/ is the checker here, nothing else."""
+    from oracle import oracle as O
+    O.build()
+    O.set_num_threads(host_cores())
+    rec = sim.force()
+    r, _, f = sim.download()
+    t0 = time.perf_counter()
+    tot, fo, ovr, npair = O.force(r, box, R_CUT, cells=True, omp=True)
+    sec = time.perf_counter() - t0
+    return {"n": n, "against": "oracle/atlj_oracle.c (C restatement of md_lj_ll_module.py:69-224), %d threads, %.2f s"
+                               % (O.num_threads(True), sec),
+            "pair_counts_equal": bool(int(rec[8]) == int(npair)), "pairs": int(npair),
+            "overlap_equal": bool((rec[7] != 0.0) == bool(ovr)),
+            "max_rel_diff_totals": float(np.max(np.abs(rec[:4] - tot) / np.abs(tot))),
+            "max_abs_diff_f": float(np.max(np.abs(f - fo))),
+            "max_rel_diff_f": float(np.max(np.abs(f - fo)) / np.max(np.abs(fo)))}
+
+
+def reference_python_rows(budget=40.0):
+    """The reference's own NumPy routines and its unmodified md_nve_lj.py timed on THIS host (subprocess, so that
+    nothing of the reference is imported into the bench process) -> dict for cpu_baseline["reference_python"]."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference_python.py"), "--budget",
+                            str(budget)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+        return json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "time_reference_python.py failed: %s" % str(e)[:200]}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
@@ -234,14 +338,8 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = args.workload
-    if wl == "c5":
-        nc = NC_WEAK[world]
-    elif wl == "c2":
-        nc = 20
-    elif wl == "c4":
-        nc = 63
-    else:
-        raise SystemExit("unknown workload " + wl)
+    nc = workload_nc(wl, world)
+    parity = slab_parity(rank, world, dist) if world > 1 else None
     n, box, r, v = make_system(nc)
 
     if world > 1:
@@ -330,6 +428,8 @@ def run_ours(args, rank, world, local_rank):
         for a in (pr, pv, pf, pi):
             a.free()
 
+    parity_m = melted_parity(sim, box, n) if world == 1 and not args.no_cpu else None
+
     other = None
     if world == 1 and not args.no_other:
         other = other_workloads()
@@ -360,12 +460,16 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        # bounded sample: nc=40 (256,000 atoms) of the same fluid; O(N) algorithm
+        # bounded sample: 25 steps of the SAME system (about 12 s on 16 threads)
         t0 = time.perf_counter()
-        cv, threads, cn, cdt = cpu_nve(40, 150, 2)
+        cv, threads, cn, cdt = cpu_nve(nc, 25, 2)
         cpu = {"value": cv, "unit": "atom-steps/s", "cores": threads, "kind": "port",
-               "sample": "150 velocity-Verlet steps of N=%d (fcc nc=40 + Gaussian displacement), C restatement of the "
-                         "reference with OpenMP over cells, %.1f s" % (cn, time.perf_counter() - t0)}
+               "sample": "25 velocity-Verlet steps of the whole system, N=%d (fcc nc=%d + Gaussian displacement), C "
+                         "restatement of the reference with OpenMP over cells (%d threads set explicitly), %.1f s"
+                         % (cn, nc, threads, time.perf_counter() - t0),
+               # the reference's own NumPy path on the same host cores; gfortran is not in the
+               # image, so the Fortran twin (item 3) cannot be built
+               "reference_python": reference_python_rows()}
 
     line = {
         "metric": "LJ atom-steps/sec (rho=0.75, r_cut=2.5)", "value": value, "unit": "atom-steps/s",
@@ -373,12 +477,10 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic: fcc lattice (initialize.py formula), Gaussian velocities seed 20170101 at T=%.1f, "
                 "melted %d steps before timing" % (T_INIT, args.melt),
-        "config": {"workload": "%s: NVE LJ, N=%d (fcc nc=%d), rho=0.75, r_cut=2.5, dt=0.005, link cells sc=%d"
-                               % (wl, n_total, nc, int(np.floor(box / R_CUT))),
-                   "atoms_per_gpu": n_rank, "l2": "state %.0f MB per GPU exceeds the 126 MB L2"
-                   % (n_rank * 24 * 7 / 1e6) if n_rank * 24 * 7 > 126e6 else "state fits in L2 (device-resident loop)",
-                   "temperature": temp, "pot_per_atom": epot, "pairs_per_atom": pairs_per_step / n_total,
-                   "overlap": ovr, "melt_s": t_melt, "parallelism": "slab%d" % world if world > 1 else "single"},
+        "config": workload_config(wl, nc, world),
+        "state": {"temperature": temp, "pot_per_atom": epot, "pairs_per_atom": pairs_per_step / n_total,
+                  "overlap": ovr, "melt_s": t_melt},
+        "parity": parity, "parity_melted": parity_m,
         "e2e": e2e, "gpu_launches": int(l1 - l0), "clocks": clocks, "roofline": roofline,
         "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "other_workloads": other,
         "kernel_ms_per_step": {k: cat[k] / args.steps for k in cat},

@@ -5,8 +5,11 @@ the GPU (csrc/cnf.cu), byte-for-byte what np.savetxt(fmt='%15.10f') writes and b
 np.savetxt / np.loadtxt cost minutes at 16 M atoms (one Python-level format call per row); block-end checkpoints
 (md_nve_lj.py:194-196) would dominate a device-resident run.
 
-Only the fixed layout that write_cnf_atoms produces is accepted by read_cnf_atoms: a file in another notation
-(exponents, other widths, comments) raises - read those with the reference's own reader.
+The GPU parser is the fast path for the fixed layout write_cnf_atoms produces (n*cols fields of 16 bytes).  Any
+other layout the reference's reader accepts - files written by the Fortran programs with `(*(f15.10))` (15-character
+fields, no separator column), CRLF line ends, a trailing blank line, exponent notation, other widths - is read the
+way config_io_module.py:37 reads it, with np.loadtxt on the host: this is text input, not the force path, and a
+cnf.inp from the Fortran `initialize` must still start md_nve_lj.py.
 """
 import ctypes as C
 import os
@@ -56,6 +59,22 @@ def write_cnf_sim(filename, sim, with_v=True):
         body.tofile(f)
 
 
+def _read_generic(filename, with_v):
+    """config_io_module.py:30-48 as written there (np.loadtxt): every layout the reference's reader accepts."""
+    with open(filename, "r") as f:
+        n = int(f.readline())
+        box = float(f.readline())
+    rv = np.loadtxt(filename, skiprows=2, ndmin=2)
+    rows, cols = rv.shape
+    assert rows == n, "{:d}{}{:d}".format(rows, ' rows not equal to ', n)
+    assert cols >= 3, "{:d}{}".format(cols, ' cols less than 3')
+    r = rv[:, 0:3].astype(np.float64)
+    if with_v:
+        assert cols >= 6, "{:d}{}".format(cols, ' cols less than 6')
+        return n, box, r, rv[:, 3:6].astype(np.float64)
+    return n, box, r
+
+
 def read_cnf_atoms(filename, with_v=False):
     """Read in atomic configuration (config_io_module.py:30)."""
     with open(filename, "rb") as f:
@@ -63,18 +82,18 @@ def read_cnf_atoms(filename, with_v=False):
         box = float(f.readline())    # Simulation box length (assumed cubic)
         start = f.tell()
         size = os.fstat(f.fileno()).st_size - start
-        assert n > 0 and size % (n * FIELD) == 0, "{:d}{}{:d}".format(size, ' body bytes are not whole rows of ', n)
-        cols = size // (n * FIELD)
-        rows = n
-        assert rows == n, "{:d}{}{:d}".format(rows, ' rows not equal to ', n)
-        assert cols >= 3, "{:d}{}".format(cols, ' cols less than 3')
-        if with_v:
-            assert cols >= 6, "{:d}{}".format(cols, ' cols less than 6')
-        body = np.fromfile(f, dtype=np.uint8, count=size)
-    r = np.empty((n, 3))
-    v = np.empty((n, 3)) if with_v else None
-    _lib.check(_lib.lib().atlj_cnf_parse(body.ctypes.data, n, int(cols), r.ctypes.data,
-                                         None if v is None else v.ctypes.data))
-    if with_v:
-        return n, box, r, v
-    return n, box, r
+        fixed = n > 0 and size > 0 and size % (n * FIELD) == 0
+        cols = size // (n * FIELD) if fixed else 0
+        body = np.fromfile(f, dtype=np.uint8, count=size) if fixed and cols >= 3 else None
+    if body is not None:
+        assert not with_v or cols >= 6, "{:d}{}".format(cols, ' cols less than 6')
+        r = np.empty((n, 3))
+        v = np.empty((n, 3)) if with_v else None
+        rc = _lib.lib().atlj_cnf_parse(body.ctypes.data, n, int(cols), r.ctypes.data,
+                                       None if v is None else v.ctypes.data)
+        if rc != _lib.ERR_ARG:       # ERR_ARG: right size, but not the fixed '%15.10f ' notation -> generic reader
+            _lib.check(rc)
+            if with_v:
+                return n, box, r, v
+            return n, box, r
+    return _read_generic(filename, with_v)

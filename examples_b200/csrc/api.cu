@@ -227,7 +227,17 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
     }
   }
+  s->forces_valid = true;
   return ATLJ_OK;
+}
+
+// The integrators start with a half kick from s->f (md_nve_lj.py:168 computes the forces before the loop): after an
+// upload without a force call the forces are evaluated here instead of silently integrating with f = 0.
+int sim_ensure_forces(atlj_sim *s, double strain) {
+  if (s->forces_valid || s->mg.on) return ATLJ_OK;  // a slab's first evaluation is its dt = 0 step
+  int rc = sim_ensure_rec(s, 1);
+  if (rc) return rc;
+  return sim_force(s, strain, false, s->rec_dev, false);
 }
 
 // read back and clear the device error flags; maps to the reference's assertion codes
@@ -288,8 +298,8 @@ int atlj_set_device(int device) {
 atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   if (device_ok() != ATLJ_OK) return nullptr;
   if (capacity < 1) capacity = 1;
-  if (capacity > (1ll << 30)) {
-    set_error("capacity too large");
+  if (capacity > 0x7fffffffll / 3 - 4096) {  // kernels index components with 3*n in 32-bit integers
+    set_error("capacity %lld exceeds %lld atoms per GPU", (long long)capacity, 0x7fffffffll / 3 - 4096);
     return nullptr;
   }
   atlj_sim *s = new atlj_sim();
@@ -370,6 +380,7 @@ int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, 
   g.h = (g.nx_own == sc) ? 0 : 1;
   g.nxl = g.nx_own + 2 * g.h;
   s->g = g;
+  s->forces_valid = false;
   // prefilter threshold in cell units with a 1e-4 relative margin (error bound of the fp32 path ~1.5e-6)
   double rc_cell = sqrt(r_cut_box_sq) * sc;
   s->p.rc2_cell = (float)(rc_cell * rc_cell * (1.0 + 1e-4));
@@ -405,6 +416,7 @@ int atlj_sim_upload(atlj_sim *s, const double *r_host, const double *v_host, con
     if (rc) return rc;
   }
   ATLJ_CUDA(cudaMemsetAsync(s->f, 0, b, s->st));
+  s->forces_valid = false;  // the run_* entry points evaluate the forces first when they are not current
   ATLJ_CUDA(cudaStreamSynchronize(s->st));  // the host arrays may be reused by the caller
   return ATLJ_OK;
 }
@@ -435,7 +447,7 @@ int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_hos
 int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host) {
   if (!s || !s->configured || nsteps < 0) return ATLJ_ERR_ARG;
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
-  if (rc) return rc;
+  if (rc || (rc = sim_ensure_forces(s, 0.0))) return rc;
   const long long n3 = 3 * s->n;
   const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first
   if (!with_hessian && s->use_cells && nsteps > 0 && !s->unfused) {
@@ -512,6 +524,7 @@ int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_hos
   }
   int rc;
   s->n = n;
+  s->n_total = n;
   s->cur = 0;
   const size_t b = sizeof(double) * 3 * (size_t)n;
   ATLJ_CUDA(cudaMemcpyAsync(s->r[0], r_host, b, cudaMemcpyHostToDevice, s->st));
@@ -674,6 +687,7 @@ int atlj_force_1(const double *ri_host, const double *r_host, int64_t nj, double
   ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
   if ((rc = ensure_partials(s, (int)((nj + 127) / 128) + 1))) return rc;
   const int nb = launch_force_1(s->st, ri_host, s->r[0], (int)nj, s->p, s->f, s->partials);
+  if (nb < 0) return nb;
   if ((rc = launch_finalize(s->st, s->partials, nb, ATLJ_MODEL_LJ, false, s->rec_dev))) return rc;
   ATLJ_CUDA(cudaMemcpyAsync(f_partial_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
   double rec[ATLJ_NREC];

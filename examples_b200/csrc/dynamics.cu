@@ -277,6 +277,7 @@ enum { SC_NHC = 0, SC_SUMV = 32, SC_SUMF = 36, SC_COEF = 40 };
 static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const double *noise_dev, uint64_t seed,
                      int nsteps, double *rec_host) {
   int rc;
+  if ((rc = sim_ensure_forces(s, 0.0))) return rc;
   const int n = (int)s->n;
   const long long n3 = 3 * s->n;
   const double t = dt / 2;  // bd_nvt_lj.py:223
@@ -328,7 +329,7 @@ int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m
                      const double *q, int nsteps, double *rec_host) {
   if (!s || !s->configured || nsteps < 0 || m < 1 || m > 8 || !eta || !p_eta || !q) return ATLJ_ERR_ARG;
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
-  if (rc) return rc;
+  if (rc || (rc = sim_ensure_forces(s, 0.0))) return rc;
   const long long n3 = 3 * s->n;
   double h[32];
   memset(h, 0, sizeof(h));
@@ -377,7 +378,7 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
     return ATLJ_ERR_ARG;
   }
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
-  if (rc) return rc;
+  if (rc || (rc = sim_ensure_forces(s, *strain))) return rc;
   const int n = (int)s->n;
   const long long n3 = 3 * s->n;
   const int nb = atom_blocks(n) < SL_CTAS ? atom_blocks(n) : SL_CTAS;

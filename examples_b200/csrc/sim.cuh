@@ -27,6 +27,7 @@ struct atlj_sim {
   int64_t n_total = 0;       // atoms of the whole system (all ranks); indexes injected noise by global id
   long long step_count = 0;  // steps taken so far (counter of the device RNG)
   bool configured = false;
+  bool forces_valid = false;  // s->f belongs to the current positions (cleared by upload / configure, set by sim_force)
   bool use_cells = false;  // sc >= 4: link-cell route; otherwise all pairs
   atlj::Geom g{};
   atlj::Phys p{};
@@ -77,6 +78,7 @@ struct Timer {
 // after_sort (may be null): recorded on the sim's stream when the sorted r, v, id of this evaluation are final
 int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bool check_index_allpairs,
               cudaEvent_t after_sort = nullptr);
+int sim_ensure_forces(atlj_sim *s, double strain);  // evaluates s->f when it is not current (after an upload)
 int sim_check_flags(atlj_sim *s);
 double sim_per_cell(const atlj_sim *s);
 bool sim_tile2(const atlj_sim *s);

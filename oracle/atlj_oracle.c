@@ -57,6 +57,15 @@ int ato_num_threads(void) {
 #endif
 }
 
+/* bench.py sets the team size explicitly: a launcher (torch.distributed.run) exports OMP_NUM_THREADS=1 */
+void ato_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static inline int imod(int a, int m) {
   int r = a % m;
   return r < 0 ? r + m : r;

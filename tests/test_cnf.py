@@ -99,8 +99,53 @@ def test_loud_failures(tmp_path):
     raw = bytearray(open(p, "rb").read())
     raw[32 + 16 * 4 + 9] = ord("e")       # exponent notation inside a field
     open(p, "wb").write(bytes(raw))
-    with pytest.raises(_lib.AtljError, match="fixed 16-byte"):
-        read_cnf_atoms(p)
+    # right size but not the fixed notation: the GPU parser declines, the reference's own reader semantics apply
+    got = read_cnf_atoms(p)[2]
+    assert np.array_equal(got, np.loadtxt(p, skiprows=2)[:, :3])
+
+
+def _fortran_style(path, n, box, r, v=None, eol="\n", trailing_blank=False):
+    """A cnf file as the Fortran programs write it (config_io_module.f90: `(*(f15.10))`, no separator column)."""
+    with open(path, "w", newline="") as fh:
+        fh.write("%15d%s%15.8f%s" % (n, eol, box, eol))
+        rows = r if v is None else np.concatenate((r, v), axis=1)
+        for row in rows:
+            fh.write("".join("%15.10f" % x for x in row) + eol)
+        if trailing_blank:
+            fh.write(eol)
+
+
+@pytest.mark.parametrize("with_v", [False, True])
+@pytest.mark.parametrize("eol,blank", [("\n", False), ("\r\n", False), ("\n", True)])
+def test_reads_every_layout_the_reference_reader_accepts(tmp_path, with_v, eol, blank):
+    """a cnf.inp from the Fortran `initialize` (15-character fields), CRLF line ends or a trailing blank
+    line must still be readable, with the values np.loadtxt (config_io_module.py:37) returns.  Host text path: no GPU."""
+    from examples_b200.config_io_module import read_cnf_atoms
+    rng = np.random.default_rng(5)
+    n, box = 37, 7.5
+    r, v = rng.uniform(-3.7, 3.7, (n, 3)), rng.normal(0, 1, (n, 3))
+    p = str(tmp_path / "cnf.f90")
+    _fortran_style(p, n, box, r, v if with_v else None, eol, blank)
+    out = read_cnf_atoms(p, with_v=with_v)
+    want = np.loadtxt(p, skiprows=2)
+    assert out[0] == n and out[1] == box
+    assert np.array_equal(out[2], want[:, :3])
+    if with_v:
+        assert np.array_equal(out[3], want[:, 3:6])
+    else:
+        with pytest.raises(AssertionError, match="cols less than 6"):
+            read_cnf_atoms(p, with_v=True)
+
+
+def test_reads_exponent_notation(tmp_path):
+    from examples_b200.config_io_module import read_cnf_atoms
+    p = str(tmp_path / "cnf.exp")
+    r = np.array([[1.5e-3, -2.25, 3.0], [0.0, 1e1, -1e-7]])
+    with open(p, "w") as fh:
+        fh.write("2\n3.0\n")
+        np.savetxt(fh, r, fmt="%.8e")
+    n, box, got = read_cnf_atoms(p)
+    assert n == 2 and box == 3.0 and np.array_equal(got, np.loadtxt(p, skiprows=2))
 
 
 @pytest.mark.gpu
