@@ -71,7 +71,9 @@ def run_case(name, module_dirs, timeout=900):
                 with open(os.path.join(ad, fn), "w") as fh:
                     fh.write(text)
             path.insert(0, ad)
-        env = dict(os.environ, PYTHONPATH=os.pathsep.join(path))
+        # PYTHONSAFEPATH (Python >= 3.11, same as `python -P`): do not put the SCRIPT's directory in front of sys.path,
+        # otherwise the reference modules next to the script would always win over PYTHONPATH
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join(path), PYTHONSAFEPATH="1")
         p = subprocess.run([sys.executable, os.path.join(module_dirs[-1], script)], input=params, capture_output=True,
                            text=True, cwd=tmp, env=env, timeout=timeout)
         if p.returncode != 0:
