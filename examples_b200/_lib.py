@@ -45,6 +45,8 @@ def lib():
     L.atlj_device_count.restype = C.c_int
     L.atlj_set_device.argtypes = [C.c_int]
     L.atlj_kernel_launches.restype = C.c_int64
+    L.atlj_set_multi_max.restype = C.c_int64
+    L.atlj_set_multi_max.argtypes = [C.c_int64]
     L.atlj_force_lj.argtypes = [_dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                 _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.atlj_force_le.argtypes = [_dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -127,6 +129,11 @@ def device_count():
     return lib().atlj_device_count()
 
 
+def set_multi_max(natoms):
+    """Systems of at most `natoms` atoms use the eight-lanes-per-atom pair kernel (0: never).  -> previous value."""
+    return int(lib().atlj_set_multi_max(int(natoms)))
+
+
 def kernel_launches():
     return int(lib().atlj_kernel_launches())
 
@@ -135,6 +142,69 @@ def measure_fp64_peak():
     v = C.c_double(0.0)
     check(lib().atlj_measure_fp64_peak(C.byref(v)))
     return v.value
+
+
+class _PinnedBlock:
+    """One page-locked block handed out as the memory of a NumPy array (buffer protocol, PEP 688).  NumPy keeps a
+    reference to the exporter for as long as the array or any view of it lives; when the last one is gone the block
+    goes back to its pool."""
+
+    def __init__(self, pool, ptr, nbytes):
+        self.pool, self.ptr, self.nbytes = pool, ptr, nbytes
+        self._c = (C.c_char * max(nbytes, 1)).from_address(ptr)
+
+    def __buffer__(self, flags):
+        return memoryview(self._c)
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.ptr, self.nbytes)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class PinnedPool:
+    """Result arrays in page-locked host memory: force() returns `f` as an ordinary ndarray whose memory the GPU writes
+    by DMA (no staging copy, no page faults of a fresh np.empty).  A block is reused once the caller has dropped the
+    array (`total, f = force(...)` in the drivers' loops rebinds f every step, md_nve_lj.py:187)."""
+
+    KEEP = 3          # free blocks kept per size
+    MIN_BYTES = 1 << 20   # smaller results are plain NumPy arrays
+
+    def __init__(self, alloc=None, free=None):
+        self._alloc = alloc or (lambda n: lib().atlj_host_alloc(n))
+        self._free = free or (lambda p: lib().atlj_host_free(p))
+        self._idle = {}
+
+    def empty(self, shape, dtype=np.float64):
+        count = int(np.prod(shape))
+        nbytes = count * np.dtype(dtype).itemsize
+        if nbytes < self.MIN_BYTES:
+            return np.empty(shape, dtype=dtype)
+        idle = self._idle.get(nbytes)
+        ptr = idle.pop() if idle else self._alloc(nbytes)
+        if not ptr:
+            return np.empty(shape, dtype=dtype)      # page-locked memory exhausted: pageable result, staged copy
+        blk = _PinnedBlock(self, ptr, nbytes)
+        return np.frombuffer(blk, dtype=dtype, count=count).reshape(shape)
+
+    def _give_back(self, ptr, nbytes):
+        idle = self._idle.setdefault(nbytes, [])
+        if len(idle) < self.KEEP:
+            idle.append(ptr)
+        else:
+            self._free(ptr)
+
+
+_result_pool = None
+
+
+def result_empty(shape, dtype=np.float64):
+    """An uninitialised result array for a drop-in call (page-locked when large)."""
+    global _result_pool
+    if _result_pool is None:
+        _result_pool = PinnedPool()
+    return _result_pool.empty(shape, dtype)
 
 
 class PinnedArray:

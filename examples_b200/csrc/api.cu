@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostpipe.cuh"
 #include "integrate.cuh"
 #include "sim.cuh"
 
@@ -140,6 +141,21 @@ static bool sim_direct(const atlj_sim *s) {
   return s->use_cells && s->pair_kernel == 0 && !s->mg.on && cells > 0 && s->n < 3 * cells;
 }
 
+// small systems (the tiled kernels cannot fill the GPU): eight lanes per atom, exact arithmetic.  ATLJ_MULTI_MAX moves
+// the threshold for A/B runs (0 switches the kernel off).
+static int64_t g_multi_max = -1;  // atoms; -1: not initialised yet
+static int64_t multi_max() {
+  if (g_multi_max < 0) {
+    const char *mm = getenv("ATLJ_MULTI_MAX");
+    g_multi_max = mm ? atoll(mm) : 16384;
+    if (g_multi_max < 0) g_multi_max = 0;
+  }
+  return g_multi_max;
+}
+static bool sim_multi(const atlj_sim *s) {
+  return s->pair_kernel == 0 && !s->mg.on && s->n <= multi_max();
+}
+
 // ---- one force evaluation on the current positions ----------------------------------------------------------------------
 // Cell route: wrap+assign -> scan -> scatter/sort/gather (atoms re-ordered into cell order, buffers swapped) -> pair
 // kernel -> finalize.  All-pairs route (sc < 4): pair_all on the current order.
@@ -178,15 +194,18 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
     a.p = p;
     Timer::begin(s, 0);
     int nb;
-    const bool direct = sim_direct(s);
-    const bool tile2 = !direct && sim_tile2(s);
+    const bool multi = sim_multi(s);
+    const bool direct = !multi && sim_direct(s);
+    const bool tile2 = !multi && !direct && sim_tile2(s);
     // hessian after the tile2 force kernel: that kernel keeps its mask words, the hessian kernel walks them
     const bool hess2 = with_hessian && tile2;
     if (hess2) {
       if ((rc = ensure_masks(s))) return rc;
       a.masks = s->masks;
     }
-    if (direct)
+    if (multi)
+      nb = launch_pair_multi(s->st, a, false, n, true);
+    else if (direct)
       nb = launch_pair_direct(s->st, a, false, n);
     else if (tile2)
       nb = launch_pair_tile2(s->st, a, s->cb.err + 2, hess2 ? 1 : 0);
@@ -203,6 +222,8 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       Timer::begin(s, 3);
       if (hess2)
         nb = launch_pair_tile2(s->st, a, s->cb.err + 2, 2);
+      else if (multi)
+        nb = launch_pair_multi(s->st, a, true, n, true);
       else
         nb = direct ? launch_pair_direct(s->st, a, true, n) : launch_pair_tile(s->st, a, true);
       Timer::end(s);
@@ -218,12 +239,25 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       if ((rc = launch_cell_assign(s->st, g, s->r[s->cur], nullptr, n, false, strain, s->cb, nullptr))) return rc;
     }
     int nb = 0;
+    const bool multi = sim_multi(s);
+    PairArgs a;
+    a.r = s->r[s->cur], a.fin = nullptr, a.cell_start = nullptr, a.cell_count = nullptr, a.f = s->f;
+    a.partials = s->partials, a.tile_tab = nullptr, a.masks = nullptr, a.natoms = n, a.per_cell = 0.0, a.g = s->g, a.p = p;
     Timer::begin(s, 0);
-    if ((rc = launch_pair_all(s->st, s->r[s->cur], nullptr, n, p, s->f, s->partials, false, &nb))) return rc;
+    if (multi) {
+      if ((nb = launch_pair_multi(s->st, a, false, n, false)) < 0) return nb;
+    } else if ((rc = launch_pair_all(s->st, s->r[s->cur], nullptr, n, p, s->f, s->partials, false, &nb))) {
+      return rc;
+    }
     Timer::end(s);
     if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev))) return rc;
     if (with_hessian) {
-      if ((rc = launch_pair_all(s->st, s->r[s->cur], s->f, n, p, nullptr, s->partials, true, &nb))) return rc;
+      a.fin = s->f, a.f = nullptr;
+      if (multi) {
+        if ((nb = launch_pair_multi(s->st, a, true, n, false)) < 0) return nb;
+      } else if ((rc = launch_pair_all(s->st, s->r[s->cur], s->f, n, p, nullptr, s->partials, true, &nb))) {
+        return rc;
+      }
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
     }
   }
@@ -279,6 +313,12 @@ int atlj_version(void) { return 100; }
 const char *atlj_last_error(void) { return g_err; }
 int64_t atlj_kernel_launches(void) { return g_launches; }
 
+int64_t atlj_set_multi_max(int64_t natoms) {
+  const int64_t old = multi_max();
+  g_multi_max = natoms < 0 ? 0 : natoms;
+  return old;
+}
+
 int atlj_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -309,6 +349,8 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   s->pair_kernel = (op && strcmp(op, "tile1") == 0) ? 1 : 0;
   const char *uf = getenv("ATLJ_UNFUSED");  // A/B runs: the unfused 12-launch velocity-Verlet step
   s->unfused = uf && uf[0] == '1';
+  const char *ng = getenv("ATLJ_NO_GRAPH");  // A/B runs: every step launched kernel by kernel
+  s->no_graph = ng && ng[0] == '1';
   s->cap = capacity;
   size_t c = (size_t)capacity;
   bool ok = true;
@@ -322,6 +364,7 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
        dev_alloc(&s->scal, 64) == ATLJ_OK && dev_alloc(&s->vf_partials, 4 * 4096) == ATLJ_OK;
   if (ok) ok = ensure_partials(s, pair_grid_blocks()) == ATLJ_OK;
   if (ok) ok = cudaMemsetAsync(s->cb.err, 0, 8 * sizeof(int), s->st) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(s->cb.block_sums, 0, 8192 * sizeof(int), s->st) == cudaSuccess;  // scan tile states
   if (ok) ok = cudaMemsetAsync(s->scal, 0, 64 * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(s->f, 0, 3 * c * sizeof(double), s->st) == cudaSuccess;
   if (ok) ok = sim_ensure_rec(s, 64) == ATLJ_OK;
@@ -342,6 +385,8 @@ void atlj_sim_destroy(atlj_sim *s) {
   cudaFree(s->scal), cudaFree(s->rec_dev), cudaFree(s->noise_dev), cudaFree(s->vf_partials), cudaFree(s->tile_tab), cudaFree(s->masks);
   if (s->sw0) cudaEventDestroy(s->sw0), cudaEventDestroy(s->sw1);
   if (s->st_copy) cudaStreamDestroy(s->st_copy), cudaEventDestroy(s->ev_sorted), cudaEventDestroy(s->ev_copied);
+  if (s->nve_graph) cudaGraphExecDestroy(s->nve_graph);
+  if (s->st_cap) cudaStreamDestroy(s->st_cap), cudaStreamDestroy(s->st_side), cudaEventDestroy(s->ev_fork), cudaEventDestroy(s->ev_join);
   for (auto e : s->ev_free) cudaEventDestroy(e);
   for (auto &t : s->ev_done) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
   for (auto &t : s->ev_open) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
@@ -389,6 +434,10 @@ int atlj_sim_configure(atlj_sim *s, int model, double box, double r_cut_box_sq, 
   if (pair_tile_grid(g) > rows) rows = pair_tile_grid(g);
   if (pair_tile2_items(g) > rows) rows = pair_tile2_items(g);
   if (pair_direct_blocks((int)s->cap) > rows) rows = pair_direct_blocks((int)s->cap);
+  {
+    const int64_t m = s->cap < multi_max() ? s->cap : multi_max();
+    if (m > 0 && pair_multi_blocks((int)m) > rows) rows = pair_multi_blocks((int)m);
+  }
   int rc = ensure_partials(s, rows);
   if (rc) return rc;
   if ((rc = ensure_tile_tab(s, pair_tile2_tab_ints(g)))) return rc;
@@ -444,6 +493,170 @@ int atlj_sim_force(atlj_sim *s, double strain, int with_hessian, double *rec_hos
   return sim_copy_rec(s, rec_host, 1);
 }
 
+}  // extern "C" (internal helpers of atlj_sim_run_nve follow)
+
+// ---- the fused velocity-Verlet loop ------------------------------------------------------------------------------------
+// Between two pair kernels ONE pass does the trailing half kick of the finished step (with its sums), the leading half
+// kick, the drift, the wrap and the cell assignment, and finishes the record of the step that just ended (two-level
+// fixed-order reduction of the pair kernel's per-item rows and of sum v^2, sum f^2 inside that kernel).  Per step:
+// kdk_assign -> scan -> scatter -> sort+gather (which leaves cell_count zeroed for the next step) || item table -> pair
+// kernel: 6 launches, 5 on the critical path, none of whose arguments depends on the step number when `replay` is set
+// (the record pointer follows a device counter), so TWO steps (the double-buffer parity returns) are captured once as a
+// CUDA graph and replayed.  Results are identical to the unfused sequence up to the order of the final sums.
+//   rec: replay ? base of the records : record of the step that just ended (null at the first step)
+static int nve_fused_step(atlj_sim *s, cudaStream_t st, cudaStream_t side, double dt, bool first_kick, double *rec,
+                          int nb_prev, bool replay, int *nb_out) {
+  int rc;
+  const int n = (int)s->n;
+  Phys p = s->p;
+  p.strain = 0.0, p.shift = 0;
+  const bool multi = sim_multi(s);
+  const bool direct = !multi && sim_direct(s);
+  const bool tile2 = !multi && !direct && sim_tile2(s);
+  const int cur = s->cur, alt = 1 - cur;
+  KdkLoop loop;
+  loop.step_ctr = replay ? s->cb.err + 7 : nullptr;
+  loop.tab0 = tile2 ? s->tile_tab : nullptr;
+  loop.counts_zeroed = true;
+  Timer::begin(s, 2);
+  const int nvf = launch_kdk_assign(st, s->g, n, s->r[cur], s->v[cur], s->f, 0.5 * dt, dt, p.box, first_kick, s->cb,
+                                    s->vf_partials, rec, s->partials, nb_prev, p.model, nullptr,
+                                    tile2 ? s->cb.err + 6 : nullptr, &loop);
+  if (nvf < 0) return nvf;
+  Timer::end(s);
+  Timer::begin(s, 1);
+  if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
+  PairArgs a;
+  a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
+  a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
+  a.per_cell = sim_per_cell(s);
+  a.masks = nullptr;
+  const bool fork = tile2 && side != nullptr;
+  if (fork) {  // the item table needs cell_start only: beside the sort + gather
+    ATLJ_CUDA(cudaEventRecord(s->ev_fork, st));
+    ATLJ_CUDA(cudaStreamWaitEvent(side, s->ev_fork, 0));
+    if ((rc = launch_pair_tile2(side, a, s->cb.err + 2, 0, 1, true)) < 0) return rc;
+    ATLJ_CUDA(cudaEventRecord(s->ev_join, side));
+  }
+  if ((rc = launch_cell_sort_gather(st, s->g, s->cb, n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
+                                    s->id[alt], nullptr, 0, true)))
+    return rc;
+  Timer::end(s);
+  s->cur = alt;
+  if (fork) ATLJ_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  Timer::begin(s, 0);
+  int nb;
+  if (multi)
+    nb = launch_pair_multi(st, a, false, n, true);
+  else if (direct)
+    nb = launch_pair_direct(st, a, false, n);
+  else if (tile2)
+    nb = launch_pair_tile2(st, a, s->cb.err + 2, 0, fork ? 2 : 0, true);
+  else
+    nb = launch_pair_tile(st, a, false);
+  Timer::end(s);
+  if (nb < 0) return nb;
+  *nb_out = nb;
+  return ATLJ_OK;
+}
+
+// everything the captured launches bake in
+struct NveGraphKey {
+  int64_t n, n_total;
+  int kind, cur, sc, model, nb_prev, multi;
+  double dt, box, box_sq, r_cut_box_sq, pot_cut;
+  void *r0, *r1, *f, *rec, *partials, *tab, *cell_start;
+};
+
+// kind: 0 = two steps of the fused link-cell loop, 1 = one step of the all-pairs loop, 2 = the same with the hessian
+template <typename Body>
+static int nve_graph_prepare(atlj_sim *s, int kind, double dt, int nb_prev, Body body) {
+  NveGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.n = s->n, key.n_total = s->n_total, key.kind = kind, key.cur = s->cur, key.sc = s->g.sc, key.model = s->p.model;
+  key.nb_prev = nb_prev, key.multi = sim_multi(s) ? 1 : 0;
+  key.dt = dt, key.box = s->p.box, key.box_sq = s->p.box_sq, key.r_cut_box_sq = s->p.r_cut_box_sq, key.pot_cut = s->p.pot_cut;
+  key.r0 = s->r[0], key.r1 = s->r[1], key.f = s->f, key.rec = s->rec_dev, key.partials = s->partials, key.tab = s->tile_tab;
+  key.cell_start = s->cb.cell_start;
+  static_assert(sizeof(NveGraphKey) <= sizeof(s->nve_graph_key), "key storage");
+  if (s->nve_graph && memcmp(&key, s->nve_graph_key, sizeof(key)) == 0) return ATLJ_OK;
+  if (s->nve_graph) cudaGraphExecDestroy(s->nve_graph), s->nve_graph = nullptr;
+  if (!s->st_cap) {
+    ATLJ_CUDA(cudaStreamCreateWithFlags(&s->st_cap, cudaStreamNonBlocking));
+    ATLJ_CUDA(cudaStreamCreateWithFlags(&s->st_side, cudaStreamNonBlocking));
+    ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  }
+  const int64_t l0 = g_launches;
+  const int cur0 = s->cur;
+  ATLJ_CUDA(cudaStreamBeginCapture(s->st_cap, cudaStreamCaptureModeThreadLocal));
+  int rc = body(s->st_cap, s->st_side);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s->st_cap, &graph);
+  s->nve_graph_launches = (int)(g_launches - l0);
+  g_launches = l0;  // captured, not launched
+  if (rc == ATLJ_OK && (e != cudaSuccess || s->cur != cur0)) {
+    set_error("CUDA graph capture of the NVE step failed: %s", cudaGetErrorString(e));
+    rc = ATLJ_ERR_CUDA;
+  }
+  s->cur = cur0;
+  if (rc == ATLJ_OK) {
+    e = cudaGraphInstantiate(&s->nve_graph, graph, 0);
+    if (e != cudaSuccess) {
+      set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      s->nve_graph = nullptr;
+      rc = ATLJ_ERR_CUDA;
+    }
+  }
+  if (graph) cudaGraphDestroy(graph);
+  if (rc == ATLJ_OK) memcpy(s->nve_graph_key, &key, sizeof(key));
+  else cudaGetLastError();
+  return rc;
+}
+
+// one velocity-Verlet step of the all-pairs route (sc < 4: md_nve_lj.py:178-192 with md_lj_module.force, and the
+// hessian of calc_variables, md_nve_lj.py:46): kick + drift + wrap -> pair kernel -> totals [-> hessian -> its sum] ->
+// kick + sums.  ctr (replayed launches): rec is the base of the records and the row follows the device counter.
+static int nve_allpairs_step(atlj_sim *s, cudaStream_t st, double dt, bool with_hessian, double *rec, int *ctr) {
+  int rc, nb = 0;
+  const int n = (int)s->n;
+  const long long n3 = 3 * s->n;
+  Phys p = s->p;
+  p.strain = 0.0, p.shift = 0;
+  Timer::begin(s, 2);
+  if ((rc = launch_kick_drift(st, n3, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, p.box, nullptr))) return rc;
+  Timer::end(s);
+  const bool multi = sim_multi(s);
+  PairArgs a;
+  a.r = s->r[s->cur], a.fin = nullptr, a.cell_start = nullptr, a.cell_count = nullptr, a.f = s->f;
+  a.partials = s->partials, a.tile_tab = nullptr, a.masks = nullptr, a.natoms = n, a.per_cell = 0.0, a.g = s->g, a.p = p;
+  Timer::begin(s, 0);
+  if (multi) {
+    if ((nb = launch_pair_multi(st, a, false, n, false)) < 0) return nb;
+  } else if ((rc = launch_pair_all(st, s->r[s->cur], nullptr, n, p, s->f, s->partials, false, &nb))) {
+    return rc;
+  }
+  Timer::end(s);
+  if ((rc = launch_finalize(st, s->partials, nb, p.model, false, rec, nullptr, nullptr, 0, nullptr, ctr))) return rc;
+  if (with_hessian) {
+    a.fin = s->f, a.f = nullptr;
+    Timer::begin(s, 3);
+    if (multi) {
+      if ((nb = launch_pair_multi(st, a, true, n, false)) < 0) return nb;
+    } else if ((rc = launch_pair_all(st, s->r[s->cur], s->f, n, p, nullptr, s->partials, true, &nb))) {
+      return rc;
+    }
+    Timer::end(s);
+    if ((rc = launch_finalize(st, s->partials, nb, p.model, true, rec, nullptr, nullptr, 0, nullptr, ctr))) return rc;
+  }
+  Timer::begin(s, 2);
+  rc = launch_kick_sums(st, n3, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->cb.err + 4, nullptr, ctr);
+  Timer::end(s);
+  return rc;
+}
+
+extern "C" {
+
 int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, double *rec_host) {
   if (!s || !s->configured || nsteps < 0) return ATLJ_ERR_ARG;
   int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
@@ -451,53 +664,62 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
   const long long n3 = 3 * s->n;
   const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first
   if (!with_hessian && s->use_cells && nsteps > 0 && !s->unfused) {
-    // Fused loop: between two pair kernels ONE pass does the trailing half kick of the finished step (with its sums),
-    // the leading half kick, the drift, the wrap and the cell assignment, and finishes the record of the step that
-    // just ended (two-level fixed-order reduction of the pair kernel's per-item rows and of sum v^2, sum f^2 inside
-    // that kernel).  7 launches per step instead of 12; results identical to the unfused sequence below up to the
-    // order of the final sums.
     const int n = (int)s->n;
-    Phys p = s->p;
-    p.strain = 0.0, p.shift = 0;
-    int nb_prev = 0;
-    double *rec_prev = nullptr;
-    const bool direct = sim_direct(s);
-    const bool tile2 = !direct && sim_tile2(s);
-    for (int k = 0; k < nsteps; k++) {
-      double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
-      ATLJ_CUDA(cudaMemsetAsync(rec, 0, sizeof(double) * ATLJ_NREC, s->st));
-      const int cur = s->cur, alt = 1 - cur;
-      Timer::begin(s, 2);
-      const int nvf = launch_kdk_assign(s->st, s->g, n, s->r[cur], s->v[cur], s->f, half_dt, dt, p.box, k > 0, s->cb,
-                                        s->vf_partials, rec_prev, s->partials, nb_prev, p.model, nullptr,
-                                        tile2 ? s->cb.err + 6 : nullptr);
-      if (nvf < 0) return nvf;
-      Timer::end(s);
-      Timer::begin(s, 1);
-      if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
-      if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt],
-                                        s->v[alt], s->id[alt])))
-        return rc;
-      Timer::end(s);
-      s->cur = alt;
-      PairArgs a;
-      a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
-      a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;
-      a.per_cell = sim_per_cell(s);
-      a.masks = nullptr;
-      Timer::begin(s, 0);
-      nb_prev = direct ? launch_pair_direct(s->st, a, false, n)
-                       : (tile2 ? launch_pair_tile2(s->st, a, s->cb.err + 2) : launch_pair_tile(s->st, a, false));
-      Timer::end(s);
-      if (nb_prev < 0) return nb_prev;
-      rec_prev = rec;
+    const bool tile2 = !sim_multi(s) && !sim_direct(s) && sim_tile2(s);
+    ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)nsteps, s->st));
+    ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)s->g.ncell(), s->st));
+    ATLJ_CUDA(cudaMemsetAsync(s->cb.err + 7, 0, sizeof(int), s->st));  // step counter of the replayed launches
+    int nb_prev = 0, k = 0;
+    // step 0 (no finished step to close), launched directly; it also warms the kernels' attributes up
+    if ((rc = nve_fused_step(s, s->st, nullptr, dt, false, nullptr, 0, false, &nb_prev))) return rc;
+    k = 1;
+    // pairs of steps as one replayed graph (not while the per-kernel event timing is on)
+    auto two_steps = [&](cudaStream_t cap, cudaStream_t side) -> int {
+      int rc2 = ATLJ_OK, nb = nb_prev;
+      for (int j = 0; j < 2 && rc2 == ATLJ_OK; j++) rc2 = nve_fused_step(s, cap, side, dt, true, s->rec_dev, nb, true, &nb);
+      return rc2 == ATLJ_OK && nb != nb_prev ? ATLJ_ERR_ARG : rc2;
+    };
+    if (!s->timing && !s->no_graph && nsteps - k >= 2 && nve_graph_prepare(s, 0, dt, nb_prev, two_steps) == ATLJ_OK) {
+      for (; nsteps - k >= 2; k += 2) {
+        ATLJ_CUDA(cudaGraphLaunch(s->nve_graph, s->st));
+        g_launches += s->nve_graph_launches;
+      }
     }
+    for (; k < nsteps; k++)
+      if ((rc = nve_fused_step(s, s->st, nullptr, dt, true, s->rec_dev + (size_t)(k - 1) * ATLJ_NREC, nb_prev, false,
+                               &nb_prev)))
+        return rc;
+    double *rec_last = s->rec_dev + (size_t)(nsteps - 1) * ATLJ_NREC;
     Timer::begin(s, 2);
-    if ((rc = launch_finalize(s->st, s->partials, nb_prev, p.model, false, rec_prev, s->cb.err + 2, nullptr, 0,
+    if ((rc = launch_finalize(s->st, s->partials, nb_prev, s->p.model, false, rec_last, s->cb.err + 2, nullptr, 0,
                               tile2 ? s->cb.err + 6 : nullptr)))
       return rc;
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_prev + 4, s->cb.err + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec_last + 4, s->cb.err + 4))) return rc;
     Timer::end(s);
+    (void)n;
+    s->step_count += nsteps;
+    return sim_copy_rec(s, rec_host, nsteps);
+  }
+  if (!s->use_cells && nsteps > 0 && !s->unfused) {
+    // all-pairs route (the reference's N = 256 case): launch-latency bound, so one step is captured and replayed
+    ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)nsteps, s->st));
+    ATLJ_CUDA(cudaMemsetAsync(s->cb.err + 7, 0, sizeof(int), s->st));
+    int *ctr = s->cb.err + 7;
+    int k = 0;
+    if ((rc = nve_allpairs_step(s, s->st, dt, with_hessian != 0, s->rec_dev, ctr))) return rc;  // warms the kernels up
+    k = 1;
+    auto one_step = [&](cudaStream_t cap, cudaStream_t) -> int {
+      return nve_allpairs_step(s, cap, dt, with_hessian != 0, s->rec_dev, ctr);
+    };
+    if (!s->timing && !s->no_graph && nsteps - k >= 2 &&
+        nve_graph_prepare(s, with_hessian ? 2 : 1, dt, 0, one_step) == ATLJ_OK) {
+      for (; k < nsteps; k++) {
+        ATLJ_CUDA(cudaGraphLaunch(s->nve_graph, s->st));
+        g_launches += s->nve_graph_launches;
+      }
+    }
+    for (; k < nsteps; k++)
+      if ((rc = nve_allpairs_step(s, s->st, dt, with_hessian != 0, s->rec_dev, ctr))) return rc;
     s->step_count += nsteps;
     return sim_copy_rec(s, rec_host, nsteps);
   }
@@ -646,16 +868,23 @@ static int force_host(int model, const double *r_host, int64_t n, double box, do
   atlj_sim *s = host_sim(n);
   if (!s) return ATLJ_ERR_CUDA;
   if ((rc = atlj_sim_configure(s, model, box, rcbsq, bsq, pot_cut, sc > 0 ? sc : 1, 0, sc > 0 ? sc : 1))) return rc;
-  if ((rc = atlj_sim_upload(s, r_host, nullptr, nullptr, n))) return rc;
+  // positions in (chunked through the page-locked ring when the caller's array is pageable; velocities are not part of
+  // this call: the slot is zeroed because the cell sort carries it along)
+  const size_t b = sizeof(double) * 3 * (size_t)n;
+  s->n = n, s->n_total = n, s->cur = 0, s->forces_valid = false;
+  ATLJ_CUDA(cudaMemsetAsync(s->v[0], 0, b, s->st));
+  if ((rc = launch_iota(s->st, (int)n, s->id[0]))) return rc;
+  if ((rc = hostpipe_h2d(s->st, s->r[0], r_host, b))) return rc;
   if ((rc = sim_force(s, strain, false, s->rec_dev, check_index != 0))) return rc;
   double *src = s->f;
   if (s->use_cells) {  // back to the caller's atom order
     src = s->r[1 - s->cur];
     if ((rc = launch_unsort(s->st, (int)n, s->id[s->cur], s->f, src))) return rc;
   }
-  ATLJ_CUDA(cudaMemcpyAsync(f_host, src, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s->st));
   double rec[ATLJ_NREC];
-  if ((rc = sim_copy_rec(s, rec, 1))) return rc;
+  ATLJ_CUDA(cudaMemcpyAsync(rec, s->rec_dev, sizeof(rec), cudaMemcpyDeviceToHost, s->st));
+  if ((rc = hostpipe_d2h(s->st, f_host, src, b))) return rc;  // synchronises
+  if ((rc = sim_check_flags(s))) return rc;
   for (int k = 0; k < 4; k++) totals[k] = rec[k];
   *ovr = rec[7] != 0.0;
   if (npair) *npair = (int64_t)rec[8];
@@ -747,13 +976,21 @@ int atlj_hessian_lj(const double *r_host, const double *f_host, int64_t n, doubl
     a.per_cell = sim_per_cell(s);
     a.g = s->g;
     a.p = p;
-    nb = sim_direct(s) ? launch_pair_direct(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true);
+    nb = sim_multi(s) ? launch_pair_multi(s->st, a, true, (int)n, true)
+                      : (sim_direct(s) ? launch_pair_direct(s->st, a, true, (int)n) : launch_pair_tile(s->st, a, true));
     if (nb < 0) return nb;
   } else {
     if (check_index)
       if ((rc = launch_cell_assign(s->st, s->g, s->r[s->cur], nullptr, (int)n, false, 0.0, s->cb, nullptr))) return rc;
-    if ((rc = launch_pair_all(s->st, s->r[s->cur], s->v[s->cur], (int)n, p, nullptr, s->partials, true, &nb)))
+    if (sim_multi(s)) {
+      PairArgs a;
+      a.r = s->r[s->cur], a.fin = s->v[s->cur], a.cell_start = nullptr, a.cell_count = nullptr, a.f = nullptr;
+      a.partials = s->partials, a.tile_tab = nullptr, a.masks = nullptr, a.natoms = (int)n, a.per_cell = 0.0;
+      a.g = s->g, a.p = p;
+      if ((nb = launch_pair_multi(s->st, a, true, (int)n, false)) < 0) return nb;
+    } else if ((rc = launch_pair_all(s->st, s->r[s->cur], s->v[s->cur], (int)n, p, nullptr, s->partials, true, &nb))) {
       return rc;
+    }
   }
   if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, s->rec_dev))) return rc;
   double rec[ATLJ_NREC];

@@ -6,7 +6,7 @@
 // algorithm is not the reference's O(N * cells) mask sweep nor the Fortran head/list chain:
 //   1. cell_assign : wrap, triplet, local cell id; one atomicAdd per atom gives the per-cell histogram and an
 //                    arrival rank inside the cell                                  (reads 24 B, writes 8 B / atom)
-//   2. cell_scan   : exclusive scan of the histogram -> cell_start                 (4 B / cell, three small kernels)
+//   2. cell_scan   : exclusive scan of the histogram -> cell_start       (4 B / cell, one decoupled-look-back kernel)
 //   3. cell_scatter: key = (atom id << 32 | source index) -> slot cell_start + rank
 //   4. cell_sortgather: per block of 32..128 cells, keys to shared memory, one thread per cell orders its <= ~30 keys
 //                    by atom id (the arrival rank of step 1 is scheduling dependent, the sorted result is not) ->
@@ -107,8 +107,13 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
                                                         int *__restrict__ err, double *__restrict__ partials,
                                                         double *__restrict__ rec_vf,
                                                         const double *__restrict__ pair_partials, int pair_rows,
-                                                        int model, SlabArgs sl, const int *__restrict__ pair_rows_dev) {
+                                                        int model, SlabArgs sl, const int *__restrict__ pair_rows_dev,
+                                                        int *__restrict__ step_ctr, int *__restrict__ tab0) {
   if (pair_rows_dev) pair_rows = min(pair_rows, *pair_rows_dev);
+  // replayed launches (CUDA graph): the record of the finished step is rec_vf + NREC * *step_ctr; the CTA that finishes
+  // last moves the counter on.  tab0: word 0 of the pair kernel's item table, zeroed here for this step's table kernel
+  if (step_ctr) rec_vf += (size_t)ATLJ_NREC * (size_t)*step_ctr;
+  if (tab0 && blockIdx.x == 0 && threadIdx.x == 0) *tab0 = 0;
   // tiles of IT atoms: the 3*IT components are streamed with perfectly coalesced accesses (one component per thread
   // and pass), the wrapped coordinates (and, on a slab, the velocities) are parked in shared memory, then one thread
   // per atom does the integer part
@@ -258,15 +263,21 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
       err[2] = 0;  // work counter of the tiled pair kernel
     }
   }
-  if (threadIdx.x == 0) err[4] = 0;
+  if (threadIdx.x == 0) {
+    err[4] = 0;
+    if (step_ctr) *step_ctr += 1;  // every CTA read it at its start, i.e. before the last one got here
+  }
 }
 
 // -> number of CTAs (= rows of vf partials written when first_kick)
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
                       const double *pair_partials, int pair_rows, int model, const SlabArgs *slab,
-                      const int *pair_rows_dev) {
-  ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+                      const int *pair_rows_dev, const KdkLoop *loop) {
+  // (in the replayed loop the counts were zeroed by the previous step's sort + gather, word 0 of the item table is
+  // zeroed by this kernel and the record pointer follows a device counter: no memset nodes, no per-step arguments)
+  if (!loop || !loop->counts_zeroed) ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+  int *step_ctr = loop ? loop->step_ctr : nullptr, *tab0 = loop ? loop->tab0 : nullptr;
   const int nb = integ_blocks(n);
   SlabArgs sl = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
   if (slab) sl = *slab;
@@ -279,11 +290,11 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   if (inv_box != 0.0)
     kdk_assign_kernel<true><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
                                                b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
-                                               pair_rows, model, sl, pair_rows_dev);
+                                               pair_rows, model, sl, pair_rows_dev, step_ctr, tab0);
   else
     kdk_assign_kernel<false><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
                                                 b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
-                                                pair_rows, model, sl, pair_rows_dev);
+                                                pair_rows, model, sl, pair_rows_dev, step_ctr, tab0);
   ATLJ_LAUNCHED();
   return nb;
 }
@@ -318,64 +329,23 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *smem /*[SCAN_T/3
   return incl - v + smem[w];
 }
 
-// phase A: per-tile sums
-__global__ void __launch_bounds__(SCAN_T) scan_tile_sums_kernel(const int *__restrict__ cnt, int n,
-                                                                int *__restrict__ tile_sums) {
-  __shared__ int sm[SCAN_T / 32];
-  __shared__ int total;
-  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < n) s += cnt[base + k];
-  block_exclusive_scan(s, sm, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// phase B: scan the tile sums in place (one block; ntiles <= SCAN_TILE)
-__global__ void __launch_bounds__(SCAN_T) scan_tile_offsets_kernel(int *__restrict__ tile_sums, int ntiles) {
-  __shared__ int sm[SCAN_T / 32];
-  __shared__ int total;
-  int base = threadIdx.x * SCAN_ITEMS;
-  int v[SCAN_ITEMS];
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = base + k < ntiles ? tile_sums[base + k] : 0;
-    s += v[k];
-  }
-  int off = block_exclusive_scan(s, sm, &total);
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < ntiles) tile_sums[base + k] = off;
-    off += v[k];
-  }
-}
-
-// phase C: final exclusive scan, cell_start[first + c] = base + prefix; also writes the end sentinel
-// start is the padded table of the whole local grid (Geom::cs_idx); k-th owned cell sits in layer h + k / sc2
-// fold != 0: tile_off holds the raw tile SUMS (not their scan): every CTA adds up the sums of the tiles before it
-// itself - for grids of up to SCAN_T tiles (2 M cells) that saves the one-CTA kernel in between
-__global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restrict__ cnt, int n,
-                                                            const int *__restrict__ tile_off, int base_off,
-                                                            int *__restrict__ start, int sc2, int h, int fold) {
+// Single-pass scan (decoupled look-back): every CTA scans its tile of 4096 cells, publishes the tile's aggregate, then
+// adds up the aggregates / inclusive prefixes of the tiles before it, 32 at a time (CTAs are scheduled in index
+// order, so a CTA only ever waits for CTAs that are already running).  One launch instead of three; integer sums, so
+// the result does not depend on the order in which the look-back finds its terms.
+// state[t] = value << 2 | flag (0 = nothing yet, 1 = aggregate of tile t, 2 = inclusive prefix up to tile t);
+// state[SCAN_STATE_CTR] counts finished CTAs: the last one clears the states for the next launch.
+// cell_start[first + c] = base_off + prefix, written into the padded table of the whole local grid (Geom::cs_idx: the
+// k-th owned cell sits in layer h + k / sc2; one end sentinel per layer).
+constexpr int SCAN_STATE_CTR = 4095;  // CellBufs::block_sums holds 4096 64-bit words
+__global__ void __launch_bounds__(SCAN_T) scan_lookback_kernel(const int *__restrict__ cnt, int n, int base_off,
+                                                                int *__restrict__ start, int sc2, int h,
+                                                                unsigned long long *__restrict__ state) {
   __shared__ int sm[SCAN_T / 32];
   __shared__ int total;
   __shared__ int s_before;
-  if (fold) {
-    int t = (int)threadIdx.x < (int)blockIdx.x ? tile_off[threadIdx.x] : 0;  // blockIdx.x <= SCAN_T tiles
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int a = 0;
-      for (int w = 0; w < SCAN_T / 32; w++) a += sm[w];
-      s_before = a;
-    }
-    __syncthreads();
-  }
-  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  const int tile = blockIdx.x;
+  const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
 #pragma unroll
@@ -383,7 +353,42 @@ __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restric
     v[k] = base + k < n ? cnt[base + k] : 0;
     s += v[k];
   }
-  int off = block_exclusive_scan(s, sm, &total) + (fold ? s_before : tile_off[blockIdx.x]) + base_off;
+  const int local = block_exclusive_scan(s, sm, &total);
+  if (threadIdx.x == 0) {
+    const unsigned long long word = ((unsigned long long)(unsigned)total << 2) | (tile == 0 ? 2ull : 1ull);
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + tile), "l"(word) : "memory");
+  }
+  if (threadIdx.x < 32) {
+    int before = 0;
+    int j0 = tile - 1;  // look-back window [j0 - 31, j0]
+    while (j0 >= 0) {
+      const int j = j0 - (int)threadIdx.x;
+      unsigned long long w = 2ull;  // lanes past tile 0: an empty inclusive prefix
+      if (j >= 0) {
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(state + j) : "memory");
+        } while ((w & 3ull) == 0ull);
+      }
+      // the nearest tile that already knows its inclusive prefix ends the look-back
+      const unsigned has_p = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
+      const int stop = has_p ? __ffs(has_p) - 1 : 32;
+      int val = ((int)threadIdx.x <= stop) ? (int)(w >> 2) : 0;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+      before += val;
+      if (has_p) break;
+      j0 -= 32;
+    }
+    if (threadIdx.x == 0) {
+      s_before = before;
+      if (tile > 0) {
+        const unsigned long long word = ((unsigned long long)(unsigned)(before + total) << 2) | 2ull;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + tile), "l"(word) : "memory");
+      }
+    }
+  }
+  __syncthreads();
+  int off = local + s_before + base_off;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
     const int c = base + k;
@@ -395,25 +400,29 @@ __global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const int *__restric
     }
     off += v[k];
   }
+  // the CTA that finishes last clears the states: every other CTA is past its look-back by then
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(state + SCAN_STATE_CTR, 1ull) == (unsigned long long)gridDim.x - 1ull) s_before = -1;
+  }
+  __syncthreads();
+  if (s_before == -1) {
+    for (int t = threadIdx.x; t < (int)gridDim.x; t += SCAN_T) state[t] = 0ull;
+    if (threadIdx.x == 0) state[SCAN_STATE_CTR] = 0ull;
+  }
 }
 
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base) {
   int n = g.n_own_cells();
   int first = g.first_own_cell();
   int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (ntiles > SCAN_TILE) {
-    set_error("cell grid too large for the two-level scan (%d cells)", n);
+  if (ntiles > SCAN_STATE_CTR) {
+    set_error("cell grid too large for the scan (%d cells)", n);
     return ATLJ_ERR_ARG;
   }
-  scan_tile_sums_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums);
-  ATLJ_LAUNCHED();
-  const int fold = ntiles <= SCAN_T ? 1 : 0;
-  if (!fold) {
-    scan_tile_offsets_kernel<<<1, SCAN_T, 0, st>>>(b.block_sums, ntiles);
-    ATLJ_LAUNCHED();
-  }
-  scan_final_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, b.block_sums, base, b.cell_start, g.sc * g.sc,
-                                               g.h, fold);
+  scan_lookback_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, base, b.cell_start, g.sc * g.sc, g.h,
+                                                  reinterpret_cast<unsigned long long *>(b.block_sums));
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }
@@ -497,13 +506,13 @@ static inline int sg_cells_per_block(int ncells) { return ncells >= 148 * 2 * 12
 
 __global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base, int block0, int cpb,
                                                                     const int *__restrict__ cell_start,
-                                                                    const int *__restrict__ cell_count,
+                                                                    int *cell_count,
                                                                     unsigned long long *__restrict__ keys,
                                                                     const double *__restrict__ r_in,
                                                                     const double *__restrict__ v_in,
                                                                     double *__restrict__ r_out,
                                                                     double *__restrict__ v_out,
-                                                                    int *__restrict__ id_out) {
+                                                                    int *__restrict__ id_out, int zero_counts) {
   __shared__ unsigned long long sk[SG_KEYS];
   __shared__ int s_lo, s_hi;
   const int nown = g.n_own_cells(), first = g.first_own_cell();
@@ -513,6 +522,7 @@ __global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base,
   if (threadIdx.x < cpb && c < nown) {
     mystart = cell_start[g.cs_idx(first + c)] - base;
     mycnt = cell_count[first + c];
+    if (zero_counts) cell_count[first + c] = 0;  // ready for the next step's histogram
   }
   if (threadIdx.x == 0) s_lo = mystart;
   const int clast = min(c0 + cpb, nown) - 1;
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base,
 // messages are packed from); 2 = the remaining blocks (a slab rank runs them while the halo exchange is in flight)
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev, int which) {
+                            const int *n_dev, int which, bool zero_counts) {
   if (n <= 0) return ATLJ_OK;
   if (which != 2) {
     cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in,
@@ -565,7 +575,8 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
     // large grids: 128 cells and 128 threads per CTA (measured best at 2 M atoms); small grids: fewer cells per CTA
     // and twice the threads for the gather
     cell_sortgather_kernel<<<cnt, cpb == 128 ? 128 : SG_T, 0, st>>>(g, base, b0, cpb, b.cell_start, b.cell_count,
-                                                                    b.keys, r_in, v_in, r_out, v_out, id_out);
+                                                                    b.keys, r_in, v_in, r_out, v_out, id_out,
+                                                                    zero_counts ? 1 : 0);
     ATLJ_LAUNCHED();
     return ATLJ_OK;
   };

@@ -148,16 +148,25 @@ struct SlabArgs {
 // (= rows of vf_partials written when first_kick) or a negative status
 // rec_vf (used when first_kick): the finished step's record: its [4], [5] = sum v^2, sum f^2 and, when pair_partials
 // is given, the pair kernel's totals (per-item rows reduced in fixed order) are written by the kernel's last CTA
+// loop (may be null): the device-resident NVE loop, whose launches must not depend on the step number so that two
+// steps can be captured once and replayed as a CUDA graph
+struct KdkLoop {
+  int *step_ctr;       // device counter: rec_vf is the BASE of the records and the finished step's record is row *step_ctr
+                       // (null: rec_vf is that record itself)
+  int *tab0;           // word 0 of the tiled pair kernel's item table, zeroed by the kernel (null: the launcher of the
+                       // pair kernel does it)
+  bool counts_zeroed;  // cell_count was left zeroed by the previous step's launch_cell_sort_gather(zero_counts)
+};
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
                       const double *pair_partials, int pair_rows, int model, const SlabArgs *slab = nullptr,
-                      const int *pair_rows_dev = nullptr);
+                      const int *pair_rows_dev = nullptr, const KdkLoop *loop = nullptr);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev = nullptr, int which = 0);
+                            const int *n_dev = nullptr, int which = 0, bool zero_counts = false);
 
 struct PairArgs {
   const double *r;       // sorted positions (owned + halo), AoS
@@ -184,12 +193,18 @@ int pair_tile2_items(const Geom &g);  // work items (= rows of partials) of the 
 // pointer (rows_dev) next to the upper bound returned here.
 // mode 0: forces; 1: forces, and a.masks receives every atom's mask words; 2: hessian sum from a.fin and the masks of a
 // mode-1 launch on the same cell table
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode = 0);
+// part 0: item table + pair kernel; 1: the item table only (it depends on cell_start alone, so the replayed loop runs it
+// beside the sort + gather); 2: the pair kernel only.  tab_zeroed: word 0 of the table is already 0 (KdkLoop::tab0)
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode = 0, int part = 0,
+                      bool tab_zeroed = false);
 size_t pair_tile2_mask_bytes(long long natoms);
 int pair_tile2_tab_ints(const Geom &g);  // ints of PairArgs::tile_tab for this geometry
 // direct link-cell kernel (cells of ~1 atom): one thread per owned atom, no staging
 int pair_direct_blocks(int n);
 int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n);
+// small systems: eight lanes per atom, exact arithmetic, candidates from the cell table (cells) or all n atoms
+int pair_multi_blocks(int n);
+int launch_pair_multi(cudaStream_t st, const PairArgs &a, bool hessian, int n, bool cells);
 // one atom against nj partners (smc_lj_module.force_1): -> rows of partials written
 int launch_force_1(cudaStream_t st, const double ri[3], const double *r, int nj, const Phys &p, double *f_partial,
                    double *partials);
@@ -201,6 +216,6 @@ int launch_pair_all(cudaStream_t st, const double *r, const double *fin, int n, 
 // vf_partials (may be null): [nvf][4] partial {sum v^2, sum f^2} of the integration kernel, reduced into rec[4], rec[5]
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
                     int *reset_counter = nullptr, const double *vf_partials = nullptr, int nvf = 0,
-                    const int *rows_dev = nullptr);
+                    const int *rows_dev = nullptr, const int *step_ctr = nullptr);
 
 }  // namespace atlj

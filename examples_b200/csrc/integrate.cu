@@ -38,8 +38,12 @@ __global__ void __launch_bounds__(IT) kick_drift_kernel(long long n3, double *__
 __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__restrict__ v,
                                                        const double *__restrict__ f, double half_dt,
                                                        double *__restrict__ partials, const int *__restrict__ n_dev,
-                                                       int *__restrict__ done, double *__restrict__ out2) {
+                                                       int *__restrict__ done, double *__restrict__ out2,
+                                                       int *__restrict__ step_ctr) {
   if (n_dev) n3 = min(n3, 3ll * *n_dev);
+  // replayed launches: out2 is relative to the record of step *step_ctr; this kernel ends the step and moves the
+  // counter on (its last CTA, after every CTA has read it)
+  if (step_ctr) out2 += (size_t)ATLJ_NREC * (size_t)*step_ctr;
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
   long long stride = (long long)gridDim.x * IT;
   double s[2] = {0.0, 0.0};
@@ -64,7 +68,10 @@ __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__r
     a[1] += __ldcg(partials + 4 * (size_t)b + 1);
   }
   block_reduce_store<2>(a, out2);
-  if (threadIdx.x == 0) *done = 0;
+  if (threadIdx.x == 0) {
+    *done = 0;
+    if (step_ctr) *step_ctr += 1;
+  }
 }
 
 // generic second stage: out[k] = sum_b partials[b][k], k < K <= 4, fixed order
@@ -105,9 +112,9 @@ int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const
 }
 
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
-                     double *out2, int *done, const int *n_dev) {
+                     double *out2, int *done, const int *n_dev, int *step_ctr) {
   int nb = integ_blocks(n3);
-  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev, done, out2);
+  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev, done, out2, step_ctr);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -189,6 +189,133 @@ int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n) 
   return blocks;
 }
 
+// ---- small systems: eight lanes per atom --------------------------------------------------------------------------------
+// Below ~1e5 atoms the tiled kernels cannot fill a B200 (N = 32,000 is 250 chunks of 128 atoms for 592 warp
+// schedulers) and a step is bound by the latency of ONE chunk.  Here an atom's candidates are spread over MK_L = 8
+// lanes of a warp (4 atoms per warp, 16 per CTA): N = 32,000 gives 8,000 warps.  Every lane runs the reference's exact
+// arithmetic (pair_sep, md_lj_module.py:96-99) on its share of the candidates, parks the in-range ones in a small
+// shared-memory list (pass 1: divergent but cheap), evaluates them (pass 2: nearly uniform trip count), and the eight
+// partial forces are added with warp shuffles in a fixed order (md_lj_module.py:109,113).  CELLS: candidates are the
+// atom's 27 (LE: up to 30) neighbour cells on the cell-sorted arrays (md_lj_ll_module.py:122-165); !CELLS: all atoms
+// (md_lj_module.py:95-115, the reference's N = 256 case).
+constexpr int MK_T = 128, MK_L = 8, MK_LIST = 20;
+
+template <int MODEL, bool HESS, bool CELLS>
+__global__ void __launch_bounds__(MK_T) pair_multi_kernel(PairArgs a, int n) {
+  constexpr bool LE = (MODEL == ATLJ_MODEL_WCA);
+  __shared__ int cand[MK_LIST * MK_T];  // [slot][thread]: conflict-free
+  const Geom g = a.g;
+  const Phys p = a.p;
+  const int sub = threadIdx.x & (MK_L - 1);
+  const int i = (int)(((long long)blockIdx.x * MK_T + threadIdx.x) / MK_L);
+  const bool act = i < n;
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0ull, 0};
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  if (act) {
+    const double rix = a.r[3 * (size_t)i], riy = a.r[3 * (size_t)i + 1], riz = a.r[3 * (size_t)i + 2];
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    if (HESS) fix = a.fin[3 * (size_t)i], fiy = a.fin[3 * (size_t)i + 1], fiz = a.fin[3 * (size_t)i + 2];
+    auto one = [&](int j) {
+      double dx, dy, dz, s;
+      if (pair_sep<LE>(rix, riy, riz, a.r[3 * (size_t)j], a.r[3 * (size_t)j + 1], a.r[3 * (size_t)j + 2], p.strain,
+                       p.r_cut_box_sq, dx, dy, dz, s)) {
+        if (HESS)
+          pair_hess_term(p, dx, dy, dz, s, fix - a.fin[3 * (size_t)j], fiy - a.fin[3 * (size_t)j + 1],
+                         fiz - a.fin[3 * (size_t)j + 2], acc);
+        else
+          pair_force_term<MODEL>(p, dx, dy, dz, s, fx, fy, fz, acc);
+      }
+    };
+    int cnt = 0;
+    auto range = [&](int j0, int j1) {  // this lane's share of the candidates [j0, j1)
+      for (int j = j0 + sub; j < j1; j += MK_L) {
+        if (j == i) continue;
+        double dx, dy, dz, s;
+        if (pair_sep<LE>(rix, riy, riz, a.r[3 * (size_t)j], a.r[3 * (size_t)j + 1], a.r[3 * (size_t)j + 2], p.strain,
+                         p.r_cut_box_sq, dx, dy, dz, s)) {
+          if (cnt < MK_LIST)
+            cand[(cnt++) * MK_T + threadIdx.x] = j;
+          else
+            one(j);  // list full (a crowded neighbourhood): evaluate on the spot
+        }
+      }
+    };
+    if (CELLS) {
+      const double scd = (double)g.sc;
+      // the atom's own cell, with the arithmetic of the cell assignment (md_lj_ll_module.py:108)
+      const int c0 = (int)floor(__dmul_rn(__dadd_rn(rix, 0.5), scd));
+      const int cy = (int)floor(__dmul_rn(__dadd_rn(riy, 0.5), scd));
+      const int cz = (int)floor(__dmul_rn(__dadd_rn(riz, 0.5), scd));
+      const int lx = c0 - g.x_lo + g.h;
+      // a slot outside the grid only happens after an index error (reported by the cell build): contribute nothing
+      const bool ok = lx >= g.h && lx < g.h + g.nx_own && cy >= 0 && cy < g.sc && cz >= 0 && cz < g.sc;
+      for (int kk = 0; ok && kk < MAX_NB / 3; kk++) {
+        const int nc = neighbour_cell(g, LE, p.shift, lx, cy, cz, 3 * kk + 1);  // the dz = 0 cell of the slot
+        if (nc < 0) continue;
+        // the three z neighbours of one (dx, dy) slot are ONE index range of the sorted arrays unless z wraps
+        const int idx = g.cs_idx(nc);
+        const int lo = cz > 0 ? idx - 1 : idx, hi = cz < g.sc - 1 ? idx + 2 : idx + 1;
+        range(a.cell_start[lo], a.cell_start[hi]);
+        if (cz == 0 || cz == g.sc - 1) {
+          const int w = cz == 0 ? idx + g.sc - 1 : idx - (g.sc - 1);
+          range(a.cell_start[w], a.cell_start[w + 1]);
+        }
+      }
+    } else {
+      range(0, n);
+    }
+    for (int c = 0; c < cnt; c++) one(cand[c * MK_T + threadIdx.x]);
+  }
+  if (!HESS) {
+    // the eight lanes of an atom are adjacent lanes of one warp: fixed-order butterfly over lane bits 2, 1, 0
+#pragma unroll
+    for (int o = MK_L / 2; o >= 1; o >>= 1) {
+      fx += __shfl_xor_sync(FULL, fx, o);
+      fy += __shfl_xor_sync(FULL, fy, o);
+      fz += __shfl_xor_sync(FULL, fz, o);
+    }
+    if (act && sub == 0) {
+      a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
+      a.f[3 * (size_t)i + 1] = 24.0 * fy;
+      a.f[3 * (size_t)i + 2] = 24.0 * fz;
+    }
+  }
+  block_store_partials<MK_T / 32>(acc, a.partials + 8 * (size_t)blockIdx.x);
+}
+
+int pair_multi_blocks(int n) {
+  const long long b = ((long long)n * MK_L + MK_T - 1) / MK_T;
+  return b > 0 ? (int)b : 1;
+}
+
+// -> CTAs launched (= rows of partials written) or a negative status; cells: candidates from the cell table of a.g,
+// otherwise all n atoms of a.r
+int launch_pair_multi(cudaStream_t st, const PairArgs &a, bool hessian, int n, bool cells) {
+  const int blocks = pair_multi_blocks(n);
+#define ATLJ_MK(MODEL, HESS)                                                    \
+  do {                                                                          \
+    if (cells)                                                                  \
+      pair_multi_kernel<MODEL, HESS, true><<<blocks, MK_T, 0, st>>>(a, n);      \
+    else                                                                        \
+      pair_multi_kernel<MODEL, HESS, false><<<blocks, MK_T, 0, st>>>(a, n);     \
+  } while (0)
+  if (a.p.model == ATLJ_MODEL_LJ) {
+    if (hessian)
+      ATLJ_MK(ATLJ_MODEL_LJ, true);
+    else
+      ATLJ_MK(ATLJ_MODEL_LJ, false);
+  } else {
+    if (hessian) {
+      set_error("hessian is defined for the LJ model only");
+      return ATLJ_ERR_ARG;
+    }
+    ATLJ_MK(ATLJ_MODEL_WCA, false);
+  }
+#undef ATLJ_MK
+  ATLJ_LAUNCHED();
+  return blocks;
+}
+
 // ---- force_1: one atom against a set of partners (smc_lj_module.py:100-191) ---------------------------------------
 // One thread per partner j with the reference's arithmetic; f_partial[j] = force on i due to j (times 24, :190); the
 // per-CTA rows go through the usual fixed-order finalize.  The caller zeroes everything when the overlap flag comes
@@ -226,8 +353,10 @@ __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restric
                                                          int hessian, double *__restrict__ rec,
                                                          int *__restrict__ reset_counter,
                                                          const double *__restrict__ vf_partials, int nvf,
-                                                         const int *__restrict__ rows_dev) {
+                                                         const int *__restrict__ rows_dev,
+                                                         const int *__restrict__ step_ctr) {
   if (rows_dev) nblocks = min(nblocks, *rows_dev);
+  if (step_ctr) rec += (size_t)ATLJ_NREC * (size_t)*step_ctr;  // replayed launches: the row follows a device counter
   if (threadIdx.x == 0 && reset_counter) *reset_counter = 0;
   __shared__ double sm[FIN_T / 32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -261,9 +390,9 @@ __global__ void __launch_bounds__(FIN_T) finalize_kernel(const double *__restric
 }
 
 int launch_finalize(cudaStream_t st, const double *partials, int nblocks, int model, bool hessian, double *rec,
-                    int *reset_counter, const double *vf_partials, int nvf, const int *rows_dev) {
+                    int *reset_counter, const double *vf_partials, int nvf, const int *rows_dev, const int *step_ctr) {
   finalize_kernel<<<1, FIN_T, 0, st>>>(partials, nblocks, model, hessian ? 1 : 0, rec, reset_counter, vf_partials, nvf,
-                                       rows_dev);
+                                       rows_dev, step_ctr);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -742,7 +742,7 @@ static int tile2_grid() {
 // the device only: the kernel stores it in *rows_out (work_counter + 4), which the reducers read.
 // mode: T2_FORCE, T2_FORCE_SAVE (a.masks receives the mask words) or T2_HESS (a.fin = forces, a.masks from the
 // T2_FORCE_SAVE launch on the same cell table; the item table of that launch is reused).
-int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode) {
+int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int mode, int part, bool tab_zeroed) {
   const int grid = mode == T2_HESS ? tile2_grid<T2_HESS>()
                                    : tile2_grid<T2_FORCE>();
   if (grid < 0) {
@@ -770,12 +770,13 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   const double cell = a.p.box / a.g.sc;
   if (ncz_max > (int)(200.0 / cell) - 2) ncz_max = (int)(200.0 / cell) - 2;
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
-  if (mode != T2_HESS) {
-    ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
+  if (mode != T2_HESS && part != 2) {
+    if (!tab_zeroed) ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
     tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, a.tile_tab);
     ATLJ_LAUNCHED();
   }
   const int bound = nrp * (gstride - 1);
+  if (part == 1) return bound;
   const int nblk = grid < bound ? grid : bound;
   if (mode == T2_HESS)
     pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,

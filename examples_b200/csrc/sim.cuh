@@ -47,6 +47,13 @@ struct atlj_sim {
   uint2 *masks = nullptr;      // pair_tile2 mask words (allocated with the first hessian request)
   double *vf_partials = nullptr;  // [<= 4096][4] partial {sum v^2, sum f^2} of the integration kernels
   bool unfused = false;
+  bool no_graph = false;
+  // replayed NVE loop: two captured steps (api.cu nve_graph_prepare)
+  cudaGraphExec_t nve_graph = nullptr;
+  int nve_graph_launches = 0;       // kernel launches one replay stands for
+  unsigned char nve_graph_key[160] = {0};
+  cudaStream_t st_cap = nullptr, st_side = nullptr;  // capture stream and its fork (item table beside the sort)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *scal = nullptr;      // 64 device scalars (thermostat state, reduction results)
   double *rec_dev = nullptr;   // per-step records
   int64_t rec_cap = 0;

@@ -48,7 +48,7 @@ def _force_le(box, strain, r, sc, check_index):
     r_cut_box_sq = r_cut_box ** 2
     box_sq = box ** 2
     shift = math.floor(strain * sc) if sc > 0 else 0
-    f = np.empty_like(r)
+    f = _lib.result_empty(r.shape)      # page-locked when large: the GPU writes it by DMA
     totals = np.empty(4, dtype=np.float64)
     ovr = C.c_int(0)
     npair = C.c_int64(0)

@@ -64,7 +64,7 @@ def _force(box, r_cut, r, sc, check_index):
     r = _lib.as_f64(r)
     n = r.shape[0]
     r_cut_box_sq, box_sq, pot_cut = _host_scalars(box, r_cut)
-    f = np.empty_like(r)
+    f = _lib.result_empty(r.shape)      # page-locked when large: the GPU writes it by DMA
     totals = np.empty(4, dtype=np.float64)
     ovr = C.c_int(0)
     npair = C.c_int64(0)

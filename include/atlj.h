@@ -52,6 +52,11 @@ const char *atlj_last_error(void);
 int atlj_device_count(void);      /* number of CUDA devices, 0 if none          */
 int atlj_set_device(int device);  /* all later calls of this thread use device  */
 int64_t atlj_kernel_launches(void); /* kernels launched by this library so far (bench: gpu_launches) */
+/* Kernel selection by system size (no reference counterpart): systems of at most `natoms` atoms on one GPU use the
+ * eight-lanes-per-atom pair kernel (the tiled kernels cannot fill a B200 there); 0 switches it off.
+ * Default 16384 (measured: at N = 32,000 the tiled kernel is the faster one again), or the environment variable ATLJ_MULTI_MAX.  Returns the previous value.  Results are the same
+ * pair set with the same exact in-range / overlap decisions whichever kernel runs; tests use it to cover each one. */
+int64_t atlj_set_multi_max(int64_t natoms);
 
 /* ---------------------------------------------------------------------------------------------
  * stateless drop-in path: host arrays in, host arrays out (H2D + kernels + D2H per call)

@@ -24,6 +24,9 @@ CASES = {
     "nve_256": ("md_nve_lj.py", '{"nblock":2,"nstep":50}', 4, None),
     "nve_ll_864": ("md_nve_lj.py", '{"nblock":2,"nstep":25}', 6,
                    {"md_lj_module.py": "from md_lj_ll_module import *  # GUIDE.md:288-289\n"}),
+    # md_nvt_lj.py:227,256 and md_npt_lj.py:289,320-331 call np.random.seed() (OS entropy) and draw the thermostat /
+    # barostat momenta: SEEDED cases are started through runpy with np.random.seed pinned to a fixed value, so that
+    # the unmodified script draws the same numbers in the golden run and in the test
     "nvt_256": ("md_nvt_lj.py", '{"nblock":2,"nstep":50}', 4, None),
     "npt_256": ("md_npt_lj.py", '{"nblock":2,"nstep":50}', 4, None),
     # strain_rate * dt * nstep must be an integer (md_nvt_lj_le.py:198-201): 4.0 * 0.005 * 50 = 1, so the strain crosses
@@ -32,6 +35,13 @@ CASES = {
     "le_ll_2048": ("md_nvt_lj_le.py", '{"nblock":2,"nstep":50,"strain_rate":4.0}', 8,
                    {"md_lj_le_module.py": "from md_lj_llle_module import *  # GUIDE.md:476-477\n"}),
 }
+
+SEEDED = {"nvt_256": 20170101, "npt_256": 20170102}
+_RUNPY = ("import sys, runpy, numpy as np\n"
+          "_seed = np.random.seed\n"
+          "np.random.seed = lambda *a, **k: _seed(%d)\n"
+          "sys.argv = [%r]\n"
+          "runpy.run_path(%r, run_name='__main__')\n")
 
 # lines that legitimately differ between two runs or two force back-ends: versions, wall clock, the banner line that
 # names the routine ("Fast NumPy force routine" / "CUDA force routine (libatlj, sm_100a)")
@@ -74,8 +84,11 @@ def run_case(name, module_dirs, timeout=900):
         # PYTHONSAFEPATH (Python >= 3.11, same as `python -P`): do not put the SCRIPT's directory in front of sys.path,
         # otherwise the reference modules next to the script would always win over PYTHONPATH
         env = dict(os.environ, PYTHONPATH=os.pathsep.join(path), PYTHONSAFEPATH="1")
-        p = subprocess.run([sys.executable, os.path.join(module_dirs[-1], script)], input=params, capture_output=True,
-                           text=True, cwd=tmp, env=env, timeout=timeout)
+        path_script = os.path.join(module_dirs[-1], script)
+        cmd = [sys.executable, path_script]
+        if name in SEEDED:
+            cmd = [sys.executable, "-c", _RUNPY % (SEEDED[name], path_script, path_script)]
+        p = subprocess.run(cmd, input=params, capture_output=True, text=True, cwd=tmp, env=env, timeout=timeout)
         if p.returncode != 0:
             raise RuntimeError("%s exited %d:\n%s\n%s" % (script, p.returncode, p.stdout[-2000:], p.stderr[-2000:]))
         with open(os.path.join(tmp, "cnf.out")) as fh:

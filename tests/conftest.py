@@ -15,6 +15,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: with the small-system pair kernel (eight lanes per atom; forced on up to 1e5 atoms
+    here, the default is 16,384) and with the routes large systems take (tiled / direct / all-pairs kernels), so that each kernel keeps
+    its parity coverage at the sizes the oracle and the goldens can check."""
+    if metafunc.definition.get_closest_marker("gpu") is not None:
+        metafunc.fixturenames.append("pair_route")
+        metafunc.parametrize("pair_route", ["small", "tiled"], indirect=True)
+
+
+@pytest.fixture
+def pair_route(request):
+    from examples_b200 import _lib
+    limit = 100000 if request.param == "small" else 0
+    old = _lib.set_multi_max(limit)
+    old_env = os.environ.get("ATLJ_MULTI_MAX")
+    os.environ["ATLJ_MULTI_MAX"] = str(limit)      # subprocesses (the unmodified reference drivers)
+    yield request.param
+    _lib.set_multi_max(old)
+    if old_env is None:
+        os.environ.pop("ATLJ_MULTI_MAX", None)
+    else:
+        os.environ["ATLJ_MULTI_MAX"] = old_env
+
+
 @pytest.fixture(scope="session")
 def golden():
     """Outputs of the unmodified reference Python modules (oracle/make_golden.py)."""

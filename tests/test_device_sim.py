@@ -233,7 +233,13 @@ def test_energy_drift_trace_10k_steps():
     assert rel_err(rec[:300, 1], rec_g[:300, 0]) < 1e-8 and rel_err(rec[:300, 4], rec_g[:300, 1]) < 1e-8
     e = (0.5 * rec[:, 4] + rec[:, 1]) / n
     eg = (0.5 * rec_g[:, 1] + rec_g[:, 0]) / n
-    assert abs(e.mean() - eg.mean()) < 5e-5
+    blocks_ref = eg.reshape(10, -1).mean(axis=1)
+    # the conserved energy random-walks (cut-and-shifted force, finite dt): the golden's own block means wander over
+    # 3.4e-4, and two runs that differ in summation order are decorrelated after ~6,000 steps, so their whole-trace
+    # means agree to within that wander and no better
+    print("drift trace: mean %.9f (golden %.9f), diff %.2e, golden block-mean range %.2e"
+          % (e.mean(), eg.mean(), e.mean() - eg.mean(), np.ptp(blocks_ref)))
+    assert abs(e.mean() - eg.mean()) < np.ptp(blocks_ref), (e.mean(), eg.mean())
     assert 0.5 < e.var() / eg.var() < 2.0, (e.var(), eg.var())          # conserved-energy MSD (7.3e-8 in the golden)
     blocks, blocks_g = e.reshape(10, -1).mean(axis=1), eg.reshape(10, -1).mean(axis=1)
     # the conserved energy performs a small random walk (block means wander by ~3e-4 in the golden itself); after the

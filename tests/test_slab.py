@@ -97,7 +97,11 @@ def test_slab_scheme_two_ranks_gloo(oracle):
 def test_emulated_slabs_match_single_domain(nc, world):
     from examples_b200.device import Simulation
     from examples_b200.lattice import ran_velocities
+    from examples_b200 import _lib
     from examples_b200.slab import EmulatedSlabs
+    # bit-identical forces need the same summation order: the single domain must take the tiled kernel the slabs use,
+    # not the small-system kernel this size would select (the pair_route fixture restores the setting)
+    _lib.set_multi_max(0)
     n, box, r = liquid_like(nc, 0.75, 0.06)
     v = ran_velocities(n, 1.5)
     one = Simulation(box, 2.5, r, v)

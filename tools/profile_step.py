@@ -15,11 +15,15 @@ sc = int(os.environ["ATLJ_SC"]) if "ATLJ_SC" in os.environ else None   # coarser
 sim = Simulation(box, R_CUT, r, v, sc=sc)
 sim.force()
 sim.run_nve(DT, melt, record=False)
+sim.sync()
+sim.timer_start()
+sim.run_nve(DT, steps, record=False)
+ms = sim.timer_stop()
 sim.enable_timing(True)
 sim.timing()
 rec = sim.run_nve(DT, steps)
 t = sim.timing()
-print("sc=%d " % sim.sc, end="")
+print("sc=%d whole step %.4f ms (graph replay unless ATLJ_NO_GRAPH=1) " % (sim.sc, ms / steps), end="")
 print("N=%d steps=%d pairs/atom=%.3f T=%.3f ms/step: pair %.4f cells %.4f integrate %.4f"
       % (n, steps, rec[-1, 8] / n, rec[-1, 4] / (3 * n - 3), t["pair"] / steps, t["cells"] / steps,
          t["integrate"] / steps))
