@@ -57,6 +57,8 @@ def lib():
     L.atlj_neighbour_cells.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p]
     L.atlj_sim_create.restype = _vp
     L.atlj_sim_create.argtypes = [C.c_int64, _vp]
+    L.atlj_sim_create_ex.restype = _vp
+    L.atlj_sim_create_ex.argtypes = [C.c_int64, _vp, C.c_int]
     L.atlj_sim_destroy.restype = None
     L.atlj_sim_destroy.argtypes = [_vp]
     L.atlj_sim_configure.argtypes = [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -88,12 +90,9 @@ def lib():
     L.atlj_sim_mg_phase1.argtypes = [_vp, C.c_double]
     L.atlj_sim_mg_phase2.argtypes = [_vp]
     L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]
-    L.atlj_sim_mg_arena.restype = _vp
-    L.atlj_sim_mg_arena.argtypes = [_vp]
-    L.atlj_sim_mg_arena_bytes.restype = C.c_int64
-    L.atlj_sim_mg_arena_bytes.argtypes = [_vp]
     L.atlj_sim_mg_set_peers.argtypes = [_vp, _vp, _vp]
-    L.atlj_sim_mg_ipc_handle.argtypes = [_vp, C.c_char_p]
+    L.atlj_sim_mg_blob_bytes.restype = C.c_int64
+    L.atlj_sim_mg_ipc_blob.argtypes = [_vp, C.c_char_p]
     L.atlj_sim_mg_ipc_open.argtypes = [_vp, C.c_char_p, C.c_char_p]
     L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
     L.atlj_host_alloc.restype = _vp

@@ -64,6 +64,22 @@ static int dev_alloc(T **p, size_t count) {
   return ATLJ_OK;
 }
 
+// An allocation that cudaIpcGetMemHandle can export on its own: at least 8 MB and a multiple of 2 MB (small cudaMalloc
+// blocks are carved out of shared 2 MB pages and the handle would name the whole page); the last 256 bytes carry a
+// signature the importing process verifies.
+static const unsigned long long IPC_MAGIC = 0x61746c6a6d670002ull;  // "atljmg" 2
+static int dev_alloc_ipc(void **p, size_t bytes, size_t *alloc_bytes, cudaStream_t st) {
+  size_t want = bytes + 256;
+  if (want < (8u << 20)) want = 8u << 20;
+  want = (want + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  ATLJ_CUDA(cudaMalloc(p, want));
+  ATLJ_CUDA(cudaMemsetAsync(*p, 0, want, st));
+  ATLJ_CUDA(cudaMemcpyAsync((unsigned char *)*p + want - 256, &IPC_MAGIC, sizeof(IPC_MAGIC), cudaMemcpyHostToDevice, st));
+  ATLJ_CUDA(cudaStreamSynchronize(st));
+  *alloc_bytes = want;
+  return ATLJ_OK;
+}
+
 static int ensure_tile_tab(atlj_sim *s, int ints) {
   if (ints <= s->tile_tab_ints) return ATLJ_OK;
   cudaFree(s->tile_tab);
@@ -82,7 +98,12 @@ static int ensure_cells(atlj_sim *s, int ncell) {
   int rc;
   if ((rc = dev_alloc(&s->cb.cell_count, (size_t)ncell))) return rc;
   // padded table: one end sentinel per x layer (Geom::cs_idx); sized for the worst padding (sc = 1)
-  if ((rc = dev_alloc(&s->cb.cell_start, 2 * (size_t)ncell + 2))) return rc;
+  if (s->ipc_safe) {
+    if ((rc = dev_alloc_ipc((void **)&s->cb.cell_start, sizeof(int) * (2 * (size_t)ncell + 2), &s->cs_alloc_bytes, s->st)))
+      return rc;
+  } else if ((rc = dev_alloc(&s->cb.cell_start, 2 * (size_t)ncell + 2))) {
+    return rc;
+  }
   ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)ncell, s->st));
   ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_start, 0, sizeof(int) * (2 * (size_t)ncell + 2), s->st));
   s->ncell_alloc = ncell;
@@ -281,7 +302,9 @@ int sim_check_flags(atlj_sim *s) {
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
   if (h[0] || h[1] || h[5]) ATLJ_CUDA(cudaMemsetAsync(s->cb.err, 0, sizeof(h), s->st));
   if (h[5]) {
-    set_error("timed out waiting for a neighbour rank's message (slab exchange)");
+    set_error("timed out waiting for a neighbour rank's message (slab exchange; ATLJ_PEER_TIMEOUT_MS): every kernel "
+              "queued after the timeout was skipped, the state is that of the last complete step - upload it again "
+              "before continuing");
     return ATLJ_ERR_CUDA;
   }
   if (h[0]) {
@@ -335,7 +358,9 @@ int atlj_set_device(int device) {
   return ATLJ_OK;
 }
 
-atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
+atlj_sim *atlj_sim_create(int64_t capacity, void *stream) { return atlj_sim_create_ex(capacity, stream, 0); }
+
+atlj_sim *atlj_sim_create_ex(int64_t capacity, void *stream, int flags) {
   if (device_ok() != ATLJ_OK) return nullptr;
   if (capacity < 1) capacity = 1;
   if (capacity > 0x7fffffffll / 3 - 4096) {  // kernels index components with 3*n in 32-bit integers
@@ -352,11 +377,15 @@ atlj_sim *atlj_sim_create(int64_t capacity, void *stream) {
   const char *ng = getenv("ATLJ_NO_GRAPH");  // A/B runs: every step launched kernel by kernel
   s->no_graph = ng && ng[0] == '1';
   s->cap = capacity;
+  s->ipc_safe = (flags & ATLJ_SIM_IPC) != 0;
   size_t c = (size_t)capacity;
   bool ok = true;
   for (int k = 0; k < 2 && ok; k++) {
-    ok = ok && dev_alloc(&s->r[k], 3 * c) == ATLJ_OK && dev_alloc(&s->v[k], 3 * c) == ATLJ_OK &&
-         dev_alloc(&s->id[k], c) == ATLJ_OK;
+    if (s->ipc_safe)
+      ok = dev_alloc_ipc((void **)&s->r[k], sizeof(double) * 3 * c, &s->r_alloc_bytes, s->st) == ATLJ_OK;
+    else
+      ok = dev_alloc(&s->r[k], 3 * c) == ATLJ_OK;
+    ok = ok && dev_alloc(&s->v[k], 3 * c) == ATLJ_OK && dev_alloc(&s->id[k], c) == ATLJ_OK;
   }
   ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
        dev_alloc(&s->cb.rank, c) == ATLJ_OK && dev_alloc(&s->cb.keys, c) == ATLJ_OK &&

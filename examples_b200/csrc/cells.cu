@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   __shared__ double xs[3 * IT];
   __shared__ double vs[3 * IT];
   const bool slab = sl.to_left != nullptr;
+  if (slab && err[5]) return;  // a neighbour's message timed out earlier in this run: the state stays as it is
   if (sl.n_dev) n = min(n, *sl.n_dev);
   double s[2] = {0.0, 0.0};
   const double scd = (double)g.sc;

@@ -168,6 +168,15 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
                             const int *n_dev = nullptr, int which = 0, bool zero_counts = false);
 
+// slab ranks: the halo layers are written by the neighbours; a pair kernel that reaches a boundary x layer acquires
+// their stamps first (null pointers: nothing to wait for)
+struct HaloWait {
+  const int *stamp_left = nullptr, *stamp_right = nullptr;  // message headers: [1] = stamp
+  int stamp = 0;
+  unsigned long long timeout_ns = 0;
+  int *err = nullptr;  // device flags; [5] is raised on a timeout and turns the rest of the run into no-ops
+};
+
 struct PairArgs {
   const double *r;       // sorted positions (owned + halo), AoS
   const double *fin;     // sorted forces (hessian) or nullptr
@@ -182,6 +191,7 @@ struct PairArgs {
                          // that a slab cuts the same chunks - and sums in the same order - as the single domain
   Geom g;
   Phys p;
+  HaloWait halo;
 };
 int pair_grid_blocks();  // upper bound of the all-pairs kernel's CTAs (partials has at least this many rows)
 int pair_tile_grid(const Geom &g);  // CTAs of the tiled kernel (rows of partials it writes)

@@ -6,22 +6,25 @@
 // One velocity-Verlet step (md_nve_lj.py:178-192) is
 //   phase 1  kick + drift + wrap on the owned atoms; atoms that left the slab are packed (r, v, id) STRAIGHT INTO THE
 //            NEIGHBOUR'S receive buffer over NVLink (tens of atoms per face)
-//   phase 2  cell assignment of the atoms already held; arrivals appended and assigned; scan; counting sort; the
-//            first and last owned layer are packed -- per-cell counts + positions, already in cell order -- again
-//            straight into the neighbours' receive buffers (one layer per face: ~6e4 atoms = 1.4 MB at 2 M atoms/GPU)
-//   phase 3  halo layers unpacked behind the owned atoms ([owned | left halo | right halo]; the per-layer sentinels of
-//            the padded cell_start make that legal), full-stencil pair kernel on the owned rows (no force return
-//            traffic), kick, local sums.  The 12-double step records are all-reduced ONCE per run (NCCL).
+//   phase 2  ONE kernel waits for the neighbours' migration messages, appends the arrivals and assigns their cells;
+//            scan; counting sort; then the first and last owned layer -- positions, already in cell order, and their
+//            cell table -- are written STRAIGHT INTO THE NEIGHBOURS' POSITION ARRAYS AND CELL TABLES (their halo regions:
+//            one layer per face, ~6e4 atoms = 1.4 MB at 2 M atoms/GPU).  Nothing is unpacked on the receiving side.
+//   phase 3  the pair kernel starts at once on the rows that need no halo (interior x layers first) and only the CTAs
+//            that reach a boundary layer acquire the neighbours' stamps: the exchange is hidden behind ~85 % of the
+//            pair kernel.  Full stencil on the owned rows (no force return traffic).  The 12-double step records are
+//            all-reduced ONCE per run (NCCL).
 //
-// Transport.  The exchange is fused into the pack kernels: peer memory is mapped once (CUDA IPC between the one-process-
-// per-GPU ranks, plain pointers when several ranks are emulated in one process) and the pack kernels store over
-// NVLink 5 / NVSwitch into the neighbour's buffer; the CTA that finishes last publishes the message with a system-
-// scope release of a step stamp in the buffer's header, and the consumer's stream holds a one-thread kernel that
-// acquires that stamp.  No copy, no SM-hungry communication kernel, no host synchronisation per step.
-// Receive buffers are double-buffered by step parity; that is sufficient flow control because a rank cannot start
-// step s before it has consumed its neighbours' step s-1 messages, which they sent only after consuming the step s-2
-// messages that used the same parity.  (An NCCL send/recv version of this exchange measured 35 us latency per
-// exchange and could not overlap with the saturating pair kernel: profiles/r1_slab_history.md.)
+// Transport.  Peer memory is mapped once (CUDA IPC between the one-process-per-GPU ranks, plain pointers when several
+// ranks are emulated in one process); kernels store over NVLink 5 / NVSwitch into it, the CTA that finishes last
+// publishes a message with a system-scope release of a step stamp, consumers acquire that stamp.  No copy engine, no
+// SM-hungry communication kernel, no host synchronisation per step.
+// Flow control.  Migration buffers are double-buffered by step parity; the halo regions live in the double-buffered
+// position arrays (r[0], r[1] alternate every step on every rank).  A rank cannot start step s+1's halo writes before
+// it has consumed its neighbours' step s+1 migration messages, which they send only after their step-s pair kernel --
+// the last reader of the step-s halo data and of the (single) halo rows of the cell table -- has finished.
+// (An NCCL send/recv version of this exchange measured 35 us latency per exchange and could not overlap with the
+// saturating pair kernel: profiles/r1_slab_history.md.)
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
@@ -34,7 +37,23 @@ namespace atlj {
 
 constexpr int HDR_INTS = 16;  // 64-byte header of every message: [0] = number of atoms, [1] = step stamp (ready flag)
 
-__host__ __device__ static inline size_t halo_counts_ints(int sc) { return (((size_t)sc * sc + 15) / 16) * 16; }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// spins until the producer (another GPU) has published stamp in hdr[1]; false after timeout_ns (a neighbour that died
+// must not hang this GPU): the caller raises err[5] and every later kernel of the run becomes a no-op
+__device__ __forceinline__ bool acquire_stamp(const int *hdr, int stamp, unsigned long long timeout_ns) {
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hdr + 1) : "memory");
+    if (v == stamp) return true;
+    if (global_ns() - t0 > timeout_ns) return false;
+  }
+}
 
 __device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
   hdr[0] = count;
@@ -42,166 +61,122 @@ __device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(stamp) : "memory");
 }
 
-// the consumer side: spins until the producer (another GPU) has published the message of this step
-// (gives up after ~4e9 clocks, about 2 s, and raises err[5]: a neighbour that died must not hang this GPU)
-__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp, int *err) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const long long t0 = clock64();
-  for (const int *h : {hdr_a, hdr_b}) {
-    int v;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(h + 1) : "memory");
-      if (v == stamp) break;
-      if (clock64() - t0 > 4000000000ll) {
-        atomicOr(&err[5], 1);
-        return;
-      }
+// consumer side for the pair kernels that cannot wait themselves (first tiled kernel): one thread acquires both stamps
+__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp, unsigned long long timeout_ns,
+                                  int *err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || err[5]) return;
+  if (!acquire_stamp(hdr_a, stamp, timeout_ns) || !acquire_stamp(hdr_b, stamp, timeout_ns)) atomicOr(&err[5], 1);
+}
+
+// ---- phase 2: wait for the migration messages, append the arrivals behind the atoms already held, assign their cells --
+// (one launch: every CTA acquires the two stamps itself, then takes its share of the arrivals)
+constexpr int ARR_CTAS = 32, ARR_T = 256;
+__global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, const unsigned char *__restrict__ recv_left,
+                                                         const unsigned char *__restrict__ recv_right, int cap,
+                                                         int stamp, unsigned long long timeout_ns,
+                                                         double *__restrict__ r, double *__restrict__ v,
+                                                         int *__restrict__ id, const int *__restrict__ n_old_dev,
+                                                         long long own_cap, int *__restrict__ n_after,
+                                                         int *__restrict__ cellid, int *__restrict__ rank,
+                                                         int *__restrict__ cell_count, int *__restrict__ err) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    s_ok = err[5] == 0 && acquire_stamp(reinterpret_cast<const int *>(recv_left), stamp, timeout_ns) &&
+           acquire_stamp(reinterpret_cast<const int *>(recv_right), stamp, timeout_ns);
+    if (!s_ok) atomicOr(&err[5], 1);
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int n_old = *n_old_dev;
+  const int cl = min(*reinterpret_cast<const int *>(recv_left), cap);
+  const int cr = min(*reinterpret_cast<const int *>(recv_right), cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *n_after = n_old + cl + cr;
+    if ((long long)n_old + cl + cr > own_cap) atomicOr(&err[1], 1);
+  }
+  const double scd = (double)g.sc;
+  for (int k = blockIdx.x * ARR_T + threadIdx.x; k < cl + cr; k += ARR_CTAS * ARR_T) {
+    const bool right = k >= cl;
+    const long long dst = (long long)n_old + k;
+    if (dst >= own_cap) break;
+    const double *s = reinterpret_cast<const double *>((right ? recv_right : recv_left) + sizeof(int) * HDR_INTS) +
+                      7 * (size_t)(right ? k - cl : k);
+    const double x = s[0], y = s[1], z = s[2];  // wrapped by the sender
+#pragma unroll
+    for (int c = 0; c < 3; c++) r[3 * dst + c] = s[c], v[3 * dst + c] = s[3 + c];
+    id[dst] = (int)s[6];
+    // md_lj_ll_module.py:108, same separately rounded operations as cell_assign_kernel
+    const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(x, 0.5), scd));
+    const long long c1 = (long long)floor(__dmul_rn(__dadd_rn(y, 0.5), scd));
+    const long long c2 = (long long)floor(__dmul_rn(__dadd_rn(z, 0.5), scd));
+    const int lx = (int)c0 - g.x_lo + g.h;
+    const bool bad = c0 < 0 || c0 >= g.sc || c1 < 0 || c1 >= g.sc || c2 < 0 || c2 >= g.sc || lx < g.h ||
+                     lx >= g.h + g.nx_own;  // an arrival always belongs to an owned layer
+    if (bad) {
+      atomicOr(&err[0], 1);
+      cellid[dst] = -1, rank[dst] = 0;
+    } else {
+      const int cid = (lx * g.sc + (int)c1) * g.sc + (int)c2;
+      cellid[dst] = cid;
+      rank[dst] = atomicAdd(&cell_count[cid], 1);
     }
   }
 }
 
-// ---- phase 2: append the arrivals behind the atoms already held ----------------------------------------------------
-__global__ void __launch_bounds__(256) append_kernel(const unsigned char *__restrict__ recv_left,
-                                                     const unsigned char *__restrict__ recv_right, int cap,
-                                                     double *__restrict__ r, double *__restrict__ v,
-                                                     int *__restrict__ id, const int *__restrict__ n_old_dev,
-                                                     long long capacity, int *__restrict__ n_after,
-                                                     int *__restrict__ err) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_old = *n_old_dev;
-  const int cl = min(*reinterpret_cast<const int *>(recv_left), cap);
-  const int cr = min(*reinterpret_cast<const int *>(recv_right), cap);
-  if (t == 0) {
-    *n_after = n_old + cl + cr;
-    if ((long long)n_old + cl + cr > capacity) atomicOr(&err[1], 1);
-  }
-  if (t >= 2 * cap) return;
-  const int which = t >= cap, k = t - which * cap;
-  if (k >= (which ? cr : cl)) return;
-  const long long dst = (long long)n_old + (which ? cl : 0) + k;
-  if (dst >= capacity) return;
-  const double *s =
-      reinterpret_cast<const double *>((which ? recv_right : recv_left) + sizeof(int) * HDR_INTS) + 7 * (size_t)k;
-#pragma unroll
-  for (int c = 0; c < 3; c++) r[3 * dst + c] = s[c], v[3 * dst + c] = s[3 + c];
-  id[dst] = (int)s[6];
-}
-
-// first / last owned layer -> message in the left / right neighbour's buffer (blockIdx.y = direction): header,
-// per-cell counts, positions (already contiguous and in cell order).  done[dir] counts finished CTAs; the last one
-// publishes.  Thread (0,0,0) also moves the new owned count (end sentinel of the last owned layer) to n_own.
+// first / last owned layer -> the left / right neighbour's halo region (blockIdx.y = direction): positions (already
+// contiguous and in cell order) into its position array, the layer's cell table (rebased to where the positions land)
+// into the halo row of its cell_start.  done[dir] counts finished CTAs; the last one publishes the stamp in the
+// neighbour's halo header.  Thread (0,0,0) of direction 1 also moves the new owned count (end sentinel of the last
+// owned layer) to n_own.
 __global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, const int *__restrict__ cs,
-                                                        const double *__restrict__ r_sorted, unsigned char *to_left,
-                                                        unsigned char *to_right, int cap, int stamp,
-                                                        int *__restrict__ done, int *__restrict__ err,
-                                                        int *__restrict__ n_own, double *__restrict__ rec) {
+                                                        const double *__restrict__ r_sorted, double *dst_r_left,
+                                                        double *dst_r_right, int *dst_cs_left, int *dst_cs_right,
+                                                        int base_left, int base_right, int *hdr_left, int *hdr_right,
+                                                        int cap, int stamp, int *__restrict__ done,
+                                                        int *__restrict__ err, int *__restrict__ n_own,
+                                                        long long own_cap, double *__restrict__ rec) {
+  if (err[5]) return;
   const int sc2 = g.sc * g.sc;
   const int dir = blockIdx.y;
   const int lx = dir == 0 ? g.h : g.h + g.nx_own - 1;
   const int *row = cs + (size_t)lx * (sc2 + 1);
   if (dir == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
     *n_own = row[sc2];
+    if (row[sc2] > own_cap) atomicOr(&err[1], 1);
     if (rec) rec[11] = (double)row[sc2];
   }
-  int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
-  int *cnt = hdr + HDR_INTS;
-  double *pos = reinterpret_cast<double *>(cnt + halo_counts_ints(g.sc));
+  int *hdr = dir ? hdr_right : hdr_left;
+  int *dcs = dir ? dst_cs_right : dst_cs_left;
+  double *pos = dir ? dst_r_right : dst_r_left;
+  const int base = dir ? base_right : base_left;
   const int start = row[0];
   int total = row[sc2] - start;
-  if (total > cap) {
+  if (total > cap) {  // more atoms in the layer than the neighbour's halo region holds: flagged, message truncated
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&err[1], 1);
     total = cap;
   }
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-  for (long long c = gt; c < sc2; c += stride) cnt[c] = row[c + 1] - row[c];
-  // 16-byte stores towards the neighbour (the destination is 64-byte aligned; the source only 8-byte aligned)
+  for (long long c = gt; c <= sc2; c += stride) dcs[c] = base + min(row[c] - start, total);
+  // 16-byte stores towards the neighbour (base is even: the destination is 16-byte aligned; the source only 8-byte)
   const double *src = r_sorted + 3 * (size_t)start;
   const long long n2 = (3ll * total) >> 1;
   double2 *pos2 = reinterpret_cast<double2 *>(pos);
   for (long long e = gt; e < n2; e += stride) pos2[e] = make_double2(src[2 * e], src[2 * e + 1]);
   if (gt == 0 && ((3ll * total) & 1)) pos[3ll * total - 1] = src[3ll * total - 1];
+  // one system-scope fence per CTA, by the thread that counts the CTA as done: the barrier orders the other threads'
+  // stores before it (cumulativity), so they need no fence of their own
   __shared__ int s_last;
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&done[dir], 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&done[dir], 1) == (int)gridDim.x - 1;
+  }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     publish(hdr, total, stamp);
     done[dir] = 0;
   }
 }
-
-// ---- phase 3: a received layer becomes halo layer lx of the local grid ---------------------------------------------
-// cell_start of the layer = base + exclusive scan of the per-cell counts (one CTA; sc^2 <= 1024 * 64)
-__global__ void __launch_bounds__(1024) halo_cs_kernel(Geom g, const unsigned char *__restrict__ from_left,
-                                                       const unsigned char *__restrict__ from_right,
-                                                       const int *__restrict__ n_own_dev, int *__restrict__ cs,
-                                                       long long capacity, int cap, int *__restrict__ err) {
-  __shared__ int wsum[32];
-  // block 0: the left neighbour's layer -> local layer 0, behind the owned atoms; block 1: the right neighbour's
-  // layer -> local layer nxl-1, behind the left halo
-  const int lx = blockIdx.x == 0 ? 0 : g.nxl - 1;
-  const unsigned char *buf = blockIdx.x == 0 ? from_left : from_right;
-  const unsigned char *before = blockIdx.x == 0 ? nullptr : from_left;
-  const int n_own = *n_own_dev;
-  const int sc2 = g.sc * g.sc;
-  const int *hdr = reinterpret_cast<const int *>(buf);
-  const int *cnt = hdr + HDR_INTS;
-  int base = n_own + (before ? min(*reinterpret_cast<const int *>(before), cap) : 0);
-  const int per = (sc2 + 1023) / 1024;
-  const int c0 = threadIdx.x * per;
-  int sum = 0;
-  for (int k = 0; k < per; k++)
-    if (c0 + k < sc2) sum += cnt[c0 + k];
-  int incl = sum;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    int s = wsum[lane], si = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) si += t;
-    }
-    wsum[lane] = si - s;
-  }
-  __syncthreads();
-  int off = base + wsum[w] + incl - sum;
-  int *row = cs + (size_t)lx * (sc2 + 1);
-  for (int k = 0; k < per; k++) {
-    if (c0 + k < sc2) {
-      row[c0 + k] = off;
-      off += cnt[c0 + k];
-      if (c0 + k == sc2 - 1) {
-        row[sc2] = off;
-        if (off > capacity || off - base != min(hdr[0], cap)) atomicOr(&err[1], 1);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) halo_copy_kernel(Geom g, const unsigned char *__restrict__ from_left,
-                                                        const unsigned char *__restrict__ from_right,
-                                                        const int *__restrict__ n_own_dev, int cap,
-                                                        long long capacity, double *__restrict__ r_sorted) {
-  const unsigned char *buf = blockIdx.y == 0 ? from_left : from_right;
-  const unsigned char *before = blockIdx.y == 0 ? nullptr : from_left;
-  const int n_own = *n_own_dev;
-  const int *hdr = reinterpret_cast<const int *>(buf);
-  const double *pos = reinterpret_cast<const double *>(hdr + HDR_INTS + halo_counts_ints(g.sc));
-  const long long base = n_own + (before ? min(*reinterpret_cast<const int *>(before), cap) : 0);
-  long long total = min(hdr[0], cap);
-  if (base + total > capacity) total = capacity - base > 0 ? capacity - base : 0;
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = gt; e < 3 * total; e += stride) r_sorted[3 * base + e] = pos[e];
-}
-
 
 // ---- NCCL (only the per-run all-reduce of the step records), bound at run time -------------------------------------
 struct NcclApi {
@@ -257,18 +232,14 @@ static int nccl_load() {
     }                                                                                                   \
   } while (0)
 
-// ---- receive arena: [kind: migration, halo][from: left, right][parity] ------------------------------------------------
-static inline size_t arena_off(const MgState &m, int kind, int from, int parity) {
-  const size_t mig = m.mig_bytes, halo = m.halo_bytes;
-  return kind == 0 ? (size_t)(2 * from + parity) * mig : 4 * mig + (size_t)(2 * from + parity) * halo;
+// ---- receive arena: migration [from: left, right][parity], then the two halo headers [from: left, right] ----------------
+static inline unsigned char *mig_recv(unsigned char *arena, const MgState &m, int from, int parity) {
+  return arena + (size_t)(2 * from + parity) * m.mig_bytes;
 }
-static inline unsigned char *my_recv(const MgState &m, int kind, int from, int parity) {
-  return m.arena + arena_off(m, kind, from, parity);
+static inline int *halo_hdr(unsigned char *arena, const MgState &m, int from) {
+  return reinterpret_cast<int *>(arena + 4 * m.mig_bytes + (size_t)from * sizeof(int) * HDR_INTS);
 }
 // where my message towards `dir` (0 = left, 1 = right) lands: the neighbour's "from the other side" buffer
-static inline unsigned char *peer_recv(const MgState &m, int kind, int dir, int parity) {
-  return m.peer_arena[dir] + arena_off(m, kind, 1 - dir, parity);
-}
 
 // device-side row count of the tiled LJ kernel's partials (null for the other pair kernels)
 static const int *tile2_rows(atlj_sim *s) {
@@ -286,35 +257,28 @@ static int phase1(atlj_sim *s, double dt, bool first_kick, double *rec_prev, int
   const int par = (int)(m.step & 1);
   SlabArgs sl;
   sl.n_dev = m.cnt_dev + 1, sl.id = s->id[s->cur];
-  sl.to_left = peer_recv(m, 0, 0, par), sl.to_right = peer_recv(m, 0, 1, par);
+  sl.to_left = mig_recv(m.peer_arena[0], m, 1, par), sl.to_right = mig_recv(m.peer_arena[1], m, 0, par);
   sl.mig_cap = (int)m.mig_cap, sl.stamp = (int)(m.step + 1), sl.mig_cnt = m.cnt_dev + 4;
   Timer::begin(s, 2);
-  const int nb = launch_kdk_assign(s->st, s->g, (int)s->cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
-                                   first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev, s->p.model, &sl,
-                                   tile2_rows(s));
+  const int nb = launch_kdk_assign(s->st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt,
+                                   s->p.box, first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev,
+                                   s->p.model, &sl, tile2_rows(s));
   Timer::end(s);
   return nb < 0 ? nb : ATLJ_OK;
 }
 
-// phase 2: arrivals appended and assigned, scan, counting sort, boundary layers packed into the neighbours' buffers
+// phase 2: arrivals appended and assigned, scan, counting sort, boundary layers written into the neighbours' halo regions
 static int phase2(atlj_sim *s, double *rec) {
   int rc;
   MgState &m = s->mg;
-  const int cap = (int)m.mig_cap, nup = (int)s->cap, par = (int)(m.step & 1), stamp = (int)(m.step + 1);
+  const int cap = (int)m.mig_cap, nup = (int)m.own_cap, par = (int)(m.step & 1), stamp = (int)(m.step + 1);
   const int cur = s->cur, alt = 1 - cur;
   Timer::begin(s, 4);
-  const unsigned char *ml = my_recv(m, 0, 0, par), *mr = my_recv(m, 0, 1, par);
-  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(ml), reinterpret_cast<const int *>(mr), stamp,
-                                         s->cb.err);
+  arrivals_kernel<<<ARR_CTAS, ARR_T, 0, s->st>>>(s->g, mig_recv(m.arena, m, 0, par), mig_recv(m.arena, m, 1, par), cap,
+                                                  stamp, m.timeout_ns, s->r[cur], s->v[cur], s->id[cur], m.cnt_dev + 1,
+                                                  (long long)m.own_cap, m.cnt_dev, s->cb.cellid, s->cb.rank,
+                                                  s->cb.cell_count, s->cb.err);
   ATLJ_LAUNCHED();
-  Timer::end(s);
-  Timer::begin(s, 3);
-  append_kernel<<<(2 * cap + 255) / 256, 256, 0, s->st>>>(ml, mr, cap, s->r[cur], s->v[cur], s->id[cur], m.cnt_dev + 1,
-                                                         (long long)s->cap, m.cnt_dev, s->cb.err);
-  ATLJ_LAUNCHED();
-  if ((rc = launch_cell_assign(s->st, s->g, s->r[cur], s->r[cur], 2 * cap, false, 0.0, s->cb, nullptr, m.cnt_dev, true,
-                               m.cnt_dev + 1)))
-    return rc;
   Timer::end(s);
   Timer::begin(s, 1);
   if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
@@ -323,10 +287,17 @@ static int phase2(atlj_sim *s, double *rec) {
     return rc;
   Timer::end(s);
   s->cur = alt;
+  // my first layer is the left neighbour's RIGHT halo (its local layer nxl - 1, behind its left halo region); my last
+  // layer is the right neighbour's LEFT halo (its local layer 0).  All ranks share own_cap / halo_cap and flip their
+  // position buffers in step, so the neighbour's sorted buffer of this step is its r[alt] as well.
+  const size_t sc2p = (size_t)s->g.sc * s->g.sc + 1;
+  const int base_left = (int)(m.own_cap + m.halo_cap), base_right = (int)m.own_cap;
   Timer::begin(s, 5);
-  halo_pack_kernel<<<dim3(ATLJ_HALO_PACK_CTAS, 2), 256, 0, s->st>>>(s->g, s->cb.cell_start, s->r[alt], peer_recv(m, 1, 0, par),
-                                                    peer_recv(m, 1, 1, par), (int)m.halo_cap, stamp, m.cnt_dev + 8,
-                                                    s->cb.err, m.cnt_dev + 1, rec);
+  halo_pack_kernel<<<dim3(ATLJ_HALO_PACK_CTAS, 2), 256, 0, s->st>>>(
+      s->g, s->cb.cell_start, s->r[alt], m.peer_r[0][alt] + 3 * (size_t)base_left, m.peer_r[1][alt] + 3 * (size_t)base_right,
+      m.peer_cs[0] + (size_t)(m.peer_nxl[0] - 1) * sc2p, m.peer_cs[1], base_left, base_right,
+      halo_hdr(m.peer_arena[0], m, 1), halo_hdr(m.peer_arena[1], m, 0), (int)m.halo_cap, stamp, m.cnt_dev + 8, s->cb.err,
+      m.cnt_dev + 1, (long long)m.own_cap, rec);
   ATLJ_LAUNCHED();
   Timer::end(s);
   return ATLJ_OK;
@@ -342,31 +313,30 @@ static PairArgs pair_args(atlj_sim *s) {
   return a;
 }
 
-// phase 3: the received layers become the halo layers 0 and nxl-1 of the local grid, behind the owned atoms; pair
-// kernel over the owned rows.  -> rows of partials written (the record is finished by the next phase 1 or by tail())
+// phase 3: pair kernel over the owned rows; the halo layers 0 and nxl-1 were written by the neighbours, and the kernel
+// itself acquires their stamps when it reaches a boundary layer.  -> rows of partials written (the record is finished by
+// the next phase 1 or by tail())
 static int phase3(atlj_sim *s) {
   MgState &m = s->mg;
-  const Geom &g = s->g;
-  const int par = (int)(m.step & 1), stamp = (int)(m.step + 1);
-  const int *n_dev = m.cnt_dev + 1;
-  const unsigned char *hl = my_recv(m, 1, 0, par), *hr = my_recv(m, 1, 1, par);
-  Timer::begin(s, 6);
-  wait_stamp_kernel<<<1, 32, 0, s->st>>>(reinterpret_cast<const int *>(hl), reinterpret_cast<const int *>(hr), stamp,
-                                         s->cb.err);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  Timer::begin(s, 3);
-  halo_cs_kernel<<<2, 1024, 0, s->st>>>(g, hl, hr, n_dev, s->cb.cell_start, (long long)s->cap, (int)m.halo_cap,
-                                        s->cb.err);
-  ATLJ_LAUNCHED();
-  halo_copy_kernel<<<dim3(444, 2), 256, 0, s->st>>>(g, hl, hr, n_dev, (int)m.halo_cap, (long long)s->cap, s->r[s->cur]);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  const PairArgs a = pair_args(s);
-  Timer::begin(s, 0);
-  const int nb = sim_tile2(s) ? launch_pair_tile2(s->st, a, s->cb.err + 2)
-                                                                   : launch_pair_tile(s->st, a, false);
-  Timer::end(s);
+  const int stamp = (int)(m.step + 1);
+  PairArgs a = pair_args(s);
+  const int *hl = halo_hdr(m.arena, m, 0), *hr = halo_hdr(m.arena, m, 1);
+  int nb;
+  if (sim_tile2(s)) {
+    a.halo.stamp_left = hl, a.halo.stamp_right = hr, a.halo.stamp = stamp, a.halo.timeout_ns = m.timeout_ns;
+    a.halo.err = s->cb.err;
+    Timer::begin(s, 0);
+    nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
+    Timer::end(s);
+  } else {
+    Timer::begin(s, 6);
+    wait_stamp_kernel<<<1, 32, 0, s->st>>>(hl, hr, stamp, m.timeout_ns, s->cb.err);
+    ATLJ_LAUNCHED();
+    Timer::end(s);
+    Timer::begin(s, 0);
+    nb = launch_pair_tile(s->st, a, false);
+    Timer::end(s);
+  }
   m.step++;
   return nb;
 }
@@ -377,7 +347,8 @@ static int tail(atlj_sim *s, double dt, double *rec, int nb) {
   if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s))))
     return rc;
   Timer::begin(s, 2);
-  rc = launch_kick_sums(s->st, 3ll * s->cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->cb.err + 4, s->mg.cnt_dev + 1);
+  rc = launch_kick_sums(s->st, 3ll * s->mg.own_cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->cb.err + 4,
+                        s->mg.cnt_dev + 1);
   Timer::end(s);
   return rc;
 }
@@ -397,10 +368,9 @@ static int pull_n(atlj_sim *s) {
 
 static void mg_free(atlj_sim *s) {
   MgState &m = s->mg;
-  for (int d = 0; d < 2; d++) {
-    if (m.peer_ipc[d]) cudaIpcCloseMemHandle(m.peer_arena[d]);
-    m.peer_arena[d] = nullptr, m.peer_ipc[d] = false;
-  }
+  for (int k = 0; k < m.n_ipc_mapped; k++) cudaIpcCloseMemHandle(m.ipc_mapped[k]);
+  m.n_ipc_mapped = 0;
+  for (int d = 0; d < 2; d++) m.peer_arena[d] = nullptr, m.peer_r[d][0] = m.peer_r[d][1] = nullptr, m.peer_cs[d] = nullptr;
   cudaFree(m.arena);
   m.arena = nullptr;
   cudaFree(m.cnt_dev);
@@ -413,6 +383,16 @@ static void mg_free(atlj_sim *s) {
 }
 void sim_mg_destroy(atlj_sim *s) { mg_free(s); }
 
+static const unsigned long long MG_MAGIC = 0x61746c6a6d670002ull;  // the signature of api.cu's dev_alloc_ipc
+
+// what a neighbour needs to write into this rank's memory (exchanged once, by any means)
+struct MgBlob {
+  cudaIpcMemHandle_t arena, r0, r1, cs;
+  unsigned long long arena_bytes, r_bytes, cs_bytes;
+  long long own_cap, halo_cap, mig_cap;
+  int nxl, sc;
+};
+
 }  // namespace atlj
 
 using namespace atlj;
@@ -424,28 +404,30 @@ int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap) {
     set_error("mg_enable: configure the sim with a proper sub-range of x layers first");
     return ATLJ_ERR_ARG;
   }
-  if ((long long)s->g.sc * s->g.sc > 1024ll * 64) {
-    set_error("mg_enable: sc = %d too large for the one-CTA halo scan", s->g.sc);
+  halo_cap += halo_cap & 1;  // even: the neighbours' 16-byte stores into the halo regions stay aligned
+  int64_t own_cap = s->cap - 2 * halo_cap;
+  own_cap -= own_cap & 1;
+  if (own_cap < s->n || own_cap < 2) {
+    set_error("mg_enable: capacity %lld cannot hold %lld owned atoms and two halo layers of %lld", (long long)s->cap,
+              (long long)s->n, (long long)halo_cap);
     return ATLJ_ERR_ARG;
   }
   mg_free(s);
   MgState &m = s->mg;
-  m.mig_cap = mig_cap, m.halo_cap = halo_cap;
+  m.mig_cap = mig_cap, m.halo_cap = halo_cap, m.own_cap = own_cap;
+  const char *to = getenv("ATLJ_PEER_TIMEOUT_MS");
+  if (to && atof(to) > 0) m.timeout_ns = (unsigned long long)(atof(to) * 1e6);
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };
   m.mig_bytes = up(sizeof(int) * HDR_INTS + sizeof(double) * 7 * (size_t)mig_cap);
-  m.halo_bytes = up(sizeof(int) * (HDR_INTS + halo_counts_ints(s->g.sc)) + sizeof(double) * 3 * (size_t)halo_cap);
-  // 256 B tail holds a magic word the neighbours verify after mapping.  At least 8 MB and a multiple of 2 MB, so that
+  // 256 B tail holds a signature the neighbours verify after mapping.  At least 8 MB and a multiple of 2 MB, so that
   // the arena is an allocation of its own: cudaIpcGetMemHandle exports the whole underlying allocation, and small
   // cudaMalloc blocks are carved out of shared 2 MB pages.
-  m.arena_bytes = 4 * m.mig_bytes + 4 * m.halo_bytes + 256;
-  const size_t alloc = ((m.arena_bytes > (8u << 20) ? m.arena_bytes : (8u << 20)) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
-  ATLJ_CUDA(cudaMalloc((void **)&m.arena, alloc));
-  ATLJ_CUDA(cudaMemsetAsync(m.arena, 0, alloc, s->st));
-  {
-    const unsigned long long magic = 0x61746c6a6d670001ull;  // "atljmg" 1
-    ATLJ_CUDA(cudaMemcpyAsync(m.arena + m.arena_bytes - 256, &magic, sizeof(magic), cudaMemcpyHostToDevice, s->st));
-    ATLJ_CUDA(cudaStreamSynchronize(s->st));
-  }
+  m.arena_bytes = 4 * m.mig_bytes + 2 * sizeof(int) * HDR_INTS + 256;
+  m.arena_bytes = ((m.arena_bytes > (8u << 20) ? m.arena_bytes : (8u << 20)) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  ATLJ_CUDA(cudaMalloc((void **)&m.arena, m.arena_bytes));
+  ATLJ_CUDA(cudaMemsetAsync(m.arena, 0, m.arena_bytes, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(m.arena + m.arena_bytes - 256, &MG_MAGIC, sizeof(MG_MAGIC), cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
   ATLJ_CUDA(cudaMalloc((void **)&m.cnt_dev, 16 * sizeof(int)));
   ATLJ_CUDA(cudaMemsetAsync(m.cnt_dev, 0, 16 * sizeof(int), s->st));
   ATLJ_CUDA(cudaHostAlloc((void **)&m.cnt_host, 16 * sizeof(int), cudaHostAllocDefault));
@@ -461,53 +443,93 @@ void atlj_sim_set_total(atlj_sim *s, int64_t n_total) {
   if (s) s->n_total = n_total;
 }
 
-/* receive arena of this rank: device pointer (same-process peers) and size */
-void *atlj_sim_mg_arena(atlj_sim *s) { return (s && s->mg.on) ? s->mg.arena : nullptr; }
-int64_t atlj_sim_mg_arena_bytes(atlj_sim *s) { return (s && s->mg.on) ? (int64_t)s->mg.arena_bytes : -1; }
-
 /* peers living in the same process (several ranks emulated on one GPU): plain device pointers */
-int atlj_sim_mg_set_peers(atlj_sim *s, void *left_arena, void *right_arena) {
-  if (!s || !s->mg.on || !left_arena || !right_arena) return ATLJ_ERR_ARG;
-  s->mg.peer_arena[0] = (unsigned char *)left_arena, s->mg.peer_arena[1] = (unsigned char *)right_arena;
-  s->mg.peer_ipc[0] = s->mg.peer_ipc[1] = false;
-  return ATLJ_OK;
-}
-
-/* peers in other processes (one process per GPU): CUDA IPC handle of the arena, 64 bytes */
-int atlj_sim_mg_ipc_handle(atlj_sim *s, char *out64) {
-  if (!s || !s->mg.on || !out64) return ATLJ_ERR_ARG;
-  cudaIpcMemHandle_t h;
-  ATLJ_CUDA(cudaIpcGetMemHandle(&h, s->mg.arena));
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  memcpy(out64, &h, 64);
-  return ATLJ_OK;
-}
-int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left64, const char *right64) {
-  if (!s || !s->mg.on || !left64 || !right64) return ATLJ_ERR_ARG;
+int atlj_sim_mg_set_peers(atlj_sim *s, atlj_sim *left, atlj_sim *right) {
+  if (!s || !s->mg.on || !left || !right || !left->mg.on || !right->mg.on) return ATLJ_ERR_ARG;
   MgState &m = s->mg;
-  const bool same = memcmp(left64, right64, 64) == 0;  // two ranks: both neighbours are the one peer
+  atlj_sim *peer[2] = {left, right};
   for (int d = 0; d < 2; d++) {
-    if (d == 1 && same) {
-      m.peer_arena[1] = m.peer_arena[0], m.peer_ipc[1] = false;
-      break;
+    const MgState &pm = peer[d]->mg;
+    if (pm.own_cap != m.own_cap || pm.halo_cap != m.halo_cap || pm.mig_cap != m.mig_cap || peer[d]->g.sc != s->g.sc) {
+      set_error("mg_set_peers: all ranks must use the same capacities and cell grid");
+      return ATLJ_ERR_ARG;
     }
-    cudaIpcMemHandle_t h;
-    memcpy(&h, d == 0 ? left64 : right64, 64);
-    void *p = nullptr;
-    ATLJ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    m.peer_arena[d] = (unsigned char *)p, m.peer_ipc[d] = true;
-    unsigned long long magic = 0;  // the mapping must show the neighbour's arena, not some other part of its memory
-    ATLJ_CUDA(cudaMemcpy(&magic, m.peer_arena[d] + m.arena_bytes - 256, sizeof(magic), cudaMemcpyDeviceToHost));
-    if (magic != 0x61746c6a6d670001ull) {
-      set_error("mg_ipc_open: the mapped peer buffer does not carry the arena signature (IPC mapping offset)");
-      return ATLJ_ERR_CUDA;
-    }
+    m.peer_arena[d] = pm.arena, m.peer_r[d][0] = peer[d]->r[0], m.peer_r[d][1] = peer[d]->r[1];
+    m.peer_cs[d] = peer[d]->cb.cell_start, m.peer_nxl[d] = peer[d]->g.nxl;
   }
   return ATLJ_OK;
 }
 
+/* peers in other processes (one process per GPU): the blob names this rank's receive arena, position buffers and
+ * cell table (CUDA IPC handles) and its layout */
+int64_t atlj_sim_mg_blob_bytes(void) { return (int64_t)sizeof(MgBlob); }
+
+int atlj_sim_mg_ipc_blob(atlj_sim *s, char *out) {
+  if (!s || !s->mg.on || !out) return ATLJ_ERR_ARG;
+  if (!s->ipc_safe) {
+    set_error("mg_ipc_blob: create the sim with ATLJ_SIM_IPC so that its buffers can be exported");
+    return ATLJ_ERR_ARG;
+  }
+  MgBlob b;
+  memset(&b, 0, sizeof(b));
+  ATLJ_CUDA(cudaIpcGetMemHandle(&b.arena, s->mg.arena));
+  ATLJ_CUDA(cudaIpcGetMemHandle(&b.r0, s->r[0]));
+  ATLJ_CUDA(cudaIpcGetMemHandle(&b.r1, s->r[1]));
+  ATLJ_CUDA(cudaIpcGetMemHandle(&b.cs, s->cb.cell_start));
+  b.arena_bytes = s->mg.arena_bytes, b.r_bytes = s->r_alloc_bytes, b.cs_bytes = s->cs_alloc_bytes;
+  b.own_cap = s->mg.own_cap, b.halo_cap = s->mg.halo_cap, b.mig_cap = s->mg.mig_cap, b.nxl = s->g.nxl, b.sc = s->g.sc;
+  memcpy(out, &b, sizeof(b));
+  return ATLJ_OK;
+}
+
+int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_blob) {
+  if (!s || !s->mg.on || !left_blob || !right_blob) return ATLJ_ERR_ARG;
+  MgState &m = s->mg;
+  const bool same = memcmp(left_blob, right_blob, sizeof(MgBlob)) == 0;  // two ranks: both neighbours are the one peer
+  for (int d = 0; d < 2; d++) {
+    if (d == 1 && same) {
+      m.peer_arena[1] = m.peer_arena[0], m.peer_r[1][0] = m.peer_r[0][0], m.peer_r[1][1] = m.peer_r[0][1];
+      m.peer_cs[1] = m.peer_cs[0], m.peer_nxl[1] = m.peer_nxl[0];
+      break;
+    }
+    MgBlob b;
+    memcpy(&b, d == 0 ? left_blob : right_blob, sizeof(b));
+    if (b.own_cap != m.own_cap || b.halo_cap != m.halo_cap || b.mig_cap != m.mig_cap || b.sc != s->g.sc) {
+      set_error("mg_ipc_open: all ranks must use the same capacities and cell grid");
+      return ATLJ_ERR_ARG;
+    }
+    struct {
+      cudaIpcMemHandle_t *h;
+      unsigned long long bytes;
+      void **out;
+    } maps[4] = {{&b.arena, b.arena_bytes, (void **)&m.peer_arena[d]},
+                 {&b.r0, b.r_bytes, (void **)&m.peer_r[d][0]},
+                 {&b.r1, b.r_bytes, (void **)&m.peer_r[d][1]},
+                 {&b.cs, b.cs_bytes, (void **)&m.peer_cs[d]}};
+    for (auto &mp : maps) {
+      void *p = nullptr;
+      ATLJ_CUDA(cudaIpcOpenMemHandle(&p, *mp.h, cudaIpcMemLazyEnablePeerAccess));
+      m.ipc_mapped[m.n_ipc_mapped++] = p;
+      unsigned long long magic = 0;  // the mapping must show the neighbour's buffer, not some other part of its memory
+      ATLJ_CUDA(cudaMemcpy(&magic, (unsigned char *)p + mp.bytes - 256, sizeof(magic), cudaMemcpyDeviceToHost));
+      if (magic != MG_MAGIC) {
+        set_error("mg_ipc_open: a mapped peer buffer does not carry its signature (IPC mapping offset)");
+        return ATLJ_ERR_CUDA;
+      }
+      *mp.out = p;
+    }
+    m.peer_nxl[d] = b.nxl;
+  }
+  return ATLJ_OK;
+}
+
+static bool mg_ready(const atlj_sim *s) {
+  return s && s->mg.on && s->mg.peer_arena[0] && s->mg.peer_arena[1] && s->mg.peer_r[0][0] && s->mg.peer_r[1][0] &&
+         s->mg.peer_cs[0] && s->mg.peer_cs[1];
+}
+
 int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
-  if (!s || !s->mg.on || !s->mg.peer_arena[0]) return ATLJ_ERR_ARG;
+  if (!mg_ready(s)) return ATLJ_ERR_ARG;
   int rc = sim_ensure_rec(s, 1);
   if (rc || (rc = push_n(s))) return rc;
   ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
@@ -516,13 +538,13 @@ int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
   return ATLJ_OK;
 }
 int atlj_sim_mg_phase2(atlj_sim *s) {
-  if (!s || !s->mg.on) return ATLJ_ERR_ARG;
+  if (!mg_ready(s)) return ATLJ_ERR_ARG;
   int rc = phase2(s, s->rec_dev);
   if (rc || (rc = pull_n(s))) return rc;
   return sim_check_flags(s);
 }
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
-  if (!s || !s->mg.on) return ATLJ_ERR_ARG;
+  if (!mg_ready(s)) return ATLJ_ERR_ARG;
   const int nb = phase3(s);
   if (nb < 0) return nb;
   int rc = tail(s, dt, s->rec_dev, nb);
@@ -553,7 +575,7 @@ int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128) {
 }
 
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
-  if (!s || !s->mg.on || !s->mg.comm || !s->mg.peer_arena[0] || !s->mg.peer_arena[1] || nsteps < 0) {
+  if (!mg_ready(s) || !s->mg.comm || nsteps < 0) {
     set_error("run_nve_mg: enable the slab, map the neighbours' buffers and connect first");
     return ATLJ_ERR_ARG;
   }

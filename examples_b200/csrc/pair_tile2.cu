@@ -123,6 +123,12 @@ __device__ unsigned long long g_t2stats[8];
 __device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
 __device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2 *>(&u); }
 
+__device__ __forceinline__ unsigned long long halo_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
   __shared__ int wsum[U_NT / 32];
   __shared__ unsigned s_q2max;
-  __shared__ int s_maxwin, s_item;
+  __shared__ int s_maxwin, s_item, s_halo;
 
   const Geom g = a.g;
   const Phys p = a.p;
@@ -236,22 +242,63 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const double sci = 1.0 / (double)sc;
   const __half *hq = reinterpret_cast<const __half *>(hp);
   const unsigned ux_s = (unsigned)__cvta_generic_to_shared(ux);
+  // Slab ranks: the x layers that read a halo layer (the first and the last owned one) come LAST in the item order,
+  // so that the neighbours' halo writes are hidden behind the interior layers; a CTA acquires the neighbours' stamps
+  // when it takes its first boundary item.
+  const int nbl = g.h ? min(2, g.nx_own) : 0;  // boundary layers
+  const int nrp_int = (g.nx_own - nbl) * nyb, nrp_bnd = nbl * nyb;
+  if (a.halo.err && a.halo.err[5]) return;  // a neighbour's message timed out earlier in this run
+  if (tid == 0) s_halo = a.halo.stamp_left == nullptr;
 
   for (;;) {
     // ---- next work item ----------------------------------------------------------------------------------------
     __syncthreads();
     if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u, s_maxwin = 0;
+    const int halo_ok = s_halo;  // read between the two barriers: thread 0 only writes it after the second one
     __syncthreads();
     const int item = s_item;
     const int nitems = tab[0] * nrp;
     if (item == 0 && tid == 0) *rows_out = nitems;
     if (item >= nitems) break;
-    const int grp = item / nrp, rp = item - grp * nrp;
+    int grp, xo, yb;  // item -> (group of chunks, owned x layer, row pair of that layer)
+    const int n_int = tab[0] * nrp_int;
+    if (item < n_int) {
+      grp = item / nrp_int;
+      const int q = item - grp * nrp_int;
+      xo = q / nyb, yb = q - xo * nyb;
+      xo += nbl ? 1 : 0;
+    } else {
+      const int t = item - n_int;
+      grp = t / nrp_bnd;
+      const int q = t - grp * nrp_bnd;
+      xo = q / nyb, yb = q - xo * nyb;
+      xo = xo ? g.nx_own - 1 : 0;
+      if (!halo_ok) {  // CTA-uniform
+        if (tid == 0) {
+          const unsigned long long t0 = halo_now_ns();
+          int ok = 0;
+          for (;;) {
+            int vl, vr;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(vl) : "l"(a.halo.stamp_left + 1) : "memory");
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(vr) : "l"(a.halo.stamp_right + 1) : "memory");
+            if (vl == a.halo.stamp && vr == a.halo.stamp) {
+              ok = 1;
+              break;
+            }
+            if (halo_now_ns() - t0 > a.halo.timeout_ns) break;
+          }
+          if (!ok) atomicOr(&a.halo.err[5], 1);
+          s_halo = ok ? 1 : -1;
+        }
+        __syncthreads();
+        if (s_halo < 0) break;  // timed out: the run is void (err[5]); leave without touching the halo data
+      }
+    }
+    const int rp = xo * nyb + yb;
     if (grp >= tab[16 + rp]) {  // this row pair has fewer items than the longest one: an all-zero row of partials
       if (tid < 8) a.partials[8 * (size_t)item + tid] = 0.0;
       continue;
     }
-    const int xo = rp / nyb, yb = rp - xo * nyb;  // owned x layer, row pair of this item
     const int lx = g.h + xo, y0 = 2 * yb;
     const bool two = (y0 + 1 < sc);
     // atoms [gA, gB) of the row pair's interleaved order

@@ -5,24 +5,36 @@
 #include "common.cuh"
 
 // slab decomposition state (mg.cu)
+// Per-atom arrays of a slab rank: [0, own_cap) owned atoms (cell order), [own_cap, own_cap + halo_cap) the left
+// neighbour's last layer (local layer 0), [own_cap + halo_cap, cap) the right neighbour's first layer (local layer
+// nxl - 1).  The halo regions of r[0], r[1] and the halo rows of cell_start are WRITTEN BY THE NEIGHBOURS (peer memory,
+// NVLink); only migrating atoms (r, v, id: a few hundred per face and step) go through the message arena.
 struct MgState {
   bool on = false;
   int rank = 0, world = 1;
-  int64_t mig_cap = 0, halo_cap = 0;  // atoms per message
-  size_t mig_bytes = 0, halo_bytes = 0, arena_bytes = 0;
-  unsigned char *arena = nullptr;                       // my receive buffers: [migration|halo][from left|right][parity]
-  unsigned char *peer_arena[2] = {nullptr, nullptr};    // the left / right neighbour's arena, mapped into this process
-  bool peer_ipc[2] = {false, false};                    // mapped with cudaIpcOpenMemHandle (to be closed)
+  int64_t mig_cap = 0, halo_cap = 0, own_cap = 0;  // atoms
+  size_t mig_bytes = 0, arena_bytes = 0;
+  unsigned char *arena = nullptr;  // my receive buffers: migration [from left|right][parity], then 2 halo headers
+  // the neighbours' memory, mapped into this process (CUDA IPC) or plain pointers (ranks emulated in one process)
+  unsigned char *peer_arena[2] = {nullptr, nullptr};
+  double *peer_r[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [left|right][buffer]
+  int *peer_cs[2] = {nullptr, nullptr};
+  int peer_nxl[2] = {0, 0};
+  void *ipc_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // to be closed
+  int n_ipc_mapped = 0;
   long long step = 0;                                   // exchange counter: parity selects the buffer, step+1 = stamp
   int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended, [1] owned atoms (after the sort),
                             // [4..6] migration slot counters + CTAs done, [8], [9] halo pack CTAs done
   int *cnt_host = nullptr;  // pinned mirror of cnt_dev[1]
   void *comm = nullptr;     // ncclComm_t (all-reduce of the step records)
+  unsigned long long timeout_ns = 30000000000ull;  // a neighbour's message: give up after this long (ATLJ_PEER_TIMEOUT_MS)
 };
 
 struct atlj_sim {
   cudaStream_t st = nullptr;
   int64_t cap = 0;  // atom capacity of every per-atom buffer
+  bool ipc_safe = false;     // r[0], r[1], cell_start are allocations of their own (exportable with CUDA IPC)
+  size_t r_alloc_bytes = 0, cs_alloc_bytes = 0;  // their sizes when ipc_safe (a signature sits in the last 256 bytes)
   int64_t n = 0;    // owned atoms
   int64_t n_total = 0;       // atoms of the whole system (all ranks); indexes injected noise by global id
   long long step_count = 0;  // steps taken so far (counter of the device RNG)

@@ -27,7 +27,8 @@ class Simulation:
     """One GPU's worth of atoms.  `model` is 'lj' (cut-and-shifted LJ, totals cut,pot,vir,lap) or 'wca'
     (WCA + Lees-Edwards, totals pot,vir,lap,pyx)."""
 
-    def __init__(self, box, r_cut, r, v=None, model="lj", ids=None, capacity=None, stream=0, slab=None, sc=None):
+    def __init__(self, box, r_cut, r, v=None, model="lj", ids=None, capacity=None, stream=0, slab=None, sc=None,
+                 ipc=False):
         L = _lib.lib()
         self.model = MODEL_LJ if model == "lj" else MODEL_WCA
         if self.model == MODEL_WCA:
@@ -50,7 +51,7 @@ class Simulation:
             self.sc = int(sc)
         x_lo, x_hi = (0, max(self.sc, 1)) if slab is None else slab
         cap = int(capacity if capacity is not None else n + n // 8 + 1024)
-        self._h = L.atlj_sim_create(cap, C.c_void_p(stream))
+        self._h = L.atlj_sim_create_ex(cap, C.c_void_p(stream), 1 if ipc else 0)   # 1 = ATLJ_SIM_IPC
         if not self._h:
             raise _lib.AtljError("atlj_sim_create failed: " + L.atlj_last_error().decode())
         _lib.check(L.atlj_sim_configure(self._h, self.model, self.box, self.r_cut_box_sq, self.box_sq, self.pot_cut,

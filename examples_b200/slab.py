@@ -48,9 +48,12 @@ def halo_mask(r, sc, x_lo, x_hi):
 
 
 def capacities(n_total, sc, nx_own, slack=1.5):
-    """Per-rank buffer sizes (atoms): owned + halo capacity, migration message, halo message."""
+    """Per-rank buffer sizes (atoms): owned + halo capacity, migration message, halo layer.  Every rank of a run
+    must use the same numbers (the neighbours write into each other's arrays): pass the LARGEST nx_own of the
+    partition."""
     per_layer = n_total / sc
     halo_cap = int(per_layer * slack) + 1024
+    halo_cap += halo_cap & 1
     # migration message: in a liquid ~1e-3 of a layer crosses a face per step, but a run that starts from the lattice
     # can have a whole atomic plane sitting on a slab boundary, half of which crosses at once
     mig_cap = max(4096, int(per_layer * 0.6))
@@ -61,18 +64,19 @@ def capacities(n_total, sc, nx_own, slack=1.5):
 class SlabRank(Simulation):
     """One rank's share of the system: a Simulation restricted to x layers [x_lo, x_hi) with halo/migration buffers."""
 
-    def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0):
+    def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0, ipc=False):
         self.rank, self.world = rank, world
         n_total = r_all.shape[0]
         sc = math.floor(box / r_cut)
         assert sc >= 4, "the cell route needs sc >= 4"
-        self.x_lo, self.x_hi = partition(sc, world)[rank]
+        parts = partition(sc, world)
+        self.x_lo, self.x_hi = parts[rank]
         r_all = np.ascontiguousarray(r_all - np.rint(r_all))
         mine = np.flatnonzero(owned_mask(r_all, sc, self.x_lo, self.x_hi)).astype(np.int32)
-        cap, mig_cap, halo_cap = capacities(n_total, sc, self.x_hi - self.x_lo)
+        cap, mig_cap, halo_cap = capacities(n_total, sc, max(hi - lo for lo, hi in parts))
         v = None if v_all is None else np.ascontiguousarray(v_all[mine])
         super().__init__(box, r_cut, np.ascontiguousarray(r_all[mine]), v, model=model, ids=mine, capacity=cap,
-                         stream=stream, slab=(self.x_lo, self.x_hi))
+                         stream=stream, slab=(self.x_lo, self.x_hi), ipc=ipc)
         self.n_total = n_total
         L = _lib.lib()
         L.atlj_sim_set_total(self._h, n_total)
@@ -90,17 +94,15 @@ class SlabRank(Simulation):
         _lib.check(_lib.lib().atlj_sim_mg_phase3(self._h, float(dt), rec.ctypes.data))
         return rec
 
-    def arena(self):
-        """Device pointer of this rank's receive buffers (neighbours in the same process write into it directly)."""
-        return _lib.lib().atlj_sim_mg_arena(self._h)
-
     def set_peers(self, left, right):
-        _lib.check(_lib.lib().atlj_sim_mg_set_peers(self._h, left.arena(), right.arena()))
+        """Neighbours in the same process (emulation): they write into each other's arrays through plain pointers."""
+        _lib.check(_lib.lib().atlj_sim_mg_set_peers(self._h, left._h, right._h))
 
     # ---- one process per GPU ----------------------------------------------------------------------------------------
     def ipc_handle(self):
-        buf = C.create_string_buffer(64)
-        _lib.check(_lib.lib().atlj_sim_mg_ipc_handle(self._h, buf))
+        """CUDA IPC handles of this rank's receive arena, position buffers and cell table + the layout."""
+        buf = C.create_string_buffer(int(_lib.lib().atlj_sim_mg_blob_bytes()))
+        _lib.check(_lib.lib().atlj_sim_mg_ipc_blob(self._h, buf))
         return buf.raw
 
     def ipc_open(self, left_handle, right_handle):
@@ -133,7 +135,7 @@ class SlabSimulation(SlabRank):
 
     def __init__(self, box, r_cut, r_all, v_all, rank, world, model="lj", stream=0):
         import torch.distributed as dist
-        super().__init__(box, r_cut, r_all, v_all, rank, world, model=model, stream=stream)
+        super().__init__(box, r_cut, r_all, v_all, rank, world, model=model, stream=stream, ipc=True)
         handles = [None] * world
         dist.all_gather_object(handles, self.ipc_handle())   # map the neighbours' receive buffers (CUDA IPC)
         self.ipc_open(handles[(rank - 1) % world], handles[(rank + 1) % world])

@@ -111,6 +111,10 @@ typedef struct atlj_sim atlj_sim;
 /* capacity = maximum number of atoms this rank will ever hold (owned + halo).
  * stream = a cudaStream_t (0 = legacy default stream); all work is enqueued on it. */
 atlj_sim *atlj_sim_create(int64_t capacity, void *stream);
+/* flags: ATLJ_SIM_IPC = the position buffers and the cell table are allocations of their own, so that a slab rank can
+ * export them to its neighbours with CUDA IPC (the neighbours write this rank's halo layers directly) */
+#define ATLJ_SIM_IPC 1
+atlj_sim *atlj_sim_create_ex(int64_t capacity, void *stream, int flags);
 void atlj_sim_destroy(atlj_sim *s);
 
 /* Model and geometry.  sc = floor(box/r_cut) (md_lj_ll_module.py:106); r_cut_box_sq, box_sq, pot_cut as
@@ -162,19 +166,23 @@ int atlj_sim_run_baoab_noise(atlj_sim *s, double dt, double o_decay, double o_no
                              int nsteps, double *rec_host);
 
 /* ---- slab domain decomposition over the GPUs of one box (one rank per GPU; no reference counterpart, the yardstick
- * is the single-domain result).  A rank is a sim configured with a proper sub-range [x_lo, x_hi) of x cell layers.
- * Migrating atoms and halo layers are written by the pack kernels straight into the neighbours' receive buffers over
- * NVLink (peer memory mapped once with CUDA IPC) and published with a system-scope step stamp; the per-step records
- * are all-reduced once per run through NCCL.  mig_cap / halo_cap = atoms per migration / halo message. ---------- */
+ * is the single-domain result).  A rank is a sim (created with ATLJ_SIM_IPC when its neighbours live in other
+ * processes) configured with a proper sub-range [x_lo, x_hi) of x cell layers.  Its per-atom arrays hold
+ * [owned | left halo layer | right halo layer]; the halo regions of the position buffers and the halo rows of the cell
+ * table are written by the NEIGHBOURS' pack kernels over NVLink (peer memory mapped once with CUDA IPC) and published
+ * with a system-scope step stamp that the pair kernel acquires when it reaches a boundary layer; migrating atoms
+ * (r, v, id) go through a small message arena the same way.  The per-step records are all-reduced once per run
+ * through NCCL.  mig_cap = atoms per migration message, halo_cap = atoms per halo layer; all ranks must use the same
+ * capacity, mig_cap and halo_cap. ---------- */
 int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap);
 void atlj_sim_set_total(atlj_sim *s, int64_t n_total); /* atoms of the whole system (RNG / noise indexing) */
-/* This rank's receive arena: CUDA IPC handle (64 bytes) for neighbours in other processes ... */
-int atlj_sim_mg_ipc_handle(atlj_sim *s, char *out64);
-int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left64, const char *right64);
-/* ... or plain device pointers for neighbours living in the same process (ranks emulated on one GPU). */
-void *atlj_sim_mg_arena(atlj_sim *s);
-int64_t atlj_sim_mg_arena_bytes(atlj_sim *s);
-int atlj_sim_mg_set_peers(atlj_sim *s, void *left_arena, void *right_arena);
+/* What a neighbour in another process needs to write into this rank's memory: atlj_sim_mg_blob_bytes() bytes (CUDA IPC
+ * handles of the arena, the two position buffers and the cell table + the layout), exchanged by any means ... */
+int64_t atlj_sim_mg_blob_bytes(void);
+int atlj_sim_mg_ipc_blob(atlj_sim *s, char *out);
+int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_blob);
+/* ... or the neighbours' sims themselves when they live in the same process (ranks emulated on one GPU). */
+int atlj_sim_mg_set_peers(atlj_sim *s, atlj_sim *left, atlj_sim *right);
 /* NCCL communicator over all ranks: rank 0 obtains the id, the caller broadcasts the 128 bytes by any means. */
 int atlj_nccl_unique_id(char *out128);
 int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
@@ -183,7 +191,7 @@ int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host);
 /* The same step cut into its three device phases, for driving several ranks of one process in lockstep (tests):
  * phase1 = kick, drift, leavers written to the neighbours; phase2 = append arrivals, bin + sort, boundary layers
- * written to the neighbours; phase3 = unpack halos, pair kernel, kick, LOCAL sums.  Every rank must finish a phase
+ * written into the neighbours' halo regions; phase3 = pair kernel, kick, LOCAL sums.  Every rank must finish a phase
  * before any rank starts the next one. */
 int atlj_sim_mg_phase1(atlj_sim *s, double dt);
 int atlj_sim_mg_phase2(atlj_sim *s);
