@@ -568,7 +568,7 @@ static int nve_fused_step(atlj_sim *s, cudaStream_t st, cudaStream_t side, doubl
     ATLJ_CUDA(cudaEventRecord(s->ev_join, side));
   }
   if ((rc = launch_cell_sort_gather(st, s->g, s->cb, n, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
-                                    s->id[alt], nullptr, 0, true)))
+                                    s->id[alt], nullptr, nullptr, true)))
     return rc;
   Timer::end(s);
   s->cur = alt;

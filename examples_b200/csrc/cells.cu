@@ -119,8 +119,10 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   // per atom does the integer part
   __shared__ double xs[3 * IT];
   __shared__ double vs[3 * IT];
-  const bool slab = sl.to_left != nullptr;
+  const bool slab = sl.to_left[0] != nullptr;
   if (slab && err[5]) return;  // a neighbour's message timed out earlier in this run: the state stays as it is
+  const int xstep = slab ? *sl.xstep : 0;  // exchange step: buffer parity and stamp (read before the last CTA moves it on)
+  unsigned char *const to_left = sl.to_left[xstep & 1], *const to_right = sl.to_right[xstep & 1];
   if (sl.n_dev) n = min(n, *sl.n_dev);
   double s[2] = {0.0, 0.0};
   const double scd = (double)g.sc;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
           if (slot >= sl.mig_cap) {
             atomicOr(&err[1], 1);
           } else {
-            double *d = reinterpret_cast<double *>((dir ? sl.to_right : sl.to_left) + 64) + 7 * (size_t)slot;
+            double *d = reinterpret_cast<double *>((dir ? to_right : to_left) + 64) + 7 * (size_t)slot;
             d[0] = w0, d[1] = w1, d[2] = w2;
             d[3] = vs[3 * threadIdx.x], d[4] = vs[3 * threadIdx.x + 1], d[5] = vs[3 * threadIdx.x + 2];
             d[6] = (double)sl.id[i];
@@ -230,12 +232,13 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   if (slab && threadIdx.x == 0) {
     // header: [0] = number of atoms, [1] = step stamp, released at system scope after the count
     for (int dir = 0; dir < 2; dir++) {
-      int *hdr = reinterpret_cast<int *>(dir ? sl.to_right : sl.to_left);
+      int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
       hdr[0] = min(atomicAdd(&sl.mig_cnt[dir], 0), sl.mig_cap);
       __threadfence_system();
-      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(sl.stamp) : "memory");
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
       sl.mig_cnt[dir] = 0;
     }
+    *sl.xstep = xstep + 1;
   }
   if (first_kick) {
     double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -280,7 +283,8 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   if (!loop || !loop->counts_zeroed) ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   int *step_ctr = loop ? loop->step_ctr : nullptr, *tab0 = loop ? loop->tab0 : nullptr;
   const int nb = integ_blocks(n);
-  SlabArgs sl = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
+  SlabArgs sl;
+  memset(&sl, 0, sizeof(sl));
   if (slab) sl = *slab;
   // y = RN(1/box) for the division-free exact quotient; not for a divisor whose significand is all ones, nor when
   // the quotient could leave the normal range (never for a box length, but cheap to check)
@@ -513,11 +517,19 @@ __global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base,
                                                                     const double *__restrict__ v_in,
                                                                     double *__restrict__ r_out,
                                                                     double *__restrict__ v_out,
-                                                                    int *__restrict__ id_out, int zero_counts) {
+                                                                    int *__restrict__ id_out, int zero_counts,
+                                                                    HaloOut ho) {
   __shared__ unsigned long long sk[SG_KEYS];
   __shared__ int s_lo, s_hi;
   const int nown = g.n_own_cells(), first = g.first_own_cell();
-  const int c0 = (block0 + blockIdx.x) * cpb;
+  // slab ranks: the blocks of the first and the last owned layer run first, so that the halo data is on its way to
+  // the neighbours while the interior is still being sorted
+  int blk = block0 + blockIdx.x;
+  if (ho.dst_r_left && ho.n_first + ho.n_last <= (int)gridDim.x) {
+    const int b = blockIdx.x, nblk = gridDim.x;
+    blk = b < ho.n_first ? b : (b < ho.n_first + ho.n_last ? nblk - ho.n_last + (b - ho.n_first) : b - ho.n_last);
+  }
+  const int c0 = blk * cpb;
   const int c = c0 + threadIdx.x;
   int mystart = 0, mycnt = 0;
   if (threadIdx.x < cpb && c < nown) {
@@ -538,56 +550,100 @@ __global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base,
   }
   sort_cell_keys(kbase + (mystart - lo), mycnt);
   __syncthreads();
+  // slab ranks: slots [F0, F1) are the first owned layer = the left neighbour's right halo, [L0, L1) the last owned
+  // layer = the right neighbour's left halo; their positions are stored a second time, straight into the neighbours'
+  // position arrays (peer memory over NVLink), and the layers' cell tables, rebased to where the positions land, into
+  // the halo rows of the neighbours' cell_start.  The CTA that completes a layer publishes the step stamp.
+  int F0 = 0, F1 = 0, L0 = 0, L1 = 0;
+  const int sc2 = g.sc * g.sc;
+  if (ho.dst_r_left) {
+    const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+    F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
+  }
   for (int e = threadIdx.x; e < 3 * tot; e += blockDim.x) {
     const int s = e / 3, k = e - 3 * s;
     const unsigned long long key = kbase[s];
     const size_t src = (size_t)(key & 0xffffffffull);
-    const size_t dst = 3 * (size_t)(lo + s) + k;
-    r_out[dst] = r_in[3 * src + k];
+    const int slot = lo + s;
+    const size_t dst = 3 * (size_t)slot + k;
+    const double x = r_in[3 * src + k];
+    r_out[dst] = x;
+    if (slot >= F0 && slot < F1) ho.dst_r_left[3 * (size_t)(slot - F0) + k] = x;
+    if (slot >= L0 && slot < L1) ho.dst_r_right[3 * (size_t)(slot - L0) + k] = x;
     if (v_in) v_out[dst] = v_in[3 * src + k];
-    if (k == 0 && id_out) id_out[lo + s] = (int)(key >> 32);
+    if (k == 0 && id_out) id_out[slot] = (int)(key >> 32);
+  }
+  if (!ho.dst_r_left) return;
+  if (threadIdx.x < cpb && c < nown) {
+    const int cl = c - (g.nx_own - 1) * sc2;  // cell index inside the last layer
+    if (c < sc2) {
+      ho.dst_cs_left[c] = ho.base_left + min(mystart + base - F0, F1 - F0);
+      if (c == sc2 - 1) ho.dst_cs_left[sc2] = ho.base_left + (F1 - F0);
+    }
+    if (cl >= 0) {
+      ho.dst_cs_right[cl] = ho.base_right + min(mystart + base - L0, L1 - L0);
+      if (cl == sc2 - 1) {
+        ho.dst_cs_right[sc2] = ho.base_right + (L1 - L0);
+        const int n_own = cell_start[(size_t)(g.h + g.nx_own - 1) * (sc2 + 1) + sc2];  // end of the last owned layer
+        *ho.n_own = n_own;
+        if (ho.rec) ho.rec[(ho.rec_ctr ? (size_t)ATLJ_NREC * (size_t)*ho.rec_ctr : 0) + 11] = (double)n_own;
+        if (n_own > ho.own_cap || n_own - L0 > ho.cap || cell_start[(size_t)g.h * (sc2 + 1) + sc2] - F0 > ho.cap)
+          atomicOr(ho.err + 1, 1);  // more atoms than the neighbours' halo regions / the owned region hold
+      }
+    }
+  }
+  const bool inF = c0 < sc2, inL = clast >= (g.nx_own - 1) * sc2;
+  if (!inF && !inL) return;
+  __shared__ int s_pub;
+  __syncthreads();  // every thread's peer stores are ordered before thread 0's system-scope fence (cumulativity)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    int pub = 0;
+    if (inF && atomicAdd(ho.done, 1) == ho.n_first - 1) pub |= 1;
+    if (inL && atomicAdd(ho.done + 1, 1) == ho.n_last - 1) pub |= 2;
+    s_pub = pub;
+    const int stamp = *ho.xstep;  // the exchange step counter, already moved on by the integration kernel
+    if (pub & 1) {
+      ho.hdr_left[0] = F1 - F0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_left + 1), "r"(stamp) : "memory");
+      ho.done[0] = 0;
+    }
+    if (pub & 2) {
+      ho.hdr_right[0] = L1 - L0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_right + 1), "r"(stamp) : "memory");
+      ho.done[1] = 0;
+    }
   }
 }
 
 // n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); the sort + gather
 // walks cells, not atoms, so it needs no count at all.
-// which: 0 = everything; 1 = scatter + the blocks of cells covering the first and last owned layer (what the halo
-// messages are packed from); 2 = the remaining blocks (a slab rank runs them while the halo exchange is in flight)
+// halo (may be null): slab ranks - the first / last owned layer go to the neighbours from inside this kernel
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev, int which, bool zero_counts) {
+                            const int *n_dev, const HaloOut *halo, bool zero_counts) {
   if (n <= 0) return ATLJ_OK;
-  if (which != 2) {
-    cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in,
-                                                         b.keys);
-    ATLJ_LAUNCHED();
-  }
+  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in, b.keys);
+  ATLJ_LAUNCHED();
   const int nc = g.n_own_cells(), sc2 = g.sc * g.sc;
   const int cpb = sg_cells_per_block(nc);
   const int nblk = (nc + cpb - 1) / cpb;
-  int lo = 0, hi = nblk;  // interior blocks [lo, hi)
-  if (which != 0) {
-    lo = (sc2 + cpb - 1) / cpb;
-    hi = (nc - sc2) / cpb;
-    if (hi < lo) lo = hi = nblk;  // one or two layers: everything is boundary
+  HaloOut ho;
+  memset(&ho, 0, sizeof(ho));
+  if (halo) {
+    ho = *halo;
+    ho.n_first = (sc2 - 1) / cpb + 1;                 // blocks that hold cells of the first owned layer
+    ho.n_last = nblk - ((g.nx_own - 1) * sc2) / cpb;  // ... of the last owned layer
   }
-  auto run = [&](int b0, int cnt) -> int {
-    if (cnt <= 0) return ATLJ_OK;
-    // large grids: 128 cells and 128 threads per CTA (measured best at 2 M atoms); small grids: fewer cells per CTA
-    // and twice the threads for the gather
-    cell_sortgather_kernel<<<cnt, cpb == 128 ? 128 : SG_T, 0, st>>>(g, base, b0, cpb, b.cell_start, b.cell_count,
-                                                                    b.keys, r_in, v_in, r_out, v_out, id_out,
-                                                                    zero_counts ? 1 : 0);
-    ATLJ_LAUNCHED();
-    return ATLJ_OK;
-  };
-  int rc = ATLJ_OK;
-  if (which == 0) return run(0, nblk);
-  if (which == 1) {
-    if ((rc = run(0, lo))) return rc;
-    return run(hi, nblk - hi);
-  }
-  return run(lo, hi - lo);
+  // large grids: 128 cells and 128 threads per CTA (measured best at 2 M atoms); small grids: fewer cells per CTA
+  // and twice the threads for the gather
+  cell_sortgather_kernel<<<nblk, cpb == 128 ? 128 : SG_T, 0, st>>>(g, base, 0, cpb, b.cell_start, b.cell_count, b.keys,
+                                                                   r_in, v_in, r_out, v_out, id_out, zero_counts ? 1 : 0,
+                                                                   ho);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
 }
 
 }  // namespace atlj

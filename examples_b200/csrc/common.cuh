@@ -140,8 +140,12 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
 struct SlabArgs {
   const int *n_dev;                  // owned atoms, kept on the device (n is then an upper bound)
   const int *id;                     // global ids of the atoms held
-  unsigned char *to_left, *to_right; // the neighbours' migration buffers (peer memory): leavers are packed into them
-  int mig_cap, stamp;                // atoms per message; stamp published in the header when the message is complete
+  unsigned char *to_left[2], *to_right[2];  // the neighbours' migration buffers (peer memory), one per step parity:
+                                     // leavers are packed into them
+  int mig_cap;                       // atoms per message
+  int *xstep;                        // device counter of exchange steps: parity = *xstep & 1 selects the buffer, *xstep + 1
+                                     // is the stamp published in the header when the message is complete; the kernel's
+                                     // last CTA moves the counter on (so the launch arguments do not depend on the step)
   int *mig_cnt;                      // [0], [1] slot counters
 };
 // fused kick [+ sums] + kick + drift + wrap + cell assignment of the NVE loop; returns the number of CTAs
@@ -163,16 +167,33 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
                       const int *pair_rows_dev = nullptr, const KdkLoop *loop = nullptr);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
 int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
+// slab ranks: where the sort + gather kernel sends the first / last owned layer (the neighbours' halo regions, mg.cu)
+struct HaloOut {
+  double *dst_r_left, *dst_r_right;  // the neighbours' position arrays at their halo regions (peer memory)
+  int *dst_cs_left, *dst_cs_right;   // the halo rows of their cell tables
+  int base_left, base_right;         // atom index at which the positions land over there
+  int *hdr_left, *hdr_right;         // message headers: [0] = atoms, [1] = stamp
+  int cap;                           // atoms a halo region holds
+  const int *xstep;                  // device counter of exchange steps (already moved on by the integration kernel):
+                                     // its value is the stamp published when a layer is complete
+  const int *rec_ctr;                // when not null, rec is the base of the records and the row is *rec_ctr
+  int *done;                         // [2] finished CTAs per layer (left 0 by the kernel)
+  int *n_own;                        // device copy of the owned-atom count after the sort
+  long long own_cap;
+  double *rec;                       // step record: [11] = owned atoms (may be null)
+  int *err;
+  int n_first, n_last;               // filled in by the launcher
+};
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev = nullptr, int which = 0, bool zero_counts = false);
+                            const int *n_dev = nullptr, const HaloOut *halo = nullptr, bool zero_counts = false);
 
 // slab ranks: the halo layers are written by the neighbours; a pair kernel that reaches a boundary x layer acquires
 // their stamps first (null pointers: nothing to wait for)
 struct HaloWait {
   const int *stamp_left = nullptr, *stamp_right = nullptr;  // message headers: [1] = stamp
-  int stamp = 0;
+  const int *xstep = nullptr;  // device counter of exchange steps: its value is the stamp to wait for
   unsigned long long timeout_ns = 0;
   int *err = nullptr;  // device flags; [5] is raised on a timeout and turns the rest of the run into no-ops
 };

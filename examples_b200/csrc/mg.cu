@@ -7,9 +7,10 @@
 //   phase 1  kick + drift + wrap on the owned atoms; atoms that left the slab are packed (r, v, id) STRAIGHT INTO THE
 //            NEIGHBOUR'S receive buffer over NVLink (tens of atoms per face)
 //   phase 2  ONE kernel waits for the neighbours' migration messages, appends the arrivals and assigns their cells;
-//            scan; counting sort; then the first and last owned layer -- positions, already in cell order, and their
-//            cell table -- are written STRAIGHT INTO THE NEIGHBOURS' POSITION ARRAYS AND CELL TABLES (their halo regions:
-//            one layer per face, ~6e4 atoms = 1.4 MB at 2 M atoms/GPU).  Nothing is unpacked on the receiving side.
+//            scan; counting sort, whose gather kernel takes the first and last owned layer first and stores their
+//            positions and their cell table a second time, STRAIGHT INTO THE NEIGHBOURS' POSITION ARRAYS AND CELL TABLES
+//            (their halo regions: one layer per face, ~6e4 atoms = 1.4 MB at 2 M atoms/GPU).  No pack kernel, and
+//            nothing is unpacked on the receiving side.
 //   phase 3  the pair kernel starts at once on the rows that need no halo (interior x layers first) and only the CTAs
 //            that reach a boundary layer acquire the neighbours' stamps: the exchange is hidden behind ~85 % of the
 //            pair kernel.  Full stencil on the owned rows (no force return traffic).  The 12-double step records are
@@ -62,24 +63,30 @@ __device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
 }
 
 // consumer side for the pair kernels that cannot wait themselves (first tiled kernel): one thread acquires both stamps
-__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, int stamp, unsigned long long timeout_ns,
+__global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, const int *xstep, unsigned long long timeout_ns,
                                   int *err) {
   if (threadIdx.x != 0 || blockIdx.x != 0 || err[5]) return;
+  const int stamp = *xstep;
   if (!acquire_stamp(hdr_a, stamp, timeout_ns) || !acquire_stamp(hdr_b, stamp, timeout_ns)) atomicOr(&err[5], 1);
 }
 
 // ---- phase 2: wait for the migration messages, append the arrivals behind the atoms already held, assign their cells --
 // (one launch: every CTA acquires the two stamps itself, then takes its share of the arrivals)
 constexpr int ARR_CTAS = 32, ARR_T = 256;
-__global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, const unsigned char *__restrict__ recv_left,
-                                                         const unsigned char *__restrict__ recv_right, int cap,
-                                                         int stamp, unsigned long long timeout_ns,
+struct ArrivalBufs {
+  const unsigned char *left[2], *right[2];  // my receive buffers, one per step parity
+};
+__global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, ArrivalBufs bufs, int cap, const int *__restrict__ xstep,
+                                                         unsigned long long timeout_ns,
                                                          double *__restrict__ r, double *__restrict__ v,
                                                          int *__restrict__ id, const int *__restrict__ n_old_dev,
                                                          long long own_cap, int *__restrict__ n_after,
                                                          int *__restrict__ cellid, int *__restrict__ rank,
                                                          int *__restrict__ cell_count, int *__restrict__ err) {
   __shared__ int s_ok;
+  // the integration kernel of this step has moved the exchange counter on: its value is this step's stamp
+  const int stamp = *xstep;
+  const unsigned char *__restrict__ recv_left = bufs.left[(stamp - 1) & 1], *__restrict__ recv_right = bufs.right[(stamp - 1) & 1];
   if (threadIdx.x == 0) {
     s_ok = err[5] == 0 && acquire_stamp(reinterpret_cast<const int *>(recv_left), stamp, timeout_ns) &&
            acquire_stamp(reinterpret_cast<const int *>(recv_right), stamp, timeout_ns);
@@ -123,61 +130,6 @@ __global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, const unsigned 
   }
 }
 
-// first / last owned layer -> the left / right neighbour's halo region (blockIdx.y = direction): positions (already
-// contiguous and in cell order) into its position array, the layer's cell table (rebased to where the positions land)
-// into the halo row of its cell_start.  done[dir] counts finished CTAs; the last one publishes the stamp in the
-// neighbour's halo header.  Thread (0,0,0) of direction 1 also moves the new owned count (end sentinel of the last
-// owned layer) to n_own.
-__global__ void __launch_bounds__(256) halo_pack_kernel(Geom g, const int *__restrict__ cs,
-                                                        const double *__restrict__ r_sorted, double *dst_r_left,
-                                                        double *dst_r_right, int *dst_cs_left, int *dst_cs_right,
-                                                        int base_left, int base_right, int *hdr_left, int *hdr_right,
-                                                        int cap, int stamp, int *__restrict__ done,
-                                                        int *__restrict__ err, int *__restrict__ n_own,
-                                                        long long own_cap, double *__restrict__ rec) {
-  if (err[5]) return;
-  const int sc2 = g.sc * g.sc;
-  const int dir = blockIdx.y;
-  const int lx = dir == 0 ? g.h : g.h + g.nx_own - 1;
-  const int *row = cs + (size_t)lx * (sc2 + 1);
-  if (dir == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
-    *n_own = row[sc2];
-    if (row[sc2] > own_cap) atomicOr(&err[1], 1);
-    if (rec) rec[11] = (double)row[sc2];
-  }
-  int *hdr = dir ? hdr_right : hdr_left;
-  int *dcs = dir ? dst_cs_right : dst_cs_left;
-  double *pos = dir ? dst_r_right : dst_r_left;
-  const int base = dir ? base_right : base_left;
-  const int start = row[0];
-  int total = row[sc2] - start;
-  if (total > cap) {  // more atoms in the layer than the neighbour's halo region holds: flagged, message truncated
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&err[1], 1);
-    total = cap;
-  }
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-  for (long long c = gt; c <= sc2; c += stride) dcs[c] = base + min(row[c] - start, total);
-  // 16-byte stores towards the neighbour (base is even: the destination is 16-byte aligned; the source only 8-byte)
-  const double *src = r_sorted + 3 * (size_t)start;
-  const long long n2 = (3ll * total) >> 1;
-  double2 *pos2 = reinterpret_cast<double2 *>(pos);
-  for (long long e = gt; e < n2; e += stride) pos2[e] = make_double2(src[2 * e], src[2 * e + 1]);
-  if (gt == 0 && ((3ll * total) & 1)) pos[3ll * total - 1] = src[3ll * total - 1];
-  // one system-scope fence per CTA, by the thread that counts the CTA as done: the barrier orders the other threads'
-  // stores before it (cumulativity), so they need no fence of their own
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    s_last = atomicAdd(&done[dir], 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    publish(hdr, total, stamp);
-    done[dir] = 0;
-  }
-}
-
 // ---- NCCL (only the per-run all-reduce of the step records), bound at run time -------------------------------------
 struct NcclApi {
   void *handle = nullptr;
@@ -187,9 +139,6 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
-#ifndef ATLJ_HALO_PACK_CTAS
-#define ATLJ_HALO_PACK_CTAS 296
-#endif
 static NcclApi g_nccl;
 
 static int nccl_load() {
@@ -252,55 +201,27 @@ static const int *tile2_rows(atlj_sim *s) {
 
 // phase 1: ONE kernel: [trailing half kick + record of the finished step] + leading half kick + drift + wrap + cell
 // assignment of the atoms that stay + leavers packed into the neighbours' buffers and published
-static int phase1(atlj_sim *s, double dt, bool first_kick, double *rec_prev, int nb_prev) {
+// st: the stream to launch on (the sim's, or the capture stream); replay: nothing may depend on the step number - the
+// record pointer follows the device counter cnt_dev[11] (rec = base of the records), as the stamps and buffer parities
+// always follow cnt_dev[10]
+static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, double *rec, int nb_prev, bool replay,
+                  bool counts_zeroed) {
   MgState &m = s->mg;
-  const int par = (int)(m.step & 1);
   SlabArgs sl;
   sl.n_dev = m.cnt_dev + 1, sl.id = s->id[s->cur];
-  sl.to_left = mig_recv(m.peer_arena[0], m, 1, par), sl.to_right = mig_recv(m.peer_arena[1], m, 0, par);
-  sl.mig_cap = (int)m.mig_cap, sl.stamp = (int)(m.step + 1), sl.mig_cnt = m.cnt_dev + 4;
+  for (int par = 0; par < 2; par++)
+    sl.to_left[par] = mig_recv(m.peer_arena[0], m, 1, par), sl.to_right[par] = mig_recv(m.peer_arena[1], m, 0, par);
+  sl.mig_cap = (int)m.mig_cap, sl.xstep = m.cnt_dev + 10, sl.mig_cnt = m.cnt_dev + 4;
+  KdkLoop loop;
+  loop.step_ctr = replay ? m.cnt_dev + 11 : nullptr;
+  loop.tab0 = sim_tile2(s) ? s->tile_tab : nullptr;
+  loop.counts_zeroed = counts_zeroed;
   Timer::begin(s, 2);
-  const int nb = launch_kdk_assign(s->st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt,
-                                   s->p.box, first_kick, s->cb, s->vf_partials, rec_prev, s->partials, nb_prev,
-                                   s->p.model, &sl, tile2_rows(s));
+  const int nb = launch_kdk_assign(st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
+                                   first_kick, s->cb, s->vf_partials, rec, s->partials, nb_prev, s->p.model, &sl,
+                                   tile2_rows(s), &loop);
   Timer::end(s);
   return nb < 0 ? nb : ATLJ_OK;
-}
-
-// phase 2: arrivals appended and assigned, scan, counting sort, boundary layers written into the neighbours' halo regions
-static int phase2(atlj_sim *s, double *rec) {
-  int rc;
-  MgState &m = s->mg;
-  const int cap = (int)m.mig_cap, nup = (int)m.own_cap, par = (int)(m.step & 1), stamp = (int)(m.step + 1);
-  const int cur = s->cur, alt = 1 - cur;
-  Timer::begin(s, 4);
-  arrivals_kernel<<<ARR_CTAS, ARR_T, 0, s->st>>>(s->g, mig_recv(m.arena, m, 0, par), mig_recv(m.arena, m, 1, par), cap,
-                                                  stamp, m.timeout_ns, s->r[cur], s->v[cur], s->id[cur], m.cnt_dev + 1,
-                                                  (long long)m.own_cap, m.cnt_dev, s->cb.cellid, s->cb.rank,
-                                                  s->cb.cell_count, s->cb.err);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  Timer::begin(s, 1);
-  if ((rc = launch_cell_scan(s->st, s->g, s->cb, 0))) return rc;
-  if ((rc = launch_cell_sort_gather(s->st, s->g, s->cb, nup, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
-                                    s->id[alt], m.cnt_dev)))
-    return rc;
-  Timer::end(s);
-  s->cur = alt;
-  // my first layer is the left neighbour's RIGHT halo (its local layer nxl - 1, behind its left halo region); my last
-  // layer is the right neighbour's LEFT halo (its local layer 0).  All ranks share own_cap / halo_cap and flip their
-  // position buffers in step, so the neighbour's sorted buffer of this step is its r[alt] as well.
-  const size_t sc2p = (size_t)s->g.sc * s->g.sc + 1;
-  const int base_left = (int)(m.own_cap + m.halo_cap), base_right = (int)m.own_cap;
-  Timer::begin(s, 5);
-  halo_pack_kernel<<<dim3(ATLJ_HALO_PACK_CTAS, 2), 256, 0, s->st>>>(
-      s->g, s->cb.cell_start, s->r[alt], m.peer_r[0][alt] + 3 * (size_t)base_left, m.peer_r[1][alt] + 3 * (size_t)base_right,
-      m.peer_cs[0] + (size_t)(m.peer_nxl[0] - 1) * sc2p, m.peer_cs[1], base_left, base_right,
-      halo_hdr(m.peer_arena[0], m, 1), halo_hdr(m.peer_arena[1], m, 0), (int)m.halo_cap, stamp, m.cnt_dev + 8, s->cb.err,
-      m.cnt_dev + 1, (long long)m.own_cap, rec);
-  ATLJ_LAUNCHED();
-  Timer::end(s);
-  return ATLJ_OK;
 }
 
 static PairArgs pair_args(atlj_sim *s) {
@@ -313,28 +234,75 @@ static PairArgs pair_args(atlj_sim *s) {
   return a;
 }
 
+// phase 2: arrivals appended and assigned, scan, counting sort (its gather kernel sends the boundary layers to the
+// neighbours' halo regions); the item table of the pair kernel runs beside the sort when a side stream is given
+static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, bool replay) {
+  int rc;
+  MgState &m = s->mg;
+  const int cap = (int)m.mig_cap, nup = (int)m.own_cap;
+  const int cur = s->cur, alt = 1 - cur;
+  ArrivalBufs ab;
+  for (int par = 0; par < 2; par++) ab.left[par] = mig_recv(m.arena, m, 0, par), ab.right[par] = mig_recv(m.arena, m, 1, par);
+  Timer::begin(s, 4);
+  arrivals_kernel<<<ARR_CTAS, ARR_T, 0, st>>>(s->g, ab, cap, m.cnt_dev + 10, m.timeout_ns, s->r[cur], s->v[cur],
+                                               s->id[cur], m.cnt_dev + 1, (long long)m.own_cap, m.cnt_dev, s->cb.cellid,
+                                               s->cb.rank, s->cb.cell_count, s->cb.err);
+  ATLJ_LAUNCHED();
+  Timer::end(s);
+  // my first layer is the left neighbour's RIGHT halo (its local layer nxl - 1, behind its left halo region); my last
+  // layer is the right neighbour's LEFT halo (its local layer 0).  All ranks share own_cap / halo_cap and flip their
+  // position buffers in step, so the neighbour's sorted buffer of this step is its r[alt] as well.  The sort + gather
+  // kernel stores those two layers a second time, straight into the neighbours' memory, and publishes the stamps.
+  const size_t sc2p = (size_t)s->g.sc * s->g.sc + 1;
+  HaloOut ho;
+  memset(&ho, 0, sizeof(ho));
+  ho.base_left = (int)(m.own_cap + m.halo_cap), ho.base_right = (int)m.own_cap;
+  ho.dst_r_left = m.peer_r[0][alt] + 3 * (size_t)ho.base_left, ho.dst_r_right = m.peer_r[1][alt] + 3 * (size_t)ho.base_right;
+  ho.dst_cs_left = m.peer_cs[0] + (size_t)(m.peer_nxl[0] - 1) * sc2p, ho.dst_cs_right = m.peer_cs[1];
+  ho.hdr_left = halo_hdr(m.peer_arena[0], m, 1), ho.hdr_right = halo_hdr(m.peer_arena[1], m, 0);
+  ho.cap = (int)m.halo_cap, ho.xstep = m.cnt_dev + 10, ho.rec_ctr = replay ? m.cnt_dev + 11 : nullptr;
+  ho.done = m.cnt_dev + 8, ho.n_own = m.cnt_dev + 1;
+  ho.own_cap = (long long)m.own_cap, ho.rec = rec, ho.err = s->cb.err;
+  Timer::begin(s, 1);
+  if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
+  const bool fork = side != nullptr && sim_tile2(s);
+  if (fork) {  // the item table needs cell_start only: beside the sort + gather
+    PairArgs a = pair_args(s);
+    ATLJ_CUDA(cudaEventRecord(s->ev_fork, st));
+    ATLJ_CUDA(cudaStreamWaitEvent(side, s->ev_fork, 0));
+    if ((rc = launch_pair_tile2(side, a, s->cb.err + 2, 0, 1, true)) < 0) return rc;
+    ATLJ_CUDA(cudaEventRecord(s->ev_join, side));
+  }
+  if ((rc = launch_cell_sort_gather(st, s->g, s->cb, nup, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
+                                    s->id[alt], m.cnt_dev, &ho, true)))
+    return rc;
+  Timer::end(s);
+  s->cur = alt;
+  if (fork) ATLJ_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  return ATLJ_OK;
+}
+
 // phase 3: pair kernel over the owned rows; the halo layers 0 and nxl-1 were written by the neighbours, and the kernel
 // itself acquires their stamps when it reaches a boundary layer.  -> rows of partials written (the record is finished by
 // the next phase 1 or by tail())
-static int phase3(atlj_sim *s) {
+static int phase3(atlj_sim *s, cudaStream_t st, bool table_done) {
   MgState &m = s->mg;
-  const int stamp = (int)(m.step + 1);
   PairArgs a = pair_args(s);
   const int *hl = halo_hdr(m.arena, m, 0), *hr = halo_hdr(m.arena, m, 1);
   int nb;
   if (sim_tile2(s)) {
-    a.halo.stamp_left = hl, a.halo.stamp_right = hr, a.halo.stamp = stamp, a.halo.timeout_ns = m.timeout_ns;
+    a.halo.stamp_left = hl, a.halo.stamp_right = hr, a.halo.xstep = m.cnt_dev + 10, a.halo.timeout_ns = m.timeout_ns;
     a.halo.err = s->cb.err;
     Timer::begin(s, 0);
-    nb = launch_pair_tile2(s->st, a, s->cb.err + 2);
+    nb = launch_pair_tile2(st, a, s->cb.err + 2, 0, table_done ? 2 : 0, true);
     Timer::end(s);
   } else {
     Timer::begin(s, 6);
-    wait_stamp_kernel<<<1, 32, 0, s->st>>>(hl, hr, stamp, m.timeout_ns, s->cb.err);
+    wait_stamp_kernel<<<1, 32, 0, st>>>(hl, hr, m.cnt_dev + 10, m.timeout_ns, s->cb.err);
     ATLJ_LAUNCHED();
     Timer::end(s);
     Timer::begin(s, 0);
-    nb = launch_pair_tile(s->st, a, false);
+    nb = launch_pair_tile(st, a, false);
     Timer::end(s);
   }
   m.step++;
@@ -356,7 +324,10 @@ static int tail(atlj_sim *s, double dt, double *rec, int nb) {
 // host copy of the owned count <-> device
 static int push_n(atlj_sim *s) {
   s->mg.cnt_host[0] = (int)s->n;
+  s->mg.cnt_host[1] = (int)s->mg.step;  // exchange step counter (stamps, buffer parity)
+  s->mg.cnt_host[2] = 0;                // record row of the replayed launches
   ATLJ_CUDA(cudaMemcpyAsync(s->mg.cnt_dev + 1, s->mg.cnt_host, sizeof(int), cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->mg.cnt_dev + 10, s->mg.cnt_host + 1, 2 * sizeof(int), cudaMemcpyHostToDevice, s->st));
   return ATLJ_OK;
 }
 static int pull_n(atlj_sim *s) {
@@ -384,6 +355,14 @@ static void mg_free(atlj_sim *s) {
 void sim_mg_destroy(atlj_sim *s) { mg_free(s); }
 
 static const unsigned long long MG_MAGIC = 0x61746c6a6d670002ull;  // the signature of api.cu's dev_alloc_ipc
+
+// everything the captured launches of the slab step bake in
+struct MgGraphKey {
+  int64_t n_total;
+  int cur, sc, x_lo, nx_own, nb, pad;
+  double dt, box, r_cut_box_sq, pot_cut;
+  void *r0, *rec, *partials, *peer, *tab;
+};
 
 // what a neighbour needs to write into this rank's memory (exchanged once, by any means)
 struct MgBlob {
@@ -533,19 +512,19 @@ int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
   int rc = sim_ensure_rec(s, 1);
   if (rc || (rc = push_n(s))) return rc;
   ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
-  if ((rc = phase1(s, dt, false, nullptr, 0))) return rc;
+  if ((rc = phase1(s, s->st, dt, false, nullptr, 0, false, false))) return rc;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));
   return ATLJ_OK;
 }
 int atlj_sim_mg_phase2(atlj_sim *s) {
   if (!mg_ready(s)) return ATLJ_ERR_ARG;
-  int rc = phase2(s, s->rec_dev);
+  int rc = phase2(s, s->st, nullptr, s->rec_dev, false);
   if (rc || (rc = pull_n(s))) return rc;
   return sim_check_flags(s);
 }
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
   if (!mg_ready(s)) return ATLJ_ERR_ARG;
-  const int nb = phase3(s);
+  const int nb = phase3(s, s->st, false);
   if (nb < 0) return nb;
   int rc = tail(s, dt, s->rec_dev, nb);
   if (rc) return rc;
@@ -584,12 +563,75 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
   MgState &m = s->mg;
   if ((rc = push_n(s))) return rc;
   ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)nsteps, s->st));
-  int nb = 0;
+  int nb = 0, k = 0;
   double *rec_prev = nullptr;
-  for (int k = 0; k < nsteps; k++) {
+  // step 0 launched kernel by kernel (nothing to close, cell_count zeroed by a memset, kernel attributes warmed up)
+  if (nsteps > 0) {
+    if ((rc = phase1(s, s->st, dt, false, nullptr, 0, false, false)) || (rc = phase2(s, s->st, nullptr, s->rec_dev, false)))
+      return rc;
+    if ((nb = phase3(s, s->st, false)) < 0) return nb;
+    rec_prev = s->rec_dev;
+    k = 1;
+  }
+  // pairs of steps as ONE replayed CUDA graph: stamps, buffer parities and record rows follow device counters
+  if (!s->timing && !s->no_graph && nsteps - k >= 2) {
+    MgGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.n_total = s->n_total, key.cur = s->cur, key.sc = s->g.sc, key.x_lo = s->g.x_lo, key.nx_own = s->g.nx_own, key.nb = nb;
+    key.dt = dt, key.box = s->p.box, key.r_cut_box_sq = s->p.r_cut_box_sq, key.pot_cut = s->p.pot_cut;
+    key.r0 = s->r[0], key.rec = s->rec_dev, key.partials = s->partials, key.peer = m.peer_arena[0], key.tab = s->tile_tab;
+    static_assert(sizeof(MgGraphKey) <= sizeof(s->nve_graph_key), "key storage");
+    bool have = s->nve_graph && memcmp(&key, s->nve_graph_key, sizeof(key)) == 0;
+    if (!have) {
+      if (s->nve_graph) cudaGraphExecDestroy(s->nve_graph), s->nve_graph = nullptr;
+      if (!s->st_cap) {
+        ATLJ_CUDA(cudaStreamCreateWithFlags(&s->st_cap, cudaStreamNonBlocking));
+        ATLJ_CUDA(cudaStreamCreateWithFlags(&s->st_side, cudaStreamNonBlocking));
+        ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        ATLJ_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+      }
+      const int64_t l0 = g_launches;
+      const int cur0 = s->cur;
+      const long long step0 = m.step;
+      ATLJ_CUDA(cudaStreamBeginCapture(s->st_cap, cudaStreamCaptureModeThreadLocal));
+      int nbc = nb;
+      for (int j = 0; j < 2 && rc == ATLJ_OK; j++) {
+        if ((rc = phase1(s, s->st_cap, dt, true, s->rec_dev, nbc, true, true)) ||
+            (rc = phase2(s, s->st_cap, s->st_side, s->rec_dev, true)))
+          break;
+        if ((nbc = phase3(s, s->st_cap, sim_tile2(s))) < 0) rc = nbc;
+      }
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(s->st_cap, &graph);
+      s->nve_graph_launches = (int)(g_launches - l0);
+      g_launches = l0, m.step = step0;
+      if (rc == ATLJ_OK && (e != cudaSuccess || s->cur != cur0 || nbc != nb)) {
+        set_error("CUDA graph capture of the slab step failed: %s", cudaGetErrorString(e));
+        rc = ATLJ_ERR_CUDA;
+      }
+      s->cur = cur0;
+      if (rc == ATLJ_OK && cudaGraphInstantiate(&s->nve_graph, graph, 0) != cudaSuccess) {
+        s->nve_graph = nullptr;
+        rc = ATLJ_ERR_CUDA;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == ATLJ_OK) memcpy(s->nve_graph_key, &key, sizeof(key)), have = true;
+      else cudaGetLastError(), rc = ATLJ_OK;  // fall back to plain launches
+    }
+    if (have) {
+      for (; nsteps - k >= 2; k += 2) {
+        ATLJ_CUDA(cudaGraphLaunch(s->nve_graph, s->st));
+        g_launches += s->nve_graph_launches;
+        m.step += 2;
+      }
+      rec_prev = s->rec_dev + (size_t)(k - 1) * ATLJ_NREC;
+    }
+  }
+  for (; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
-    if ((rc = phase1(s, dt, k > 0, rec_prev, nb)) || (rc = phase2(s, rec))) return rc;
-    if ((nb = phase3(s)) < 0) return nb;
+    if ((rc = phase1(s, s->st, dt, true, rec_prev, nb, false, true)) || (rc = phase2(s, s->st, nullptr, rec, false)))
+      return rc;
+    if ((nb = phase3(s, s->st, false)) < 0) return nb;
     rec_prev = rec;
   }
   if (nsteps > 0 && (rc = tail(s, dt, rec_prev, nb))) return rc;

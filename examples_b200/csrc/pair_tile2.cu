@@ -276,12 +276,13 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
       if (!halo_ok) {  // CTA-uniform
         if (tid == 0) {
           const unsigned long long t0 = halo_now_ns();
+          const int stamp = *a.halo.xstep;
           int ok = 0;
           for (;;) {
             int vl, vr;
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(vl) : "l"(a.halo.stamp_left + 1) : "memory");
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(vr) : "l"(a.halo.stamp_right + 1) : "memory");
-            if (vl == a.halo.stamp && vr == a.halo.stamp) {
+            if (vl == stamp && vr == stamp) {
               ok = 1;
               break;
             }
