@@ -91,6 +91,7 @@ def lib():
     L.atlj_sim_mg_phase2.argtypes = [_vp]
     L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]
     L.atlj_sim_mg_set_peers.argtypes = [_vp, _vp, _vp]
+    L.atlj_sim_mg_trace.argtypes = [_vp, C.c_int, _vp]
     L.atlj_sim_mg_blob_bytes.restype = C.c_int64
     L.atlj_sim_mg_ipc_blob.argtypes = [_vp, C.c_char_p]
     L.atlj_sim_mg_ipc_open.argtypes = [_vp, C.c_char_p, C.c_char_p]

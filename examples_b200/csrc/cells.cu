@@ -7,10 +7,9 @@
 //   1. cell_assign : wrap, triplet, local cell id; one atomicAdd per atom gives the per-cell histogram and an
 //                    arrival rank inside the cell                                  (reads 24 B, writes 8 B / atom)
 //   2. cell_scan   : exclusive scan of the histogram -> cell_start       (4 B / cell, one decoupled-look-back kernel)
-//   3. cell_scatter: key = (atom id << 32 | source index) -> slot cell_start + rank
-//   4. cell_sortgather: per block of 32..128 cells, keys to shared memory, one thread per cell orders its <= ~30 keys
-//                    by atom id (the arrival rank of step 1 is scheduling dependent, the sorted result is not) ->
-//                    "ascending atom index" of the reference; then r (and v, id) are gathered into cell order
+//   3. cell_scatter: atom id -> slot cell_start + arrival rank (every cell's id list complete, in arrival order)
+//   4. cell_rankgather: one thread per source atom: slot = cell_start + (atoms of the cell with a smaller id) ->
+//                    "ascending atom index" of the reference whatever the arrival order was; it moves its r, v, id there
 // All HBM-bound; see DESIGN.md for bytes per atom.
 #include <cstring>
 
@@ -98,7 +97,7 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
 // step k, then md_lj_ll_module.py:88,106-109):  v += hdt*f [sum v^2, sum f^2 of the finished step]  ->  v += hdt*f
 // -> r += dt*v/box -> wrap -> cell triplet, histogram, arrival rank.  Same separately-rounded operations as
 // kick_sums_kernel + kick_drift_kernel + cell_assign_kernel, so results are bit-identical to the unfused sequence.
-template <bool RCP>
+template <bool RCP, bool SLAB>
 __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
                                                         const double *__restrict__ f, double half_dt, double dt,
                                                         double box, double inv_box, int first_kick,
@@ -119,10 +118,11 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   // per atom does the integer part
   __shared__ double xs[3 * IT];
   __shared__ double vs[3 * IT];
-  const bool slab = sl.to_left[0] != nullptr;
+  constexpr bool slab = SLAB;
   if (slab && err[5]) return;  // a neighbour's message timed out earlier in this run: the state stays as it is
   const int xstep = slab ? *sl.xstep : 0;  // exchange step: buffer parity and stamp (read before the last CTA moves it on)
-  unsigned char *const to_left = sl.to_left[xstep & 1], *const to_right = sl.to_right[xstep & 1];
+  unsigned char *const to_left = (xstep & 1) ? sl.to_left1 : sl.to_left0;
+  unsigned char *const to_right = (xstep & 1) ? sl.to_right1 : sl.to_right0;
   if (sl.n_dev) n = min(n, *sl.n_dev);
   double s[2] = {0.0, 0.0};
   const double scd = (double)g.sc;
@@ -292,14 +292,22 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   memcpy(&bits, &box, sizeof(bits));
   const bool ones = (bits & 0xfffffffffffffull) == 0xfffffffffffffull;
   const double inv_box = (!ones && box > 1e-100 && box < 1e100) ? 1.0 / box : 0.0;
-  if (inv_box != 0.0)
-    kdk_assign_kernel<true><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
-                                               b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
-                                               pair_rows, model, sl, pair_rows_dev, step_ctr, tab0);
-  else
-    kdk_assign_kernel<false><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid,
-                                                b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,
-                                                pair_rows, model, sl, pair_rows_dev, step_ctr, tab0);
+#define ATLJ_KDK(RCP, SLAB)                                                                                          \
+  kdk_assign_kernel<RCP, SLAB><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid, \
+                                                  b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,     \
+                                                  pair_rows, model, sl, pair_rows_dev, step_ctr, tab0)
+  if (inv_box != 0.0) {
+    if (slab)
+      ATLJ_KDK(true, true);
+    else
+      ATLJ_KDK(true, false);
+  } else {
+    if (slab)
+      ATLJ_KDK(false, true);
+    else
+      ATLJ_KDK(false, false);
+  }
+#undef ATLJ_KDK
   ATLJ_LAUNCHED();
   return nb;
 }
@@ -432,216 +440,134 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
   return ATLJ_OK;
 }
 
-// ---- 3. scatter keys into their cells ---------------------------------------------------------------------------
+// ---- 3. scatter the atom ids into their cells --------------------------------------------------------------------
+// ids[cell_start + arrival rank] = id: after this kernel every cell's id list is complete (in arrival order, which is
+// scheduling dependent - the next kernel turns it into the reference's ascending order).
 __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
                                                            const int *__restrict__ cellid,
                                                            const int *__restrict__ rank,
                                                            const int *__restrict__ cell_start,
                                                            const int *__restrict__ id_in,
-                                                           unsigned long long *__restrict__ keys) {
+                                                           unsigned *__restrict__ ids) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int cid = cellid[i];
   if (cid < 0) return;
-  unsigned id = id_in ? (unsigned)id_in[i] : (unsigned)i;
-  int slot = cell_start[g.cs_idx(cid)] - base + rank[i];
-  keys[slot] = ((unsigned long long)id << 32) | (unsigned)i;
+  ids[cell_start[g.cs_idx(cid)] - base + rank[i]] = id_in ? (unsigned)id_in[i] : (unsigned)i;
 }
 
-// ---- 4. order each cell by atom id -----------------------------------------------------------------------------
-// insertion sort for ordinary cells (keys arrive nearly ordered when the atoms were in cell order already), heap
-// sort for crowded ones (dense blobs); in place, k may point to shared or global memory
-__device__ __forceinline__ void sort_cell_keys(unsigned long long *k, int n) {
-  if (n < 2) return;
-  if (n <= 32) {
-    for (int a = 1; a < n; a++) {
-      unsigned long long x = k[a];
-      int b = a - 1;
-      while (b >= 0 && k[b] > x) {
-        k[b + 1] = k[b];
-        b--;
-      }
-      k[b + 1] = x;
-    }
-  } else {
-    for (int start = n / 2 - 1; start >= 0; start--) {
-      int root = start;
-      for (;;) {
-        int child = 2 * root + 1;
-        if (child >= n) break;
-        if (child + 1 < n && k[child] < k[child + 1]) child++;
-        if (k[root] >= k[child]) break;
-        unsigned long long t = k[root];
-        k[root] = k[child];
-        k[child] = t;
-        root = child;
-      }
-    }
-    for (int end = n - 1; end > 0; end--) {
-      unsigned long long t = k[0];
-      k[0] = k[end];
-      k[end] = t;
-      int root = 0;
-      for (;;) {
-        int child = 2 * root + 1;
-        if (child >= end) break;
-        if (child + 1 < end && k[child] < k[child + 1]) child++;
-        if (k[root] >= k[child]) break;
-        unsigned long long u = k[root];
-        k[root] = k[child];
-        k[child] = u;
-        root = child;
-      }
-    }
-  }
-}
-
-// ---- 4+5. order each cell by atom id and gather r, v, id into cell order ----------------------------------------
-// One CTA takes cpb (32..128) consecutive owned cells: their keys are one contiguous run of slots, which is loaded into
-// shared memory with coalesced reads, sorted there (one thread per cell; the arrival rank of step 1 is scheduling
-// dependent, the sorted result is not -> "ascending atom index" of md_lj_ll_module.py:118-119), and then drives the
-// gather: one thread per (atom, component), so the writes of r, v in cell order are perfectly coalesced.  A run that
-// does not fit (crowded cells) is sorted in global memory instead.
-constexpr int SG_T = 256;      // most threads per CTA: the first `cpb` of them sort one cell each, all of them gather
-constexpr int SG_KEYS = 3072;  // 24 KB of keys per CTA
-
-// cells per CTA: 128 on large grids; fewer on small ones so that the gather still spreads over every SM
-static inline int sg_cells_per_block(int ncells) { return ncells >= 148 * 2 * 128 ? 128 : (ncells >= 148 * 2 * 64 ? 64 : 32); }
-
-__global__ void __launch_bounds__(SG_T) cell_sortgather_kernel(Geom g, int base, int block0, int cpb,
-                                                                    const int *__restrict__ cell_start,
-                                                                    int *cell_count,
-                                                                    unsigned long long *__restrict__ keys,
-                                                                    const double *__restrict__ r_in,
-                                                                    const double *__restrict__ v_in,
-                                                                    double *__restrict__ r_out,
-                                                                    double *__restrict__ v_out,
-                                                                    int *__restrict__ id_out, int zero_counts,
-                                                                    HaloOut ho) {
-  __shared__ unsigned long long sk[SG_KEYS];
-  __shared__ int s_lo, s_hi;
-  const int nown = g.n_own_cells(), first = g.first_own_cell();
-  // slab ranks: the blocks of the first and the last owned layer run first, so that the halo data is on its way to
-  // the neighbours while the interior is still being sorted
-  int blk = block0 + blockIdx.x;
-  if (ho.dst_r_left && ho.n_first + ho.n_last <= (int)gridDim.x) {
-    const int b = blockIdx.x, nblk = gridDim.x;
-    blk = b < ho.n_first ? b : (b < ho.n_first + ho.n_last ? nblk - ho.n_last + (b - ho.n_first) : b - ho.n_last);
-  }
-  const int c0 = blk * cpb;
-  const int c = c0 + threadIdx.x;
-  int mystart = 0, mycnt = 0;
-  if (threadIdx.x < cpb && c < nown) {
-    mystart = cell_start[g.cs_idx(first + c)] - base;
-    mycnt = cell_count[first + c];
-    if (zero_counts) cell_count[first + c] = 0;  // ready for the next step's histogram
-  }
-  if (threadIdx.x == 0) s_lo = mystart;
-  const int clast = min(c0 + cpb, nown) - 1;
-  if (threadIdx.x < cpb && c == clast) s_hi = mystart + mycnt;
-  __syncthreads();
-  const int lo = s_lo, tot = s_hi - s_lo;
-  const bool fits = tot <= SG_KEYS;
-  unsigned long long *kbase = fits ? sk : keys + lo;
-  if (fits) {
-    for (int s = threadIdx.x; s < tot; s += blockDim.x) sk[s] = keys[lo + s];
-    __syncthreads();
-  }
-  sort_cell_keys(kbase + (mystart - lo), mycnt);
-  __syncthreads();
-  // slab ranks: slots [F0, F1) are the first owned layer = the left neighbour's right halo, [L0, L1) the last owned
-  // layer = the right neighbour's left halo; their positions are stored a second time, straight into the neighbours'
-  // position arrays (peer memory over NVLink), and the layers' cell tables, rebased to where the positions land, into
-  // the halo rows of the neighbours' cell_start.  The CTA that completes a layer publishes the step stamp.
+// ---- 4. rank inside the cell + gather --------------------------------------------------------------------------------
+// One thread per SOURCE atom: its slot in the cell-sorted arrays is cell_start + (number of atoms of its cell with a
+// smaller id) - "ascending atom index" of md_lj_ll_module.py:118-119, independent of the arrival order - and it moves
+// its own r, v, id there.  The cell's ids (a dozen, one L1 line shared by the neighbouring threads, which mostly sit
+// in the same cell because the old order was the previous step's cell order) are counted, not sorted: no shared
+// memory, no barrier, no phases - the kernel streams (reads coalesced by source, writes nearly sequential) and its
+// run time does not depend on how the grid divides into waves of CTAs (the phased sort + gather kernel it replaces
+// took 56 us with 1,300 CTAs and 105 us with 1,340 on 148 SMs).
+// Slab ranks (ho.dst_r_left != null): slots [F0, F1) are the first owned layer = the left neighbour's right halo,
+// [L0, L1) the last owned layer = the right neighbour's left halo; those positions are stored a second time, straight
+// into the neighbours' position arrays (peer memory over NVLink), the layers' cell tables - rebased to where the
+// positions land - into the halo rows of the neighbours' cell_start, and the CTA that finishes last publishes the step
+// stamp in both neighbours' headers.
+constexpr int RG_T = 256;
+__global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
+                                                                const int *__restrict__ cellid,
+                                                                const int *__restrict__ id_in,
+                                                                const int *__restrict__ cell_start,
+                                                                int *__restrict__ cell_count,
+                                                                const unsigned *__restrict__ ids,
+                                                                const double *__restrict__ r_in,
+                                                                const double *__restrict__ v_in,
+                                                                double *__restrict__ r_out,
+                                                                double *__restrict__ v_out,
+                                                                int *__restrict__ id_out, int zero_counts,
+                                                                HaloOut ho) {
+  const int i = blockIdx.x * RG_T + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
+  const int nown = g.n_own_cells(), first = g.first_own_cell(), sc2 = g.sc * g.sc;
+  if (zero_counts && i < nown) cell_count[first + i] = 0;  // ready for the next step's histogram
+  const bool halo = ho.dst_r_left != nullptr;
   int F0 = 0, F1 = 0, L0 = 0, L1 = 0;
-  const int sc2 = g.sc * g.sc;
-  if (ho.dst_r_left) {
+  if (halo) {
     const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
     F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
-  }
-  for (int e = threadIdx.x; e < 3 * tot; e += blockDim.x) {
-    const int s = e / 3, k = e - 3 * s;
-    const unsigned long long key = kbase[s];
-    const size_t src = (size_t)(key & 0xffffffffull);
-    const int slot = lo + s;
-    const size_t dst = 3 * (size_t)slot + k;
-    const double x = r_in[3 * src + k];
-    r_out[dst] = x;
-    if (slot >= F0 && slot < F1) ho.dst_r_left[3 * (size_t)(slot - F0) + k] = x;
-    if (slot >= L0 && slot < L1) ho.dst_r_right[3 * (size_t)(slot - L0) + k] = x;
-    if (v_in) v_out[dst] = v_in[3 * src + k];
-    if (k == 0 && id_out) id_out[slot] = (int)(key >> 32);
-  }
-  if (!ho.dst_r_left) return;
-  if (threadIdx.x < cpb && c < nown) {
-    const int cl = c - (g.nx_own - 1) * sc2;  // cell index inside the last layer
-    if (c < sc2) {
-      ho.dst_cs_left[c] = ho.base_left + min(mystart + base - F0, F1 - F0);
-      if (c == sc2 - 1) ho.dst_cs_left[sc2] = ho.base_left + (F1 - F0);
+    if (i <= sc2) {  // the two layers' cell tables, rebased (entry sc2 = end sentinel)
+      ho.dst_cs_left[i] = ho.base_left + min(rowF[i] - F0, F1 - F0);
+      ho.dst_cs_right[i] = ho.base_right + min(rowL[i] - L0, L1 - L0);
     }
-    if (cl >= 0) {
-      ho.dst_cs_right[cl] = ho.base_right + min(mystart + base - L0, L1 - L0);
-      if (cl == sc2 - 1) {
-        ho.dst_cs_right[sc2] = ho.base_right + (L1 - L0);
-        const int n_own = cell_start[(size_t)(g.h + g.nx_own - 1) * (sc2 + 1) + sc2];  // end of the last owned layer
-        *ho.n_own = n_own;
-        if (ho.rec) ho.rec[(ho.rec_ctr ? (size_t)ATLJ_NREC * (size_t)*ho.rec_ctr : 0) + 11] = (double)n_own;
-        if (n_own > ho.own_cap || n_own - L0 > ho.cap || cell_start[(size_t)g.h * (sc2 + 1) + sc2] - F0 > ho.cap)
-          atomicOr(ho.err + 1, 1);  // more atoms than the neighbours' halo regions / the owned region hold
+    if (i == 0) {
+      const int n_own = rowL[sc2];  // end of the last owned layer = owned atoms after the sort
+      *ho.n_own = n_own;
+      if (ho.rec) ho.rec[(ho.rec_ctr ? (size_t)ATLJ_NREC * (size_t)*ho.rec_ctr : 0) + 11] = (double)n_own;
+      if (n_own > ho.own_cap || rowL[sc2] - L0 > ho.cap || rowF[sc2] - F0 > ho.cap)
+        atomicOr(ho.err + 1, 1);  // more atoms than the owned region / the neighbours' halo regions hold
+    }
+  }
+  int cid = -1;
+  if (i < n) cid = cellid[i];
+  if (cid >= 0) {
+    const unsigned myid = id_in ? (unsigned)id_in[i] : (unsigned)i;
+    const int ci = g.cs_idx(cid);
+    const int s0 = cell_start[ci] - base, s1 = cell_start[ci + 1] - base;
+    int slot = s0;
+    for (int s = s0; s < s1; s++) slot += ids[s] < myid;
+    const double x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
+    const size_t d = 3 * (size_t)slot;
+    r_out[d] = x0, r_out[d + 1] = x1, r_out[d + 2] = x2;
+    if (v_in) v_out[d] = w0, v_out[d + 1] = w1, v_out[d + 2] = w2;
+    if (id_out) id_out[slot] = (int)myid;
+    if (halo) {
+      const int gs = slot + base;
+      if (gs >= F0 && gs < F1) {
+        double *p = ho.dst_r_left + 3 * (size_t)(gs - F0);
+        p[0] = x0, p[1] = x1, p[2] = x2;
+      }
+      if (gs >= L0 && gs < L1) {
+        double *p = ho.dst_r_right + 3 * (size_t)(gs - L0);
+        p[0] = x0, p[1] = x1, p[2] = x2;
       }
     }
   }
-  const bool inF = c0 < sc2, inL = clast >= (g.nx_own - 1) * sc2;
-  if (!inF && !inL) return;
-  __shared__ int s_pub;
-  __syncthreads();  // every thread's peer stores are ordered before thread 0's system-scope fence (cumulativity)
+  if (!halo) return;
+  // one system-scope fence per CTA, by the thread that counts the CTA as done: the barrier orders the other threads'
+  // peer stores before it (cumulativity); the last CTA publishes the stamp (the exchange step counter, which the
+  // integration kernel has already moved on) in both neighbours' headers
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    int pub = 0;
-    if (inF && atomicAdd(ho.done, 1) == ho.n_first - 1) pub |= 1;
-    if (inL && atomicAdd(ho.done + 1, 1) == ho.n_last - 1) pub |= 2;
-    s_pub = pub;
-    const int stamp = *ho.xstep;  // the exchange step counter, already moved on by the integration kernel
-    if (pub & 1) {
-      ho.hdr_left[0] = F1 - F0;
+    if (atomicAdd(ho.done, 1) == (int)gridDim.x - 1) {
+      const int stamp = *ho.xstep;
+      ho.hdr_left[0] = F1 - F0, ho.hdr_right[0] = L1 - L0;
       __threadfence_system();
       asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_left + 1), "r"(stamp) : "memory");
-      ho.done[0] = 0;
-    }
-    if (pub & 2) {
-      ho.hdr_right[0] = L1 - L0;
-      __threadfence_system();
       asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_right + 1), "r"(stamp) : "memory");
-      ho.done[1] = 0;
+      ho.done[0] = 0;
     }
   }
 }
 
-// n_dev (may be null): device-side count of atoms BEFORE the sort (n is then an upper bound); the sort + gather
-// walks cells, not atoms, so it needs no count at all.
-// halo (may be null): slab ranks - the first / last owned layer go to the neighbours from inside this kernel
+// n: atoms before the sort, or an upper bound when the count lives on the device (n_dev)
+// halo (may be null): slab ranks - the first / last owned layer go to the neighbours from inside the gather kernel
+// zero_counts: cell_count is left zeroed for the next step's histogram
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
                             const int *n_dev, const HaloOut *halo, bool zero_counts) {
   if (n <= 0) return ATLJ_OK;
-  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in, b.keys);
+  unsigned *ids = reinterpret_cast<unsigned *>(b.keys);
+  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in, ids);
   ATLJ_LAUNCHED();
-  const int nc = g.n_own_cells(), sc2 = g.sc * g.sc;
-  const int cpb = sg_cells_per_block(nc);
-  const int nblk = (nc + cpb - 1) / cpb;
   HaloOut ho;
   memset(&ho, 0, sizeof(ho));
-  if (halo) {
-    ho = *halo;
-    ho.n_first = (sc2 - 1) / cpb + 1;                 // blocks that hold cells of the first owned layer
-    ho.n_last = nblk - ((g.nx_own - 1) * sc2) / cpb;  // ... of the last owned layer
-  }
-  // large grids: 128 cells and 128 threads per CTA (measured best at 2 M atoms); small grids: fewer cells per CTA
-  // and twice the threads for the gather
-  cell_sortgather_kernel<<<nblk, cpb == 128 ? 128 : SG_T, 0, st>>>(g, base, 0, cpb, b.cell_start, b.cell_count, b.keys,
-                                                                   r_in, v_in, r_out, v_out, id_out, zero_counts ? 1 : 0,
-                                                                   ho);
+  if (halo) ho = *halo;
+  int cover = n;  // threads: every source atom, every owned cell (zero_counts), every entry of a halo cell table
+  if (zero_counts && g.n_own_cells() > cover) cover = g.n_own_cells();
+  if (halo && g.sc * g.sc + 1 > cover) cover = g.sc * g.sc + 1;
+  cell_rankgather_kernel<<<(cover + RG_T - 1) / RG_T, RG_T, 0, st>>>(g, n, n_dev, base, b.cellid, id_in, b.cell_start,
+                                                                      b.cell_count, ids, r_in, v_in, r_out, v_out,
+                                                                      id_out, zero_counts ? 1 : 0, ho);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -123,7 +123,7 @@ struct Phys {
 struct CellBufs {
   int *cellid;          // [cap] local cell id of each atom (current order)
   int *rank;            // [cap] arrival rank inside its cell
-  unsigned long long *keys;  // [cap] (id << 32 | source index), sorted per cell
+  unsigned long long *keys;  // [cap] scratch of the counting sort: the cells' atom ids (32-bit) in arrival order
   int *cell_count;      // [ncell]
   int *cell_start;      // [ncell+1]
   int *block_sums;      // scan scratch
@@ -140,8 +140,8 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
 struct SlabArgs {
   const int *n_dev;                  // owned atoms, kept on the device (n is then an upper bound)
   const int *id;                     // global ids of the atoms held
-  unsigned char *to_left[2], *to_right[2];  // the neighbours' migration buffers (peer memory), one per step parity:
-                                     // leavers are packed into them
+  unsigned char *to_left0, *to_left1, *to_right0, *to_right1;  // the neighbours' migration buffers (peer memory), one
+                                     // per step parity: leavers are packed into them
   int mig_cap;                       // atoms per message
   int *xstep;                        // device counter of exchange steps: parity = *xstep & 1 selects the buffer, *xstep + 1
                                      // is the stamp published in the header when the message is complete; the kernel's
@@ -177,12 +177,11 @@ struct HaloOut {
   const int *xstep;                  // device counter of exchange steps (already moved on by the integration kernel):
                                      // its value is the stamp published when a layer is complete
   const int *rec_ctr;                // when not null, rec is the base of the records and the row is *rec_ctr
-  int *done;                         // [2] finished CTAs per layer (left 0 by the kernel)
+  int *done;                         // finished CTAs (left 0 by the kernel)
   int *n_own;                        // device copy of the owned-atom count after the sort
   long long own_cap;
   double *rec;                       // step record: [11] = owned atoms (may be null)
   int *err;
-  int n_first, n_last;               // filled in by the launcher
 };
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,

@@ -70,11 +70,27 @@ __global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, const int 
   if (!acquire_stamp(hdr_a, stamp, timeout_ns) || !acquire_stamp(hdr_b, stamp, timeout_ns)) atomicOr(&err[5], 1);
 }
 
+// ---- optional trace (ATLJ_MG_TRACE=1): one-thread kernels between the launches of a step write %globaltimer into
+// trace[step % TRACE_STEPS][slot]; tools/slab_trace.py prints where a slab step spends its time (waits included) even
+// when the step is replayed as a graph.  slot 0 = before the integration kernel, 1 = after it, 2 = after the arrivals,
+// 3 = after the scan, 4 = after the sort + gather (halo sent), 5 = after the pair kernel.
+constexpr int TRACE_STEPS = 4096, TRACE_SLOTS = 8;
+__global__ void trace_kernel(unsigned long long *trace, const int *xstep, int slot) {
+  const int step = *xstep - (slot == 0 ? 0 : 1);
+  trace[(size_t)(step & (TRACE_STEPS - 1)) * TRACE_SLOTS + slot] = global_ns();
+}
+static int trace_mark(atlj_sim *s, cudaStream_t st, int slot) {
+  if (!s->mg.trace) return ATLJ_OK;
+  trace_kernel<<<1, 1, 0, st>>>(s->mg.trace, s->mg.cnt_dev + 10, slot);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+
 // ---- phase 2: wait for the migration messages, append the arrivals behind the atoms already held, assign their cells --
 // (one launch: every CTA acquires the two stamps itself, then takes its share of the arrivals)
 constexpr int ARR_CTAS = 32, ARR_T = 256;
 struct ArrivalBufs {
-  const unsigned char *left[2], *right[2];  // my receive buffers, one per step parity
+  const unsigned char *left0, *left1, *right0, *right1;  // my receive buffers, one per step parity
 };
 __global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, ArrivalBufs bufs, int cap, const int *__restrict__ xstep,
                                                          unsigned long long timeout_ns,
@@ -86,7 +102,9 @@ __global__ void __launch_bounds__(ARR_T) arrivals_kernel(Geom g, ArrivalBufs buf
   __shared__ int s_ok;
   // the integration kernel of this step has moved the exchange counter on: its value is this step's stamp
   const int stamp = *xstep;
-  const unsigned char *__restrict__ recv_left = bufs.left[(stamp - 1) & 1], *__restrict__ recv_right = bufs.right[(stamp - 1) & 1];
+  const bool odd = (stamp - 1) & 1;
+  const unsigned char *__restrict__ recv_left = odd ? bufs.left1 : bufs.left0;
+  const unsigned char *__restrict__ recv_right = odd ? bufs.right1 : bufs.right0;
   if (threadIdx.x == 0) {
     s_ok = err[5] == 0 && acquire_stamp(reinterpret_cast<const int *>(recv_left), stamp, timeout_ns) &&
            acquire_stamp(reinterpret_cast<const int *>(recv_right), stamp, timeout_ns);
@@ -209,18 +227,20 @@ static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, doub
   MgState &m = s->mg;
   SlabArgs sl;
   sl.n_dev = m.cnt_dev + 1, sl.id = s->id[s->cur];
-  for (int par = 0; par < 2; par++)
-    sl.to_left[par] = mig_recv(m.peer_arena[0], m, 1, par), sl.to_right[par] = mig_recv(m.peer_arena[1], m, 0, par);
+  sl.to_left0 = mig_recv(m.peer_arena[0], m, 1, 0), sl.to_left1 = mig_recv(m.peer_arena[0], m, 1, 1);
+  sl.to_right0 = mig_recv(m.peer_arena[1], m, 0, 0), sl.to_right1 = mig_recv(m.peer_arena[1], m, 0, 1);
   sl.mig_cap = (int)m.mig_cap, sl.xstep = m.cnt_dev + 10, sl.mig_cnt = m.cnt_dev + 4;
   KdkLoop loop;
   loop.step_ctr = replay ? m.cnt_dev + 11 : nullptr;
   loop.tab0 = sim_tile2(s) ? s->tile_tab : nullptr;
   loop.counts_zeroed = counts_zeroed;
+  trace_mark(s, st, 0);
   Timer::begin(s, 2);
   const int nb = launch_kdk_assign(st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
                                    first_kick, s->cb, s->vf_partials, rec, s->partials, nb_prev, s->p.model, &sl,
                                    tile2_rows(s), &loop);
   Timer::end(s);
+  trace_mark(s, st, 1);
   return nb < 0 ? nb : ATLJ_OK;
 }
 
@@ -242,13 +262,15 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
   const int cap = (int)m.mig_cap, nup = (int)m.own_cap;
   const int cur = s->cur, alt = 1 - cur;
   ArrivalBufs ab;
-  for (int par = 0; par < 2; par++) ab.left[par] = mig_recv(m.arena, m, 0, par), ab.right[par] = mig_recv(m.arena, m, 1, par);
+  ab.left0 = mig_recv(m.arena, m, 0, 0), ab.left1 = mig_recv(m.arena, m, 0, 1);
+  ab.right0 = mig_recv(m.arena, m, 1, 0), ab.right1 = mig_recv(m.arena, m, 1, 1);
   Timer::begin(s, 4);
   arrivals_kernel<<<ARR_CTAS, ARR_T, 0, st>>>(s->g, ab, cap, m.cnt_dev + 10, m.timeout_ns, s->r[cur], s->v[cur],
                                                s->id[cur], m.cnt_dev + 1, (long long)m.own_cap, m.cnt_dev, s->cb.cellid,
                                                s->cb.rank, s->cb.cell_count, s->cb.err);
   ATLJ_LAUNCHED();
   Timer::end(s);
+  trace_mark(s, st, 2);
   // my first layer is the left neighbour's RIGHT halo (its local layer nxl - 1, behind its left halo region); my last
   // layer is the right neighbour's LEFT halo (its local layer 0).  All ranks share own_cap / halo_cap and flip their
   // position buffers in step, so the neighbour's sorted buffer of this step is its r[alt] as well.  The sort + gather
@@ -265,6 +287,7 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
   ho.own_cap = (long long)m.own_cap, ho.rec = rec, ho.err = s->cb.err;
   Timer::begin(s, 1);
   if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
+  trace_mark(s, st, 3);
   const bool fork = side != nullptr && sim_tile2(s);
   if (fork) {  // the item table needs cell_start only: beside the sort + gather
     PairArgs a = pair_args(s);
@@ -277,6 +300,7 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
                                     s->id[alt], m.cnt_dev, &ho, true)))
     return rc;
   Timer::end(s);
+  trace_mark(s, st, 4);
   s->cur = alt;
   if (fork) ATLJ_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return ATLJ_OK;
@@ -305,6 +329,7 @@ static int phase3(atlj_sim *s, cudaStream_t st, bool table_done) {
     nb = launch_pair_tile(st, a, false);
     Timer::end(s);
   }
+  trace_mark(s, st, 5);
   m.step++;
   return nb;
 }
@@ -346,6 +371,8 @@ static void mg_free(atlj_sim *s) {
   m.arena = nullptr;
   cudaFree(m.cnt_dev);
   m.cnt_dev = nullptr;
+  cudaFree(m.trace);
+  m.trace = nullptr;
   if (m.cnt_host) cudaFreeHost(m.cnt_host);
   m.cnt_host = nullptr;
   if (m.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m.comm);
@@ -410,6 +437,11 @@ int atlj_sim_mg_enable(atlj_sim *s, int64_t mig_cap, int64_t halo_cap) {
   ATLJ_CUDA(cudaMalloc((void **)&m.cnt_dev, 16 * sizeof(int)));
   ATLJ_CUDA(cudaMemsetAsync(m.cnt_dev, 0, 16 * sizeof(int), s->st));
   ATLJ_CUDA(cudaHostAlloc((void **)&m.cnt_host, 16 * sizeof(int), cudaHostAllocDefault));
+  const char *tr = getenv("ATLJ_MG_TRACE");
+  if (tr && tr[0] == '1') {
+    ATLJ_CUDA(cudaMalloc((void **)&m.trace, sizeof(unsigned long long) * TRACE_STEPS * TRACE_SLOTS));
+    ATLJ_CUDA(cudaMemsetAsync(m.trace, 0, sizeof(unsigned long long) * TRACE_STEPS * TRACE_SLOTS, s->st));
+  }
   m.step = 0;
   m.on = true;
   int rc = push_n(s);
@@ -529,6 +561,21 @@ int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
   int rc = tail(s, dt, s->rec_dev, nb);
   if (rc) return rc;
   return sim_copy_rec(s, rec_host, 1);
+}
+
+/* ATLJ_MG_TRACE=1: the %globaltimer marks of the last `nsteps` exchange steps, out[nsteps][8] (ns); see trace_kernel */
+int atlj_sim_mg_trace(atlj_sim *s, int nsteps, unsigned long long *out) {
+  if (!s || !s->mg.on || !s->mg.trace || !out || nsteps < 1 || nsteps > TRACE_STEPS) return ATLJ_ERR_ARG;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  std::vector<unsigned long long> all((size_t)TRACE_STEPS * TRACE_SLOTS);
+  ATLJ_CUDA(cudaMemcpy(all.data(), s->mg.trace, sizeof(unsigned long long) * all.size(), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < nsteps; k++) {
+    const long long step = s->mg.step - nsteps + k;
+    if (step < 0) return ATLJ_ERR_ARG;
+    memcpy(out + (size_t)k * TRACE_SLOTS, all.data() + (size_t)(step & (TRACE_STEPS - 1)) * TRACE_SLOTS,
+           sizeof(unsigned long long) * TRACE_SLOTS);
+  }
+  return ATLJ_OK;
 }
 
 int atlj_nccl_unique_id(char *out128) {

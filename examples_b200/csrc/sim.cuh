@@ -27,6 +27,7 @@ struct MgState {
                             // [4..6] migration slot counters + CTAs done, [8], [9] halo pack CTAs done
   int *cnt_host = nullptr;  // pinned mirror of cnt_dev[1]
   void *comm = nullptr;     // ncclComm_t (all-reduce of the step records)
+  unsigned long long *trace = nullptr;  // ATLJ_MG_TRACE=1: %globaltimer marks between the launches of a step
   unsigned long long timeout_ns = 30000000000ull;  // a neighbour's message: give up after this long (ATLJ_PEER_TIMEOUT_MS)
 };
 

@@ -183,6 +183,10 @@ int atlj_sim_mg_ipc_blob(atlj_sim *s, char *out);
 int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_blob);
 /* ... or the neighbours' sims themselves when they live in the same process (ranks emulated on one GPU). */
 int atlj_sim_mg_set_peers(atlj_sim *s, atlj_sim *left, atlj_sim *right);
+/* Diagnostics (environment ATLJ_MG_TRACE=1 when the slab is enabled): %globaltimer marks (ns) between the launches of
+ * the last nsteps exchange steps, out[nsteps][8]: before / after the integration kernel, after the arrivals, the scan,
+ * the sort + gather, the pair kernel (tools/slab_trace.py). */
+int atlj_sim_mg_trace(atlj_sim *s, int nsteps, unsigned long long *out);
 /* NCCL communicator over all ranks: rank 0 obtains the id, the caller broadcasts the 128 bytes by any means. */
 int atlj_nccl_unique_id(char *out128);
 int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
