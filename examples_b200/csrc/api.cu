@@ -495,6 +495,7 @@ int atlj_sim_upload(atlj_sim *s, const double *r_host, const double *v_host, con
   }
   ATLJ_CUDA(cudaMemsetAsync(s->f, 0, b, s->st));
   s->forces_valid = false;  // the run_* entry points evaluate the forces first when they are not current
+  s->mg.sorted = false;
   ATLJ_CUDA(cudaStreamSynchronize(s->st));  // the host arrays may be reused by the caller
   return ATLJ_OK;
 }

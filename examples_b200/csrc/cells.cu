@@ -127,7 +127,20 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   double s[2] = {0.0, 0.0};
   const double scd = (double)g.sc;
   const int ntiles = (n + IT - 1) / IT;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // slab: tiles [0, nF) hold the first owned layer, [ntiles - nL, ntiles) the last one; they are taken first
+  int nF = 0, nL = 0, nbt = 0;
+  if (slab) {
+    nF = ntiles, nL = 0;
+    if (sl.first_end) {
+      const int f1 = min(max(*sl.first_end, 0), n), l0 = min(max(*sl.last_begin, 0), n);
+      nF = (f1 + IT - 1) / IT, nL = ntiles - l0 / IT;
+      if (nF + nL >= ntiles) nF = ntiles, nL = 0;
+    }
+    nbt = nF + nL;
+  }
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tile = !slab || t < nF ? t : (t < nbt ? ntiles - nL + (t - nF) : t - nL);
+    const bool btile = slab && t < nbt;
     const size_t e0 = 3 * (size_t)tile * IT;
     const int ne = min(3 * IT, 3 * n - (int)e0 > 0 ? (int)(3 * (size_t)n - e0) : 0);
 #pragma unroll
@@ -175,7 +188,8 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
         // the atom left the slab: hand it (r, v, id) to the neighbour, straight into its receive buffer
         const int left = g.x_lo == 0 ? g.sc - 1 : g.x_lo - 1;
         const int right = g.x_lo + g.nx_own == g.sc ? 0 : g.x_lo + g.nx_own;
-        const int dir = !slab ? -1 : (c0 == left ? 0 : (c0 == right ? 1 : -1));
+        // (an atom of an interior layer cannot reach a neighbour in one step; its messages are out already)
+        const int dir = !btile ? -1 : (c0 == left ? 0 : (c0 == right ? 1 : -1));
         if (dir < 0) {
           bad = true;  // single domain: cannot happen; slab: moved more than one layer in a step
         } else {
@@ -204,6 +218,20 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
       }
     }
     __syncthreads();
+    if (btile && threadIdx.x == 0) {
+      // the leavers' stores were fenced at system scope by their threads, before the barrier; the tile that completes
+      // the two boundary layers publishes: header [0] = number of atoms, [1] = step stamp (system-scope release)
+      __threadfence();
+      if (atomicAdd(&sl.mig_cnt[2], 1) == nbt - 1) {
+        __threadfence();
+        for (int dir = 0; dir < 2; dir++) {
+          int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
+          hdr[0] = min(atomicAdd(&sl.mig_cnt[dir], 0), sl.mig_cap);
+          __threadfence_system();
+          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
+        }
+      }
+    }
   }
   if (!first_kick && !slab) return;
   // ---- finish the record of the step that just ended; publish the migration messages ------------------------------
@@ -230,14 +258,15 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
   if (!s_last) return;
   __threadfence();
   if (slab && threadIdx.x == 0) {
-    // header: [0] = number of atoms, [1] = step stamp, released at system scope after the count
-    for (int dir = 0; dir < 2; dir++) {
-      int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
-      hdr[0] = min(atomicAdd(&sl.mig_cnt[dir], 0), sl.mig_cap);
-      __threadfence_system();
-      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
-      sl.mig_cnt[dir] = 0;
+    if (nbt == 0) {  // no atoms at all: empty messages
+      for (int dir = 0; dir < 2; dir++) {
+        int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
+        hdr[0] = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
+      }
     }
+    sl.mig_cnt[0] = sl.mig_cnt[1] = sl.mig_cnt[2] = 0;
     *sl.xstep = xstep + 1;
   }
   if (first_kick) {
@@ -504,7 +533,7 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
         atomicOr(ho.err + 1, 1);  // more atoms than the owned region / the neighbours' halo regions hold
     }
   }
-  int cid = -1;
+  int cid = -1, sent = 0;
   if (i < n) cid = cellid[i];
   if (cid >= 0) {
     const unsigned myid = id_in ? (unsigned)id_in[i] : (unsigned)i;
@@ -524,20 +553,22 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
       if (gs >= F0 && gs < F1) {
         double *p = ho.dst_r_left + 3 * (size_t)(gs - F0);
         p[0] = x0, p[1] = x1, p[2] = x2;
+        sent = 1;
       }
       if (gs >= L0 && gs < L1) {
         double *p = ho.dst_r_right + 3 * (size_t)(gs - L0);
         p[0] = x0, p[1] = x1, p[2] = x2;
+        sent = 1;
       }
     }
   }
   if (!halo) return;
-  // one system-scope fence per CTA, by the thread that counts the CTA as done: the barrier orders the other threads'
-  // peer stores before it (cumulativity); the last CTA publishes the stamp (the exchange step counter, which the
-  // integration kernel has already moved on) in both neighbours' headers
-  __syncthreads();
+  // one system-scope fence per CTA THAT STORED TO A NEIGHBOUR (a few per cent of them), by the thread that counts the
+  // CTA as done: the barrier orders the other threads' peer stores before it (cumulativity); the last CTA publishes the
+  // stamp (the exchange step counter, which the integration kernel has already moved on) in both neighbours' headers
+  sent = __syncthreads_or(sent | (i <= sc2));
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (sent) __threadfence_system();
     if (atomicAdd(ho.done, 1) == (int)gridDim.x - 1) {
       const int stamp = *ho.xstep;
       ho.hdr_left[0] = F1 - F0, ho.hdr_right[0] = L1 - L0;

@@ -146,7 +146,13 @@ struct SlabArgs {
   int *xstep;                        // device counter of exchange steps: parity = *xstep & 1 selects the buffer, *xstep + 1
                                      // is the stamp published in the header when the message is complete; the kernel's
                                      // last CTA moves the counter on (so the launch arguments do not depend on the step)
-  int *mig_cnt;                      // [0], [1] slot counters
+  int *mig_cnt;                      // [0], [1] slot counters, [2] finished boundary tiles
+  // Only atoms of the first and the last owned layer can leave the slab in one step.  The sorted arrays hold the
+  // layers one after the other, so the tiles of those two layers are integrated FIRST and the migration messages are
+  // published as soon as they are done - the rest of the kernel hides the neighbours' latency and skew.
+  const int *first_end;              // &cell_start[end sentinel of the first owned layer] of the previous sort
+  const int *last_begin;             // &cell_start[first cell of the last owned layer]      (both null: no sort yet,
+                                     // every tile counts as a boundary tile)
 };
 // fused kick [+ sums] + kick + drift + wrap + cell assignment of the NVE loop; returns the number of CTAs
 // (= rows of vf_partials written when first_kick) or a negative status

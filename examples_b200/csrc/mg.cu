@@ -230,6 +230,9 @@ static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, doub
   sl.to_left0 = mig_recv(m.peer_arena[0], m, 1, 0), sl.to_left1 = mig_recv(m.peer_arena[0], m, 1, 1);
   sl.to_right0 = mig_recv(m.peer_arena[1], m, 0, 0), sl.to_right1 = mig_recv(m.peer_arena[1], m, 0, 1);
   sl.mig_cap = (int)m.mig_cap, sl.xstep = m.cnt_dev + 10, sl.mig_cnt = m.cnt_dev + 4;
+  const size_t sc2p = (size_t)s->g.sc * s->g.sc + 1;
+  sl.first_end = m.sorted ? s->cb.cell_start + (size_t)s->g.h * sc2p + (sc2p - 1) : nullptr;
+  sl.last_begin = m.sorted ? s->cb.cell_start + (size_t)(s->g.h + s->g.nx_own - 1) * sc2p : nullptr;
   KdkLoop loop;
   loop.step_ctr = replay ? m.cnt_dev + 11 : nullptr;
   loop.tab0 = sim_tile2(s) ? s->tile_tab : nullptr;
@@ -301,6 +304,7 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
     return rc;
   Timer::end(s);
   trace_mark(s, st, 4);
+  m.sorted = true;
   s->cur = alt;
   if (fork) ATLJ_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return ATLJ_OK;
