@@ -40,6 +40,10 @@ constexpr int U_K = 12;                 // staged rows per z cell: 4 y-offsets (
 constexpr int U_NE = U_MAXC * U_K;      // (cell,row) entries per chunk
 constexpr int U_WW = 6;                 // mask words per window (<= 191 candidates per window)
 constexpr int U_NWORDS = 3 * U_WW;
+// stride of the staged coordinate arrays: slot U_CAP holds a dummy candidate far away (1e150 in every coordinate) that
+// the unused slot of a phase-2 iteration reads: its separation (3e300) is classified out of range by the same tests as
+// a real pair and contributes exactly 0 (sr^6 underflows), so a dead slot needs no instructions of its own
+constexpr int U_STR = U_CAP + 2;
 
 // Kernel modes.  T2_FORCE: forces + totals.  T2_FORCE_SAVE: the same launch with a mask buffer - every atom's mask
 // words (the filter's survivors) are kept in global memory.  T2_HESS: the hessian sum (md_lj_module.py:176-191) from those mask words - no
@@ -50,8 +54,8 @@ enum { T2_FORCE = 0, T2_FORCE_SAVE = 1, T2_HESS = 2 };
 
 static inline size_t tile2_smem_bytes(int mode) {
   const size_t tab = sizeof(int) * (U_NE + 4) + sizeof(int) * U_NE;
-  if (mode == T2_HESS) return sizeof(double) * 6 * U_CAP + tab;
-  return sizeof(double) * 3 * U_CAP + sizeof(uint4) * (U_CAP / 2 + 1) + tab;
+  if (mode == T2_HESS) return sizeof(double) * 6 * U_STR + tab;
+  return sizeof(double) * 3 * U_STR + sizeof(uint4) * (U_CAP / 2 + 1) + tab;
 }
 size_t pair_tile2_mask_bytes(long long natoms) { return sizeof(uint2) * (size_t)U_NWORDS * (size_t)natoms; }
 
@@ -78,7 +82,7 @@ constexpr int U_GK_MAX = 4;  // chunks per work item: 1 (small systems, keeps ev
 static inline int tile2_gstride(const Geom &g) { return g.sc + 2; }
 int pair_tile2_tab_ints(const Geom &g) {
   const int nrp = g.nx_own * ((g.sc + 1) / 2);
-  return 16 + nrp + nrp * tile2_gstride(g);
+  return 16 + nrp + 2 * nrp * tile2_gstride(g);  // start positions, then the z cell each item starts in
 }
 // upper bound of the partial rows a launch over this geometry writes
 int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * (tile2_gstride(g) - 1); }
@@ -99,12 +103,13 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
   __syncwarp();
   if (lane != 0) return;
   int *zb = tab + 16 + nrp + (size_t)rp * gstride;
+  int *zc = zb + (size_t)nrp * gstride;  // the z cell that holds the item's first atom (saves the kernel a search)
   const int T = (cs[ownA0 + sc] - cs[ownA0]) + (two ? cs[ownB0 + sc] - cs[ownB0] : 0);
   int z0 = 0, cum0 = 0, gpos = 0, nch = 0, ng = 0;
   while (gpos < T) {
-    // past gstride - 1 items (only a pathologically crowded row pair gets there) the last item takes all the rest
-    if (nch % gk == 0 && ng < gstride - 1) zb[ng++] = gpos;
     while (cum0 + cnt[w][z0] <= gpos) cum0 += cnt[w][z0], z0++;  // the cell that holds atom gpos
+    // past gstride - 1 items (only a pathologically crowded row pair gets there) the last item takes all the rest
+    if (nch % gk == 0 && ng < gstride - 1) zb[ng] = gpos, zc[ng] = z0, ng++;
     int lim = cum0;
     for (int c = 0; c < ncz_max && z0 + c < sc; c++) lim += cnt[w][z0 + c];
     gpos = min(gpos + U_NT, lim);  // same rule as the kernel's chunk extent
@@ -181,8 +186,7 @@ __device__ __forceinline__ double rcp46(double s) {
     ovr |= o_.ovr;                                                                     \
     if (o_.in) {                                                                       \
       U_ACCUM(o_.dx, o_.dy, o_.dz, o_.s);                                              \
-    } else {                                                                           \
-      npf--; /* it was counted with the filter's survivors */                          \
+      npf++;                                                                           \
     }                                                                                  \
   } while (0)
 
@@ -204,8 +208,7 @@ __device__ __forceinline__ double rcp46(double s) {
     if (o_.in) {                                                                       \
       const double ex_ = fix - gx[(jj)], ey_ = fiy - gy[(jj)], ez_ = fiz - gz[(jj)];   \
       U_HESS(o_.dx, o_.dy, o_.dz, o_.s, ex_, ey_, ez_);                                \
-    } else {                                                                           \
-      npf--;                                                                           \
+      npf++;                                                                           \
     }                                                                                  \
   } while (0)
 
@@ -215,19 +218,19 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
                       int *__restrict__ work_counter, int *__restrict__ rows_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
-  double *uy = ux + U_CAP;
-  double *uz = uy + U_CAP;
-  double *gx = uz + U_CAP, *gy = gx + U_CAP, *gz = gy + U_CAP;  // T2_HESS only: forces of the staged candidates
+  double *uy = ux + U_STR;
+  double *uz = uy + U_STR;
+  double *gx = uz + U_STR, *gy = gx + U_STR, *gz = gy + U_STR;  // T2_HESS only: forces of the staged candidates
   // fp16 copy for the filter: record p holds candidates 2p (low halves) and 2p+1 (high halves): (x, y, z, unused)
-  uint4 *hp = reinterpret_cast<uint4 *>(uz + U_CAP);
+  uint4 *hp = reinterpret_cast<uint4 *>(uz + U_STR);
   // [U_NE + 4] staged offset of entry e = cell*12 + row
-  int *S = MODE == T2_HESS ? reinterpret_cast<int *>(gz + U_CAP) : reinterpret_cast<int *>(hp + U_CAP / 2 + 1);
+  int *S = MODE == T2_HESS ? reinterpret_cast<int *>(gz + U_STR) : reinterpret_cast<int *>(hp + U_CAP / 2 + 1);
   int *egl = S + U_NE + 4;                               // [U_NE] global index of the first atom of entry e
   __shared__ int rowcell0[U_K];
   __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
   __shared__ int wsum[U_NT / 32];
   __shared__ unsigned s_q2max;
-  __shared__ int s_maxwin, s_item, s_halo;
+  __shared__ int s_item, s_halo;
 
   const Geom g = a.g;
   const Phys p = a.p;
@@ -238,7 +241,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const double rc2s = p.r_cut_box_sq * p.box_sq;
   const double band = 1e-8 * rc2s;
   const double sovr = (1.0 / 1.77) * (1.0 + 1e-6);
-  const int band_hi = __double2hiint(band), sovr_hi = __double2hiint(sovr);
+  const unsigned band2 = 2u * (unsigned)__double2hiint(band);
+  const int sovr_hi = __double2hiint(sovr);
   const double sci = 1.0 / (double)sc;
   const __half *hq = reinterpret_cast<const __half *>(hp);
   const unsigned ux_s = (unsigned)__cvta_generic_to_shared(ux);
@@ -249,11 +253,15 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const int nrp_int = (g.nx_own - nbl) * nyb, nrp_bnd = nbl * nyb;
   if (a.halo.err && a.halo.err[5]) return;  // a neighbour's message timed out earlier in this run
   if (tid == 0) s_halo = a.halo.stamp_left == nullptr;
+  if (tid == 0) {  // the dummy candidate (never overwritten: the staged set stays below U_CAP)
+    ux[U_CAP] = uy[U_CAP] = uz[U_CAP] = 1e150;
+    if (MODE == T2_HESS) gx[U_CAP] = gy[U_CAP] = gz[U_CAP] = 0.0;
+  }
 
   for (;;) {
     // ---- next work item ----------------------------------------------------------------------------------------
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u, s_maxwin = 0;
+    if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u;
     const int halo_ok = s_halo;  // read between the two barriers: thread 0 only writes it after the second one
     __syncthreads();
     const int item = s_item;
@@ -327,9 +335,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
     unsigned npf = 0u;
     int ovr = 0;
 
-    int z = 0;  // the cell that holds atom g0: cumf(z) <= g0 < cumf(z + 1)
-    for (int step = 512; step >= 1; step >>= 1)
-      if (z + step < sc && cumf(z + step) <= gA) z += step;
+    // the cell that holds atom g0: cumf(z) <= g0 < cumf(z + 1) (recorded by the table kernel)
+    int z = tab[16 + nrp + (size_t)nrp * gstride + (size_t)rp * gstride + grp];
     for (int g0 = gA; g0 < gB;) {
       // ---- chunk extent: the next <= U_NT atoms, over at most ncz_max cells ----------------------------------
       __syncthreads();  // the previous chunk is done with shared memory
@@ -408,17 +415,18 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         k0 = inA ? 0 : 3;
       };
       // longest window (9 consecutive entries of 3 consecutive cells are three windows; check each)
+      bool too_long;
       {
         int mw = 0;
         for (int e = tid; e < (ncz + 2) * 2; e += U_NT) {
           const int c = e >> 1, k0 = (e & 1) * 3;
           mw = max(mw, S[c * U_K + k0 + 9] - S[c * U_K + k0]);
         }
-        mw = __reduce_max_sync(FULL, mw);
-        if (lane == 0) atomicMax(&s_maxwin, mw);
+        // (the barrier itself carries the one bit the chunk needs: is any window too long for its mask words?)
+        mw = __syncthreads_or(mw > 32 * U_WW - 2);
+        too_long = mw != 0;
       }
-      __syncthreads();
-      const bool slow = total > U_CAP || s_maxwin > 32 * U_WW - 2;
+      const bool slow = total > U_CAP || too_long;
 
       if (slow) {
         // ---- crowded neighbourhood (does not occur in a fluid): exact arithmetic straight from global memory ----
@@ -461,7 +469,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           }
         }
         __syncthreads();
-        if (tid == 0) s_maxwin = 0;
         g0 = g1;
         z += ncz - 1;
         while (z < sc - 1 && cumf(z + 1) <= g0) z++;
@@ -564,7 +571,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         // (mask word, shared-memory address of ux[c] for the candidate c of bit 31); bit p <-> candidate c + 31 - p
         uint2 mw[U_NWORDS];
         int nw = 0;
-        unsigned pc = 0u;  // survivors of the filter: in-range pairs = pc - (those phase 2 rejects)
         double fix = 0.0, fiy = 0.0, fiz = 0.0;  // T2_HESS: this atom's force
         if constexpr (MODE == T2_HESS) {
           fix = gx[self], fiy = gy[self], fiz = gz[self];
@@ -574,7 +580,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             for (; nw < U_NWORDS; nw++) {
               const uint2 m = mp[nw];
               if (m.x == 0u) break;
-              pc += __popc(m.x);
               mw[nw] = make_uint2(m.x, ux_s + 8u * m.y);  // kept as staged index of bit 31's candidate
             }
           }
@@ -618,7 +623,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
                   // second member: shared-memory address of the candidate a leading-zero count of 0 stands for
                   mw[nw] = make_uint2(wd, ux_s + 8u * (unsigned)(c31 - 31));
                   nw++;
-                  pc += __popc(wd);
                 }
               }
             }
@@ -638,8 +642,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         // two independent fp64 chains (the kernel is latency-, not fp64-throughput-bound); a dead slot gets
         // s = 1e300, whose sr^6 underflows to exactly 0, so no branch is needed around the arithmetic.
         double fx = 0.0, fy = 0.0, fz = 0.0;
-        const unsigned self_addr = ux_s + 8u * (unsigned)self;
-        npf += pc;
+        const unsigned dummy_addr = ux_s + 8u * (unsigned)U_CAP;
         int nd = 0;
         int defer[4];
         int ww = 0;
@@ -680,26 +683,24 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           const int z1 = __clz(cm | 1u);
           cm &= ~(0x80000000u >> z1);
           cur.x = cm;
-          // a dead slot reads the atom's own coordinates (any valid address would do); its s is replaced below
-          const unsigned a0 = live0 ? cur.y + 8u * (unsigned)z0 : self_addr;
-          const unsigned a1 = live1 ? cur.y + 8u * (unsigned)z1 : self_addr;
-          const double dx0 = uix - lds_f64(a0), dy0 = uiy - lds_f64(a0 + 8u * U_CAP),
-                       dz0 = uiz - lds_f64(a0 + 16u * U_CAP);
-          const double dx1 = uix - lds_f64(a1), dy1 = uiy - lds_f64(a1 + 8u * U_CAP),
-                       dz1 = uiz - lds_f64(a1 + 16u * U_CAP);
+          // a dead slot reads the dummy candidate: out of range by the same tests as a real pair
+          const unsigned a0 = live0 ? cur.y + 8u * (unsigned)z0 : dummy_addr;
+          const unsigned a1 = live1 ? cur.y + 8u * (unsigned)z1 : dummy_addr;
+          const double dx0 = uix - lds_f64(a0), dy0 = uiy - lds_f64(a0 + 8u * U_STR),
+                       dz0 = uiz - lds_f64(a0 + 16u * U_STR);
+          const double dx1 = uix - lds_f64(a1), dy1 = uiy - lds_f64(a1 + 8u * U_STR),
+                       dz1 = uiz - lds_f64(a1 + 16u * U_STR);
           double s0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), s1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
           const int e0 = __double2hiint(s0 - rc2s), e1 = __double2hiint(s1 - rc2s);
-          // Survivors of the filter were counted in phase 1; a false positive (about 3 % of them: the fp16 margin) only
-          // takes one off the count and turns the slot into a dead one - no branch, most warp iterations have one.
+          // In-range pairs are counted here.  A false positive of the filter (about 3 % of the survivors: the fp16
+          // margin) and the dummy of a dead slot are simply not in range - no branch, most warp iterations have one.
           // |s - rc2s| <= band or s < sovr (tested conservatively on the high words: integer pipe, not fp64) is rare
           // and leaves the hot path: such pairs are set aside and decided with the reference's exact operation sequence.
-          const bool n0 = ((e0 & 0x7fffffff) <= band_hi) | (__double2hiint(s0) <= sovr_hi);
-          const bool n1 = ((e1 & 0x7fffffff) <= band_hi) | (__double2hiint(s1) <= sovr_hi);
-          const bool b0 = live0 & n0, b1 = live1 & n1;
-          npf -= (live0 & !n0 & (e0 >= 0)) ? 1u : 0u;
-          npf -= (live1 & !n1 & (e1 >= 0)) ? 1u : 0u;
-          live0 = live0 & !n0 & (e0 < 0);
-          live1 = live1 & !n1 & (e1 < 0);
+          const bool b0 = (((unsigned)e0 << 1) <= band2) | (__double2hiint(s0) <= sovr_hi);
+          const bool b1 = (((unsigned)e1 << 1) <= band2) | (__double2hiint(s1) <= sovr_hi);
+          const bool in0 = (e0 < 0) & !b0, in1 = (e1 < 0) & !b1;
+          npf += in0 ? 1u : 0u;
+          npf += in1 ? 1u : 0u;
           if (b0 | b1) {
             if (b0) defer[nd++] = (int)((a0 - ux_s) >> 3);
             if (b1) defer[nd++] = (int)((a1 - ux_s) >> 3);
@@ -713,13 +714,13 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
               nd = 0;
             }
           }
-          s0 = live0 ? s0 : 1e300;
-          s1 = live1 ? s1 : 1e300;
+          s0 = in0 ? s0 : 1e300;
+          s1 = in1 ? s1 : 1e300;
           if constexpr (MODE == T2_HESS) {
-            const double ex0 = fix - lds_f64(a0 + 24u * U_CAP), ey0 = fiy - lds_f64(a0 + 32u * U_CAP),
-                         ez0 = fiz - lds_f64(a0 + 40u * U_CAP);
-            const double ex1 = fix - lds_f64(a1 + 24u * U_CAP), ey1 = fiy - lds_f64(a1 + 32u * U_CAP),
-                         ez1 = fiz - lds_f64(a1 + 40u * U_CAP);
+            const double ex0 = fix - lds_f64(a0 + 24u * U_STR), ey0 = fiy - lds_f64(a0 + 32u * U_STR),
+                         ez0 = fiz - lds_f64(a0 + 40u * U_STR);
+            const double ex1 = fix - lds_f64(a1 + 24u * U_STR), ey1 = fiy - lds_f64(a1 + 32u * U_STR),
+                         ez1 = fiz - lds_f64(a1 + 40u * U_STR);
             U_HESS(dx0, dy0, dz0, s0, ex0, ey0, ez0);
             U_HESS(dx1, dy1, dz1, s1, ex1, ey1, ez1);
           } else {
@@ -747,10 +748,13 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         }
       }
       __syncthreads();
-      if (tid == 0) s_q2max = 0u, s_maxwin = 0;
+      if (tid == 0) s_q2max = 0u;
       g0 = g1;
-      z += ncz - 1;  // the cell that holds the next chunk's first atom (skipping empty cells)
-      while (z < sc - 1 && cumf(z + 1) <= g0) z++;
+      // the cell that holds the next chunk's first atom (skipping empty cells): cumloc[k] = cumf(z + k), k < U_MAXC,
+      // is still this chunk's table (it is rewritten after the barrier at the top of the chunk loop)
+      int zn = z + ncz - 1;
+      while (zn < sc - 1 && (zn + 1 - z < U_MAXC ? cumloc[zn + 1 - z] : cumf(zn + 1)) <= g0) zn++;
+      z = zn;
     }
     // cut = sr12 - sr6, pot = cut - pot_cut, vir = cut + sr12, lap = (22 sr12 - 5 sr6) sr2 (md_lj_module.py:104-108)
     Acc acc;
