@@ -92,6 +92,13 @@ def lib():
     L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]
     L.atlj_sim_mg_set_peers.argtypes = [_vp, _vp, _vp]
     L.atlj_sim_mg_trace.argtypes = [_vp, C.c_int, _vp]
+    L.atlj_sim_run_baoab_mg.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp]
+    L.atlj_sim_run_nhc_mg.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
+    L.atlj_sim_mg_phase1_baoab.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int]
+    L.atlj_sim_mg_nhc_open.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double]
+    L.atlj_sim_mg_phase1_nhc.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.atlj_sim_mg_nhc_close.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _vp]
+    L.atlj_sim_mg_nhc_finish.argtypes = [_vp, C.c_int, _vp, _vp]
     L.atlj_sim_mg_blob_bytes.restype = C.c_int64
     L.atlj_sim_mg_ipc_blob.argtypes = [_vp, C.c_char_p]
     L.atlj_sim_mg_ipc_open.argtypes = [_vp, C.c_char_p, C.c_char_p]

@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const int l = threadIdx.x + k * IT;
-      if (l < ne) {
+      if (l < ne && slab && sl.assign_only) {
+        // another integrator has moved (and wrapped) the atoms: cell assignment + migration only
+        const size_t e = e0 + l;
+        xs[l] = r[e];
+        if (btile) vs[l] = v[e];
+      } else if (l < ne) {
         const size_t e = e0 + l;
         const double ff = f[e];
         double vv = v[e];

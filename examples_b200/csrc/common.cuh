@@ -146,6 +146,8 @@ struct SlabArgs {
   int *xstep;                        // device counter of exchange steps: parity = *xstep & 1 selects the buffer, *xstep + 1
                                      // is the stamp published in the header when the message is complete; the kernel's
                                      // last CTA moves the counter on (so the launch arguments do not depend on the step)
+  int assign_only;                   // the atoms were moved (and wrapped) by another integrator kernel (BAOAB, Nose-Hoover):
+                                     // no kick, no drift - cell assignment and migration only
   int *mig_cnt;                      // [0], [1] slot counters, [2] finished boundary tiles
   // Only atoms of the first and the last owned layer can leave the slab in one step.  The sorted arrays hold the
   // layers one after the other, so the tiles of those two layers are integrated FIRST and the migration messages are

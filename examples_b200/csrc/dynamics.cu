@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(IT) baoab_kernel(int n, double *__restrict__ r
                                                    const double *__restrict__ f, const int *__restrict__ id, double t,
                                                    BoxDiv box, double decay, double amp,
                                                    const double *__restrict__ noise, unsigned long long seed,
-                                                   unsigned step) {
+                                                   unsigned step, const int *__restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);  // slab ranks keep the owned-atom count on the device
   for (int i = blockIdx.x * IT + threadIdx.x; i < n; i += gridDim.x * IT) {
     double g[3];
     const int gid = id[i];
@@ -287,7 +288,7 @@ static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const dou
     baoab_kernel<<<atom_blocks(n), IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], s->f, s->id[s->cur], t, make_box_div(s->p.box),
                                                    decay, amp,
                                                    noise_dev ? noise_dev + (size_t)k * 3 * (size_t)s->n_total : nullptr,
-                                                   seed, (unsigned)(s->step_count + k));
+                                                   seed, (unsigned)(s->step_count + k), nullptr);
     ATLJ_LAUNCHED();
     Timer::end(s);
     if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
@@ -299,7 +300,166 @@ static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const dou
   return sim_copy_rec(s, rec_host, nsteps);
 }
 
+// ---- the thermostats on slab ranks (widened) -------------------------------------------------------
+// The integrator's own elementwise kernels run on the owned atoms (count on the device); mg.cu then bins them,
+// migrates the leavers, sorts, sends the halo layers and runs the pair kernel.  BAOAB draws its noise from Philox keyed
+// by (seed; GLOBAL atom id, step), so a trajectory does not depend on the decomposition; the Nose-Hoover chain needs
+// the GLOBAL sum v^2 once per step: the step record is all-reduced (NCCL, 96 bytes) before the chain kernel reads it.
+static int baoab_move(atlj_sim *s, double dt, double decay, double amp, const double *noise_dev, uint64_t seed,
+                      unsigned step) {
+  const int cap = (int)mg_own_cap(s);
+  baoab_kernel<<<atom_blocks(cap), IT, 0, s->st>>>(cap, s->r[s->cur], s->v[s->cur], s->f, s->id[s->cur], dt / 2,
+                                                   make_box_div(s->p.box), decay, amp, noise_dev, seed, step, mg_n_dev(s));
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+
+static int nhc_open(atlj_sim *s, int m, const double *eta, const double *p_eta, const double *q) {
+  double h[32];
+  memset(h, 0, sizeof(h));
+  h[1] = 1.0;
+  for (int j = 0; j < m; j++) h[2 + j] = eta[j], h[10 + j] = p_eta[j], h[18 + j] = q[j];
+  ATLJ_CUDA(cudaMemcpyAsync(s->scal + SC_NHC, h, sizeof(h), cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));  // h is on the stack
+  return ATLJ_OK;
+}
+// chain (first call of a run: with the global sum v^2 in *ksq) + u2(dt/2) u1(dt) with the pending factor
+static int nhc_move(atlj_sim *s, double dt, double temperature, double g, int m, const double *ksq) {
+  int rc;
+  double *st = s->scal + SC_NHC;
+  nhc_chain_kernel<<<1, 32, 0, s->st>>>(st, m, dt, temperature, g, ksq, nullptr);
+  ATLJ_LAUNCHED();
+  if ((rc = launch_kick_drift(s->st, 3 * mg_own_cap(s), s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box, st + 1,
+                              mg_n_dev(s))))
+    return rc;
+  set_scalar_kernel<<<1, 1, 0, s->st>>>(st + 1, 1.0);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+// the closing chain update from the GLOBAL record of the step (rec[4] = sum v^2 over all ranks)
+static int nhc_close(atlj_sim *s, double dt, double temperature, double g, int m, double *rec) {
+  nhc_chain_kernel<<<1, 32, 0, s->st>>>(s->scal + SC_NHC, m, dt, temperature, g, rec + 4, rec);
+  ATLJ_LAUNCHED();
+  return ATLJ_OK;
+}
+static int nhc_finish(atlj_sim *s, int m, double *eta, double *p_eta) {
+  double *st = s->scal + SC_NHC;
+  double h[32];
+  scale_v_kernel<<<integ_blocks(3 * mg_own_cap(s)), IT, 0, s->st>>>(3 * (long long)s->n, s->v[s->cur], st + 1);
+  ATLJ_LAUNCHED();
+  set_scalar_kernel<<<1, 1, 0, s->st>>>(st + 1, 1.0);
+  ATLJ_LAUNCHED();
+  ATLJ_CUDA(cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  for (int j = 0; j < m; j++) eta[j] = h[2 + j], p_eta[j] = h[10 + j];
+  return ATLJ_OK;
+}
+
 extern "C" {
+
+int atlj_sim_run_baoab_mg(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int nsteps,
+                          double *rec_host) {
+  if (!s || !s->configured || !s->mg.on || nsteps < 0) return ATLJ_ERR_ARG;
+  if (!mg_connected(s)) {
+    set_error("run_baoab_mg: connect the ranks first");
+    return ATLJ_ERR_ARG;
+  }
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc || (rc = mg_begin(s))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)(nsteps > 0 ? nsteps : 1), s->st));
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    if ((rc = baoab_move(s, dt, o_decay, o_noise, nullptr, seed, (unsigned)(s->step_count + k)))) return rc;
+    if ((rc = mg_assign_exchange_force(s, rec, k == 0))) return rc;
+    if ((rc = launch_kick_sums(s->st, 3 * mg_own_cap(s), s->v[s->cur], s->f, dt / 2, s->vf_partials, rec + 4,
+                               s->cb.err + 4, mg_n_dev(s))))
+      return rc;
+  }
+  if (nsteps > 0 && (rc = mg_allreduce(s, s->rec_dev, (size_t)nsteps * ATLJ_NREC))) return rc;
+  s->step_count += nsteps;
+  if ((rc = mg_end(s))) return rc;
+  rc = sim_copy_rec(s, rec_host, nsteps);
+  if (rec_host)
+    for (int k = 0; k < nsteps; k++)
+      if (rec_host[(size_t)k * ATLJ_NREC + 7] > 0.0) rec_host[(size_t)k * ATLJ_NREC + 7] = 1.0;
+  return rc;
+}
+
+int atlj_sim_run_nhc_mg(atlj_sim *s, double dt, double temperature, double g, int m, double *eta, double *p_eta,
+                        const double *q, int nsteps, double *rec_host) {
+  if (!s || !s->configured || !s->mg.on || nsteps < 0 || m < 1 || m > 8 || !eta || !p_eta || !q) return ATLJ_ERR_ARG;
+  if (!mg_connected(s)) {
+    set_error("run_nhc_mg: connect the ranks first");
+    return ATLJ_ERR_ARG;
+  }
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc || (rc = mg_begin(s)) || (rc = nhc_open(s, m, eta, p_eta, q))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)(nsteps > 0 ? nsteps : 1), s->st));
+  // global sum v^2 of the starting velocities
+  double *ksq = s->scal + SC_SUMV;
+  if ((rc = launch_kick_sums(s->st, 3 * mg_own_cap(s), s->v[s->cur], s->f, 0.0, s->vf_partials, ksq, s->cb.err + 4,
+                             mg_n_dev(s))) ||
+      (rc = mg_allreduce(s, ksq, 2)))
+    return rc;
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    if ((rc = nhc_move(s, dt, temperature, g, m, k == 0 ? ksq : nullptr))) return rc;
+    if ((rc = mg_assign_exchange_force(s, rec, k == 0))) return rc;
+    if ((rc = launch_kick_sums(s->st, 3 * mg_own_cap(s), s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4,
+                               s->cb.err + 4, mg_n_dev(s))))
+      return rc;
+    // the chain needs the GLOBAL sum v^2: the whole record of the step is summed over the ranks here
+    if ((rc = mg_allreduce(s, rec, ATLJ_NREC)) || (rc = nhc_close(s, dt, temperature, g, m, rec))) return rc;
+  }
+  s->step_count += nsteps;
+  if ((rc = mg_end(s)) || (rc = nhc_finish(s, m, eta, p_eta))) return rc;
+  rc = sim_copy_rec(s, rec_host, nsteps);
+  if (rec_host)
+    for (int k = 0; k < nsteps; k++)
+      if (rec_host[(size_t)k * ATLJ_NREC + 7] > 0.0) rec_host[(size_t)k * ATLJ_NREC + 7] = 1.0;
+  return rc;
+}
+
+/* the same steps cut into phases for ranks emulated in one process (tests): <integrator>_phase1 on every rank, then
+ * atlj_sim_mg_phase2 on every rank, then atlj_sim_mg_phase3 (pair kernel, closing half kick, LOCAL sums) on every rank;
+ * Nose-Hoover: the caller sums the records over the ranks and hands the global record to atlj_sim_mg_nhc_close */
+int atlj_sim_mg_phase1_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int first) {
+  if (!s || !s->mg.on) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, 1);
+  if (rc || (rc = mg_begin(s))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if ((rc = baoab_move(s, dt, o_decay, o_noise, nullptr, seed, (unsigned)s->step_count))) return rc;
+  s->step_count += 1;
+  return mg_phase1_assign(s, first != 0);
+}
+int atlj_sim_mg_nhc_open(atlj_sim *s, int m, const double *eta, const double *p_eta, const double *q, double ksq_global) {
+  if (!s || !s->mg.on || m < 1 || m > 8) return ATLJ_ERR_ARG;
+  int rc = nhc_open(s, m, eta, p_eta, q);
+  if (rc) return rc;
+  ATLJ_CUDA(cudaMemcpyAsync(s->scal + SC_SUMV, &ksq_global, sizeof(double), cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  return ATLJ_OK;
+}
+int atlj_sim_mg_phase1_nhc(atlj_sim *s, double dt, double temperature, double g, int m, int first) {
+  if (!s || !s->mg.on) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_rec(s, 1);
+  if (rc || (rc = mg_begin(s))) return rc;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC, s->st));
+  if ((rc = nhc_move(s, dt, temperature, g, m, first ? s->scal + SC_SUMV : nullptr))) return rc;
+  s->step_count += 1;
+  return mg_phase1_assign(s, first != 0);
+}
+int atlj_sim_mg_nhc_close(atlj_sim *s, double dt, double temperature, double g, int m, double *rec_global_host) {
+  if (!s || !s->mg.on || !rec_global_host) return ATLJ_ERR_ARG;
+  ATLJ_CUDA(cudaMemcpyAsync(s->rec_dev, rec_global_host, sizeof(double) * ATLJ_NREC, cudaMemcpyHostToDevice, s->st));
+  int rc = nhc_close(s, dt, temperature, g, m, s->rec_dev);
+  if (rc) return rc;
+  return sim_copy_rec(s, rec_global_host, 1);
+}
+int atlj_sim_mg_nhc_finish(atlj_sim *s, int m, double *eta, double *p_eta) {
+  if (!s || !s->mg.on || m < 1 || m > 8) return ATLJ_ERR_ARG;
+  return nhc_finish(s, m, eta, p_eta);
+}
 
 int atlj_sim_run_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int nsteps,
                        double *rec_host) {

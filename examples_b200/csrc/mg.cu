@@ -223,9 +223,10 @@ static const int *tile2_rows(atlj_sim *s) {
 // record pointer follows the device counter cnt_dev[11] (rec = base of the records), as the stamps and buffer parities
 // always follow cnt_dev[10]
 static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, double *rec, int nb_prev, bool replay,
-                  bool counts_zeroed) {
+                  bool counts_zeroed, bool assign_only = false) {
   MgState &m = s->mg;
   SlabArgs sl;
+  sl.assign_only = assign_only ? 1 : 0;
   sl.n_dev = m.cnt_dev + 1, sl.id = s->id[s->cur];
   sl.to_left0 = mig_recv(m.peer_arena[0], m, 1, 0), sl.to_left1 = mig_recv(m.peer_arena[0], m, 1, 1);
   sl.to_right0 = mig_recv(m.peer_arena[1], m, 0, 0), sl.to_right1 = mig_recv(m.peer_arena[1], m, 0, 1);
@@ -351,6 +352,42 @@ static int tail(atlj_sim *s, double dt, double *rec, int nb) {
 }
 
 // host copy of the owned count <-> device
+static int push_n(atlj_sim *s);
+static int pull_n(atlj_sim *s);
+
+// ---- building blocks for the other integrators on slabs (dynamics.cu): the integrator's own kernels move the owned
+// atoms (count on the device: mg_n_dev), then mg_assign_exchange bins them, migrates the leavers, sorts, sends the halo
+// layers and runs the pair kernel; the totals of the step go to rec (LOCAL sums) ------------------------------------
+const int *mg_n_dev(const atlj_sim *s) { return s->mg.cnt_dev + 1; }
+long long mg_own_cap(const atlj_sim *s) { return s->mg.own_cap; }
+int mg_begin(atlj_sim *s) { return push_n(s); }
+int mg_end(atlj_sim *s) { return pull_n(s); }
+int mg_assign_exchange_force(atlj_sim *s, double *rec, bool first) {
+  int rc, nb;
+  if ((rc = phase1(s, s->st, 0.0, false, nullptr, 0, false, !first, true)) || (rc = phase2(s, s->st, nullptr, rec, false)))
+    return rc;
+  if ((nb = phase3(s, s->st, false)) < 0) return nb;
+  return launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s));
+}
+// emulation (ranks of one process in lockstep): phase 1 of a step whose atoms were moved by another integrator
+int mg_phase1_assign(atlj_sim *s, bool first) {
+  if (!s->mg.peer_arena[0]) return ATLJ_ERR_ARG;
+  int rc = phase1(s, s->st, 0.0, false, nullptr, 0, false, !first, true);
+  if (rc) return rc;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  return ATLJ_OK;
+}
+// sum over the ranks, in place, on the sim's stream (NCCL; every rank ends up with the same bits)
+int mg_allreduce(atlj_sim *s, double *dev, size_t count) {
+  if (!s->mg.comm) {
+    set_error("slab run: connect the ranks first (atlj_sim_mg_connect)");
+    return ATLJ_ERR_ARG;
+  }
+  ATLJ_NCCL(g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)s->mg.comm, s->st));
+  return ATLJ_OK;
+}
+bool mg_connected(const atlj_sim *s) { return s->mg.comm != nullptr; }
+
 static int push_n(atlj_sim *s) {
   s->mg.cnt_host[0] = (int)s->n;
   s->mg.cnt_host[1] = (int)s->mg.step;  // exchange step counter (stamps, buffer parity)

@@ -106,4 +106,13 @@ bool sim_tile2(const atlj_sim *s);
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
 int sim_ensure_rec(atlj_sim *s, int64_t nrec);
 void sim_mg_destroy(atlj_sim *s);
+// slab building blocks for the integrators of dynamics.cu (mg.cu)
+const int *mg_n_dev(const atlj_sim *s);  // owned atoms, on the device
+long long mg_own_cap(const atlj_sim *s);
+int mg_begin(atlj_sim *s);               // host -> device counters at the start of a run
+int mg_end(atlj_sim *s);                 // device -> host owned count at its end
+int mg_assign_exchange_force(atlj_sim *s, double *rec, bool first);  // bin, migrate, sort, halo, pair kernel, totals
+int mg_phase1_assign(atlj_sim *s, bool first);  // emulation: cell assignment + migration of a step moved elsewhere
+int mg_allreduce(atlj_sim *s, double *dev, size_t count);
+bool mg_connected(const atlj_sim *s);
 }  // namespace atlj

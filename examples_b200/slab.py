@@ -122,6 +122,28 @@ class SlabRank(Simulation):
         """Force evaluation on the current positions = one step with dt = 0 (kick and drift are exact no-ops)."""
         return self.run_nve(0.0, 1)[0]
 
+    def run_baoab(self, dt, gamma, temperature, nsteps, seed=1, noise=None):
+        """BAOAB Langevin steps on the slab (bd_nvt_lj.py:221-233); the device noise is keyed by the GLOBAL atom id, so
+        the trajectory is that of the single-domain run with the same seed."""
+        assert noise is None, "injected noise is a single-domain test facility"
+        rec = np.zeros((nsteps, NREC))
+        decay, amp = self._o_scalars(dt, gamma, temperature)
+        _lib.check(_lib.lib().atlj_sim_run_baoab_mg(self._h, float(dt), decay, amp, int(seed), int(nsteps),
+                                                    rec.ctypes.data))
+        return rec
+
+    def run_nhc(self, dt, temperature, eta, p_eta, q, nsteps, g=None):
+        """Nose-Hoover chain steps on the slab (md_nvt_lj.py:270-288); eta, p_eta updated in place on every rank."""
+        rec = np.zeros((nsteps, NREC))
+        for a in (eta, p_eta, q):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        if g is None:
+            g = 3 * (self.n_total - 1)
+        _lib.check(_lib.lib().atlj_sim_run_nhc_mg(self._h, float(dt), float(temperature), float(g), len(q),
+                                                  eta.ctypes.data, p_eta.ctypes.data, q.ctypes.data, int(nsteps),
+                                                  rec.ctypes.data))
+        return rec
+
 
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
@@ -170,6 +192,49 @@ class EmulatedSlabs:
 
     def run_nve(self, dt, nsteps):
         return np.array([self.step(dt) for _ in range(nsteps)])
+
+    def _finish(self, dt):
+        for s in self.ranks:
+            s.phase2()
+        rec = sum(s.phase3(dt) for s in self.ranks)
+        rec[7] = 1.0 if rec[7] > 0 else 0.0
+        return rec
+
+    def run_baoab(self, dt, gamma, temperature, nsteps, seed=1):
+        decay, amp = Simulation._o_scalars(dt, gamma, temperature)
+        out = []
+        for k in range(nsteps):
+            for s in self.ranks:
+                _lib.check(_lib.lib().atlj_sim_mg_phase1_baoab(s._h, float(dt), decay, amp, int(seed), int(k == 0)))
+            out.append(self._finish(dt))
+        return np.array(out)
+
+    def run_nhc(self, dt, temperature, eta, p_eta, q, nsteps, g=None):
+        L = _lib.lib()
+        n = self.ranks[0].n_total
+        if g is None:
+            g = 3 * (n - 1)
+        m = len(q)
+        ksq = sum(float(np.sum(s.download_sorted()[1] ** 2)) for s in self.ranks)   # global sum v^2 at the start
+        for s in self.ranks:
+            _lib.check(L.atlj_sim_mg_nhc_open(s._h, m, eta.ctypes.data, p_eta.ctypes.data, q.ctypes.data, ksq))
+        out = []
+        for k in range(nsteps):
+            for s in self.ranks:
+                _lib.check(L.atlj_sim_mg_phase1_nhc(s._h, float(dt), float(temperature), float(g), m, int(k == 0)))
+            rec = self._finish(dt)
+            recs = []
+            for s in self.ranks:                                                     # every rank: same global record
+                rk = rec.copy()
+                _lib.check(L.atlj_sim_mg_nhc_close(s._h, float(dt), float(temperature), float(g), m, rk.ctypes.data))
+                recs.append(rk)
+            assert all(np.array_equal(recs[0], rk) for rk in recs)
+            out.append(recs[0])
+        for s in self.ranks:
+            e, p = eta.copy(), p_eta.copy()
+            _lib.check(L.atlj_sim_mg_nhc_finish(s._h, m, e.ctypes.data, p.ctypes.data))
+        eta[:], p_eta[:] = e, p
+        return np.array(out)
 
     def gather(self):
         """r, v, f of the whole system in the original atom order."""

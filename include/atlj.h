@@ -193,6 +193,14 @@ int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
 /* nsteps velocity-Verlet steps (md_nve_lj.py:178-192) of the whole system, no host synchronisation per step.
  * rec_host (nsteps, ATLJ_NREC) holds the GLOBAL sums on every rank.  dt = 0 gives a plain force evaluation. */
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host);
+/* The thermostats on slab ranks.  BAOAB (bd_nvt_lj.py:221-233): the noise is keyed by (seed; global atom id, step), so the
+ * trajectory does not depend on the decomposition.  Nose-Hoover chain (md_nvt_lj.py:270-288): the chain needs the global
+ * sum v^2 once per step - the 12-double step record is all-reduced (NCCL) inside the step; eta, p_eta as in
+ * atlj_sim_run_nhc, identical on every rank.  Records are global sums on every rank. */
+int atlj_sim_run_baoab_mg(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int nsteps,
+                          double *rec_host);
+int atlj_sim_run_nhc_mg(atlj_sim *s, double dt, double temperature, double g, int m, double *eta, double *p_eta,
+                        const double *q, int nsteps, double *rec_host);
 /* The same step cut into its three device phases, for driving several ranks of one process in lockstep (tests):
  * phase1 = kick, drift, leavers written to the neighbours; phase2 = append arrivals, bin + sort, boundary layers
  * written into the neighbours' halo regions; phase3 = pair kernel, kick, LOCAL sums.  Every rank must finish a phase
@@ -200,6 +208,15 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host);
 int atlj_sim_mg_phase1(atlj_sim *s, double dt);
 int atlj_sim_mg_phase2(atlj_sim *s);
 int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host);
+/* ... and phase 1 of the thermostatted steps (phase 2 and 3 are the same).  Nose-Hoover in lockstep emulation:
+ * atlj_sim_mg_nhc_open (chain state + the GLOBAL sum v^2 of the start velocities) once, then per step phase1_nhc,
+ * phase2, phase3 on every rank, the caller sums the records over the ranks and gives the global record to
+ * atlj_sim_mg_nhc_close on every rank (chain update; rec[4], rec[10] filled in); atlj_sim_mg_nhc_finish at the end. */
+int atlj_sim_mg_phase1_baoab(atlj_sim *s, double dt, double o_decay, double o_noise, uint64_t seed, int first);
+int atlj_sim_mg_nhc_open(atlj_sim *s, int m, const double *eta, const double *p_eta, const double *q, double ksq_global);
+int atlj_sim_mg_phase1_nhc(atlj_sim *s, double dt, double temperature, double g, int m, int first);
+int atlj_sim_mg_nhc_close(atlj_sim *s, double dt, double temperature, double g, int m, double *rec_global_host);
+int atlj_sim_mg_nhc_finish(atlj_sim *s, int m, double *eta, double *p_eta);
 
 /* ---- host-buffer step (the end-to-end path of bench.py) --------------------------------------
  * One velocity-Verlet step (md_nve_lj.py:178-192) whose state lives in HOST memory, as it does in the

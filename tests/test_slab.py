@@ -127,3 +127,54 @@ def test_emulated_slabs_match_single_domain(nc, world):
     owners0 = [set(s.download_sorted()[3].tolist()) for s in many.ranks]
     assert sum(len(o) for o in owners0) == n
     one.close(), many.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_slabs_baoab_and_nose_hoover(world):
+    """SURVEY.md 8e widened: the thermostats on slabs.  BAOAB (bd_nvt_lj.py:221-233) draws its noise from Philox keyed
+    by the GLOBAL atom id and the step, the Nose-Hoover chain (md_nvt_lj.py:270-288) is fed the all-reduced sum v^2:
+    both must reproduce the single-domain trajectory - positions, velocities, forces bit for bit (per-atom sums run
+    in the same order), the step records to summation order."""
+    from examples_b200 import _lib
+    from examples_b200.device import Simulation
+    from examples_b200.lattice import ran_velocities
+    from examples_b200.slab import EmulatedSlabs
+    _lib.set_multi_max(0)  # same (tiled) pair kernel on both sides
+    n, box, r = liquid_like(10, 0.75, 0.06)
+    v = ran_velocities(n, 1.2)
+    nsteps = 40
+    # ---- BAOAB
+    one = Simulation(box, 2.5, r, v)
+    one.force()
+    many = EmulatedSlabs(box, 2.5, r, v, world)
+    many.force()
+    t1 = one.run_baoab(0.005, 1.0, 1.0, nsteps, seed=11)
+    tm = many.run_baoab(0.005, 1.0, 1.0, nsteps, seed=11)
+    for k in range(6):
+        assert rel_err(tm[:, k], t1[:, k]) < 1e-9, k
+    assert np.array_equal(tm[:, 8], t1[:, 8]) and np.all(tm[:, 11] == n)
+    r1, v1, f1 = one.download()
+    rm, vm, fm = many.gather()
+    assert np.array_equal(rm, r1) and np.array_equal(vm, v1) and np.array_equal(fm, f1)
+    one.close(), many.close()
+    # ---- Nose-Hoover chain (m = 3, the reference's defaults: md_nvt_lj.py:245-257)
+    m, g = 3, 3 * (n - 1)
+    q = np.full(m, 1.0 * 2.0 ** 2)
+    q[0] = g * 1.0 * 2.0 ** 2
+    e1, p1 = np.zeros(m), np.array([0.3, -0.2, 0.1])
+    em, pm = e1.copy(), p1.copy()
+    one = Simulation(box, 2.5, r, v)
+    one.force()
+    many = EmulatedSlabs(box, 2.5, r, v, world)
+    many.force()
+    t1 = one.run_nhc(0.005, 1.0, e1, p1, q, nsteps)
+    tm = many.run_nhc(0.005, 1.0, em, pm, q, nsteps)
+    for k in (0, 1, 2, 3, 4, 5, 10):
+        assert rel_err(tm[:, k], t1[:, k]) < 1e-9, k
+    assert np.array_equal(tm[:, 8], t1[:, 8])
+    assert rel_err(em, e1) < 1e-10 and rel_err(pm, p1) < 1e-10
+    r1, v1, f1 = one.download()
+    rm, vm, fm = many.gather()
+    assert rel_err(rm, r1) < 1e-9 and rel_err(vm, v1) < 1e-9 and rel_err(fm, f1) < 1e-8
+    one.close(), many.close()

@@ -51,5 +51,39 @@ if rank == 0:
           and errs["f"] < 1e-8)
     print("slab NCCL check: world=%d N=%d steps=%d %s -> %s" % (world, n, nsteps, errs, "OK" if ok else "FAIL"), flush=True)
 sim.close()
+
+# ---- the thermostats on slabs: BAOAB (noise keyed by global atom id) and the Nose-Hoover chain (all-reduced sum v^2)
+from examples_b200 import _lib as L  # noqa: E402
+L.set_multi_max(0)
+m, g = 3, 3 * (n - 1)
+q = np.full(m, 4.0)
+q[0] = g * 4.0
+for what in ("baoab", "nhc"):
+    sim = SlabSimulation(box, 2.5, r, v, rank, world)
+    sim.force()
+    eta, p_eta = np.zeros(m), np.array([0.3, -0.2, 0.1])
+    rec = sim.run_baoab(0.005, 1.0, 1.0, nsteps, seed=5) if what == "baoab" else sim.run_nhc(0.005, 1.0, eta, p_eta, q, nsteps)
+    parts = [None] * world
+    dist.all_gather_object(parts, sim.download_sorted())
+    if rank == 0:
+        one = Simulation(box, 2.5, r, v)
+        one.force()
+        e1, p1 = np.zeros(m), np.array([0.3, -0.2, 0.1])
+        ref = one.run_baoab(0.005, 1.0, 1.0, nsteps, seed=5) if what == "baoab" else one.run_nhc(0.005, 1.0, e1, p1, q, nsteps)
+        r1, v1, f1 = one.download()
+        one.close()
+        rm, vm, fm = np.empty_like(r1), np.empty_like(r1), np.empty_like(r1)
+        for a, b, c, i in parts:
+            rm[i], vm[i], fm[i] = a, b, c
+        errs = {"traj": max(rel_err(rec[:, k], ref[:, k]) for k in range(6)), "r": rel_err(rm, r1), "v": rel_err(vm, v1),
+                "f": rel_err(fm, f1)}
+        if what == "nhc":
+            errs["eta"] = rel_err(eta, e1)
+            errs["conserved"] = rel_err(rec[:, 10], ref[:, 10])
+        good = all(x < 1e-8 for x in errs.values()) and np.array_equal(rec[:, 8], ref[:, 8])
+        ok = ok and good
+        print("slab NCCL check (%s): world=%d N=%d steps=%d %s -> %s" % (what, world, n, nsteps, errs, "OK" if good else "FAIL"),
+              flush=True)
+    sim.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
