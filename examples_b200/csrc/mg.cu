@@ -730,7 +730,7 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
                                (ncclComm_t)m.comm, s->st));
     Timer::end(s);
   }
-  s->step_count += nsteps;
+  if (dt != 0.0) s->step_count += nsteps;  // a dt = 0 "step" is a force evaluation: the RNG counter does not move
   if ((rc = pull_n(s))) return rc;
   rc = sim_copy_rec(s, rec_host, nsteps);
   if (rec_host)
