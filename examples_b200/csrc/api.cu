@@ -541,19 +541,36 @@ static int nve_fused_step(atlj_sim *s, cudaStream_t st, cudaStream_t side, doubl
   Phys p = s->p;
   p.strain = 0.0, p.shift = 0;
   const bool multi = sim_multi(s);
-  const bool direct = !multi && sim_direct(s);
-  const bool tile2 = !multi && !direct && sim_tile2(s);
-  const int cur = s->cur, alt = 1 - cur;
+  const bool direct = s->use_cells && !multi && sim_direct(s);
+  const bool tile2 = s->use_cells && !multi && !direct && sim_tile2(s);
+  const int cur = s->cur, alt = s->use_cells ? 1 - cur : cur;
   KdkLoop loop;
   loop.step_ctr = replay ? s->cb.err + 7 : nullptr;
   loop.tab0 = tile2 ? s->tile_tab : nullptr;
   loop.counts_zeroed = true;
+  loop.no_assign = !s->use_cells;
   Timer::begin(s, 2);
   const int nvf = launch_kdk_assign(st, s->g, n, s->r[cur], s->v[cur], s->f, 0.5 * dt, dt, p.box, first_kick, s->cb,
                                     s->vf_partials, rec, s->partials, nb_prev, p.model, nullptr,
                                     tile2 ? s->cb.err + 6 : nullptr, &loop);
   if (nvf < 0) return nvf;
   Timer::end(s);
+  if (!s->use_cells) {
+    // all-pairs route (sc < 4, the reference's N = 256 case): two launches per step
+    PairArgs a;
+    a.r = s->r[cur], a.fin = nullptr, a.cell_start = nullptr, a.cell_count = nullptr, a.f = s->f;
+    a.partials = s->partials, a.tile_tab = nullptr, a.masks = nullptr, a.natoms = n, a.per_cell = 0.0, a.g = s->g, a.p = p;
+    int nb = 0;
+    Timer::begin(s, 0);
+    if (multi) {
+      if ((nb = launch_pair_multi(st, a, false, n, false)) < 0) return nb;
+    } else if ((rc = launch_pair_all(st, s->r[cur], nullptr, n, p, s->f, s->partials, false, &nb))) {
+      return rc;
+    }
+    Timer::end(s);
+    *nb_out = nb;
+    return ATLJ_OK;
+  }
   Timer::begin(s, 1);
   if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
   PairArgs a;
@@ -693,17 +710,18 @@ int atlj_sim_run_nve(atlj_sim *s, double dt, int nsteps, int with_hessian, doubl
   if (rc || (rc = sim_ensure_forces(s, 0.0))) return rc;
   const long long n3 = 3 * s->n;
   const double half_dt = 0.5 * dt;  // md_nve_lj.py:182: 0.5 * dt evaluated first
-  if (!with_hessian && s->use_cells && nsteps > 0 && !s->unfused) {
+  if (!with_hessian && nsteps > 0 && !s->unfused) {
     const int n = (int)s->n;
-    const bool tile2 = !sim_multi(s) && !sim_direct(s) && sim_tile2(s);
+    const bool tile2 = s->use_cells && !sim_multi(s) && !sim_direct(s) && sim_tile2(s);
     ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)nsteps, s->st));
-    ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)s->g.ncell(), s->st));
+    if (s->use_cells) ATLJ_CUDA(cudaMemsetAsync(s->cb.cell_count, 0, sizeof(int) * (size_t)s->g.ncell(), s->st));
     ATLJ_CUDA(cudaMemsetAsync(s->cb.err + 7, 0, sizeof(int), s->st));  // step counter of the replayed launches
     int nb_prev = 0, k = 0;
     // step 0 (no finished step to close), launched directly; it also warms the kernels' attributes up
     if ((rc = nve_fused_step(s, s->st, nullptr, dt, false, nullptr, 0, false, &nb_prev))) return rc;
     k = 1;
     // pairs of steps as one replayed graph (not while the per-kernel event timing is on)
+    // (the all-pairs route keeps its atom order, so the captured pair of steps is simply the same step twice)
     auto two_steps = [&](cudaStream_t cap, cudaStream_t side) -> int {
       int rc2 = ATLJ_OK, nb = nb_prev;
       for (int j = 0; j < 2 && rc2 == ATLJ_OK; j++) rc2 = nve_fused_step(s, cap, side, dt, true, s->rec_dev, nb, true, &nb);

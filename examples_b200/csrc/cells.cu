@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
                                                         double *__restrict__ rec_vf,
                                                         const double *__restrict__ pair_partials, int pair_rows,
                                                         int model, SlabArgs sl, const int *__restrict__ pair_rows_dev,
-                                                        int *__restrict__ step_ctr, int *__restrict__ tab0) {
+                                                        int *__restrict__ step_ctr, int *__restrict__ tab0,
+                                                        int no_assign) {
   if (pair_rows_dev) pair_rows = min(pair_rows, *pair_rows_dev);
   // replayed launches (CUDA graph): the record of the finished step is rec_vf + NREC * *step_ctr; the CTA that finishes
   // last moves the counter on.  tab0: word 0 of the pair kernel's item table, zeroed here for this step's table kernel
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
     }
     __syncthreads();
     const int i = tile * IT + threadIdx.x;
-    if (i < n) {
+    if (i < n && !no_assign) {
       const double w0 = xs[3 * threadIdx.x], w1 = xs[3 * threadIdx.x + 1], w2 = xs[3 * threadIdx.x + 2];
       const long long c0 = (long long)floor(__dmul_rn(__dadd_rn(w0, 0.5), scd));  // md_lj_ll_module.py:108
       const long long c1 = (long long)floor(__dmul_rn(__dadd_rn(w1, 0.5), scd));
@@ -314,7 +315,9 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
                       const int *pair_rows_dev, const KdkLoop *loop) {
   // (in the replayed loop the counts were zeroed by the previous step's sort + gather, word 0 of the item table is
   // zeroed by this kernel and the record pointer follows a device counter: no memset nodes, no per-step arguments)
-  if (!loop || !loop->counts_zeroed) ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
+  const int no_assign = loop && loop->no_assign ? 1 : 0;
+  if (!no_assign && (!loop || !loop->counts_zeroed))
+    ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   int *step_ctr = loop ? loop->step_ctr : nullptr, *tab0 = loop ? loop->tab0 : nullptr;
   const int nb = integ_blocks(n);
   SlabArgs sl;
@@ -329,7 +332,7 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
 #define ATLJ_KDK(RCP, SLAB)                                                                                          \
   kdk_assign_kernel<RCP, SLAB><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid, \
                                                   b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,     \
-                                                  pair_rows, model, sl, pair_rows_dev, step_ctr, tab0)
+                                                  pair_rows, model, sl, pair_rows_dev, step_ctr, tab0, no_assign)
   if (inv_box != 0.0) {
     if (slab)
       ATLJ_KDK(true, true);

@@ -168,6 +168,7 @@ struct KdkLoop {
   int *tab0;           // word 0 of the tiled pair kernel's item table, zeroed by the kernel (null: the launcher of the
                        // pair kernel does it)
   bool counts_zeroed;  // cell_count was left zeroed by the previous step's launch_cell_sort_gather(zero_counts)
+  bool no_assign = false;  // all-pairs route (sc < 4): kick + sums + kick + drift + wrap only, no cell assignment
 };
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,

@@ -190,17 +190,17 @@ int launch_pair_direct(cudaStream_t st, const PairArgs &a, bool hessian, int n) 
 }
 
 // ---- small systems: eight lanes per atom --------------------------------------------------------------------------------
-// Below ~1e5 atoms the tiled kernels cannot fill a B200 (N = 32,000 is 250 chunks of 128 atoms for 592 warp
+// Small systems cannot fill a B200 with the tiled kernels (N = 32,000 is 250 chunks of 128 atoms for 592 warp
 // schedulers) and a step is bound by the latency of ONE chunk.  Here an atom's candidates are spread over MK_L = 8
-// lanes of a warp (4 atoms per warp, 16 per CTA): N = 32,000 gives 8,000 warps.  Every lane runs the reference's exact
+// lanes of a warp (4 atoms per warp, 16 per CTA; a whole warp per atom below 4,096 atoms).  Every lane runs the reference's exact
 // arithmetic (pair_sep, md_lj_module.py:96-99) on its share of the candidates, parks the in-range ones in a small
 // shared-memory list (pass 1: divergent but cheap), evaluates them (pass 2: nearly uniform trip count), and the eight
 // partial forces are added with warp shuffles in a fixed order (md_lj_module.py:109,113).  CELLS: candidates are the
 // atom's 27 (LE: up to 30) neighbour cells on the cell-sorted arrays (md_lj_ll_module.py:122-165); !CELLS: all atoms
 // (md_lj_module.py:95-115, the reference's N = 256 case).
-constexpr int MK_T = 128, MK_L = 8, MK_LIST = 20;
+constexpr int MK_T = 128, MK_LIST = 20;  // lanes per atom (MK_L): 8, or 32 for systems of a few thousand atoms
 
-template <int MODEL, bool HESS, bool CELLS>
+template <int MODEL, bool HESS, bool CELLS, int MK_L>
 __global__ void __launch_bounds__(MK_T) pair_multi_kernel(PairArgs a, int n) {
   constexpr bool LE = (MODEL == ATLJ_MODEL_WCA);
   __shared__ int cand[MK_LIST * MK_T];  // [slot][thread]: conflict-free
@@ -283,8 +283,9 @@ __global__ void __launch_bounds__(MK_T) pair_multi_kernel(PairArgs a, int n) {
   block_store_partials<MK_T / 32>(acc, a.partials + 8 * (size_t)blockIdx.x);
 }
 
+static inline int multi_lanes(int n) { return n <= 4096 ? 32 : 8; }
 int pair_multi_blocks(int n) {
-  const long long b = ((long long)n * MK_L + MK_T - 1) / MK_T;
+  const long long b = ((long long)n * multi_lanes(n) + MK_T - 1) / MK_T;
   return b > 0 ? (int)b : 1;
 }
 
@@ -292,12 +293,17 @@ int pair_multi_blocks(int n) {
 // otherwise all n atoms of a.r
 int launch_pair_multi(cudaStream_t st, const PairArgs &a, bool hessian, int n, bool cells) {
   const int blocks = pair_multi_blocks(n);
-#define ATLJ_MK(MODEL, HESS)                                                    \
-  do {                                                                          \
-    if (cells)                                                                  \
-      pair_multi_kernel<MODEL, HESS, true><<<blocks, MK_T, 0, st>>>(a, n);      \
-    else                                                                        \
-      pair_multi_kernel<MODEL, HESS, false><<<blocks, MK_T, 0, st>>>(a, n);     \
+  const bool wide = multi_lanes(n) == 32;
+#define ATLJ_MK(MODEL, HESS)                                                         \
+  do {                                                                               \
+    if (cells && wide)                                                               \
+      pair_multi_kernel<MODEL, HESS, true, 32><<<blocks, MK_T, 0, st>>>(a, n);       \
+    else if (cells)                                                                  \
+      pair_multi_kernel<MODEL, HESS, true, 8><<<blocks, MK_T, 0, st>>>(a, n);        \
+    else if (wide)                                                                   \
+      pair_multi_kernel<MODEL, HESS, false, 32><<<blocks, MK_T, 0, st>>>(a, n);      \
+    else                                                                             \
+      pair_multi_kernel<MODEL, HESS, false, 8><<<blocks, MK_T, 0, st>>>(a, n);       \
   } while (0)
   if (a.p.model == ATLJ_MODEL_LJ) {
     if (hessian)
