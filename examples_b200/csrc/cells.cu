@@ -97,8 +97,11 @@ int launch_cell_assign(cudaStream_t st, const Geom &g, const double *r_in, doubl
 // step k, then md_lj_ll_module.py:88,106-109):  v += hdt*f [sum v^2, sum f^2 of the finished step]  ->  v += hdt*f
 // -> r += dt*v/box -> wrap -> cell triplet, histogram, arrival rank.  Same separately-rounded operations as
 // kick_sums_kernel + kick_drift_kernel + cell_assign_kernel, so results are bit-identical to the unfused sequence.
+#ifndef ATLJ_KDK_CTAS
+#define ATLJ_KDK_CTAS 6
+#endif
 template <bool RCP, bool SLAB>
-__global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
+__global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, int n, double *__restrict__ r, double *__restrict__ v,
                                                         const double *__restrict__ f, double half_dt, double dt,
                                                         double box, double inv_box, int first_kick,
                                                         int *__restrict__ cellid,
@@ -144,41 +147,56 @@ __global__ void __launch_bounds__(IT, 8) kdk_assign_kernel(Geom g, int n, double
     const bool btile = slab && t < nbt;
     const size_t e0 = 3 * (size_t)tile * IT;
     const int ne = min(3 * IT, 3 * n - (int)e0 > 0 ? (int)(3 * (size_t)n - e0) : 0);
+    if (slab && sl.assign_only) {
+      // another integrator has moved (and wrapped) the atoms: cell assignment + migration only
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const int l = threadIdx.x + k * IT;
-      if (l < ne && slab && sl.assign_only) {
-        // another integrator has moved (and wrapped) the atoms: cell assignment + migration only
-        const size_t e = e0 + l;
-        xs[l] = r[e];
-        if (btile) vs[l] = v[e];
-      } else if (l < ne) {
-        const size_t e = e0 + l;
-        const double ff = f[e];
-        double vv = v[e];
-        if (first_kick) {
-          vv = __dadd_rn(vv, __dmul_rn(half_dt, ff));
-          s[0] += vv * vv;
-          s[1] += ff * ff;
+      for (int k = 0; k < 3; k++) {
+        const int l = threadIdx.x + k * IT;
+        if (l < ne) {
+          xs[l] = r[e0 + l];
+          if (btile) vs[l] = v[e0 + l];
         }
-        vv = __dadd_rn(vv, __dmul_rn(half_dt, ff));
-        // (dt*v)/box, correctly rounded without the division subroutine (and its 64 registers): with y = RN(1/box)
-        // from the host, q = RN(a*y), r = a - q*box (exact in an fma), RN(q + r*y) is RN(a/box) (Markstein); the host
-        // passes inv_box = 0 for the one family of divisors the theorem excludes (significand all ones)
-        const double a = __dmul_rn(dt, vv);
-        double q;
-        if (RCP) {
-          q = __dmul_rn(a, inv_box);
-          q = __fma_rn(__fma_rn(-q, box, a), inv_box, q);
-        } else {
-          q = __ddiv_rn(a, box);
+      }
+    } else {
+      // all nine loads of a thread are issued before the first of them is used (the kernel is bound by the number of
+      // bytes in flight: with one component at a time ncu showed 66 % of the stall cycles on the loads' scoreboard)
+      double ff[3], vv[3], rr[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int l = threadIdx.x + k * IT;
+        const size_t e = e0 + min(l, ne > 0 ? ne - 1 : 0);  // clamped: a valid address, the value is not used
+        ff[k] = f[e], vv[k] = v[e], rr[k] = r[e];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int l = threadIdx.x + k * IT;
+        if (l < ne) {
+          const size_t e = e0 + l;
+          double w = vv[k];
+          if (first_kick) {
+            w = __dadd_rn(w, __dmul_rn(half_dt, ff[k]));
+            s[0] += w * w;
+            s[1] += ff[k] * ff[k];
+          }
+          w = __dadd_rn(w, __dmul_rn(half_dt, ff[k]));
+          // (dt*v)/box, correctly rounded without the division subroutine (and its 64 registers): with y = RN(1/box)
+          // from the host, q = RN(a*y), r = a - q*box (exact in an fma), RN(q + r*y) is RN(a/box) (Markstein); the
+          // host passes inv_box = 0 for the one family of divisors the theorem excludes (significand all ones)
+          const double a = __dmul_rn(dt, w);
+          double q;
+          if (RCP) {
+            q = __dmul_rn(a, inv_box);
+            q = __fma_rn(__fma_rn(-q, box, a), inv_box, q);
+          } else {
+            q = __ddiv_rn(a, box);
+          }
+          double x = wrap1(__dadd_rn(rr[k], q));
+          x = __dsub_rn(x, rint(x));  // the force routine wraps again (md_lj_ll_module.py:88); idempotent
+          v[e] = w;
+          r[e] = x;
+          xs[l] = x;
+          if (slab) vs[l] = w;
         }
-        double x = wrap1(__dadd_rn(r[e], q));
-        x = __dsub_rn(x, rint(x));  // the force routine wraps again (md_lj_ll_module.py:88); idempotent
-        v[e] = vv;
-        r[e] = x;
-        xs[l] = x;
-        if (slab) vs[l] = vv;
       }
     }
     __syncthreads();
@@ -319,7 +337,8 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   if (!no_assign && (!loop || !loop->counts_zeroed))
     ATLJ_CUDA(cudaMemsetAsync(b.cell_count, 0, sizeof(int) * (size_t)g.ncell(), st));
   int *step_ctr = loop ? loop->step_ctr : nullptr, *tab0 = loop ? loop->tab0 : nullptr;
-  const int nb = integ_blocks(n);
+  int nb = integ_blocks(n);
+  if (nb > 148 * ATLJ_KDK_CTAS) nb = 148 * ATLJ_KDK_CTAS;  // one resident wave of the grid-stride loop
   SlabArgs sl;
   memset(&sl, 0, sizeof(sl));
   if (slab) sl = *slab;
@@ -542,16 +561,19 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
     }
   }
   int cid = -1, sent = 0;
-  if (i < n) cid = cellid[i];
+  // the atom's own data is requested first: those loads are in flight while the rank is being counted
+  double x0 = 0.0, x1 = 0.0, x2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  if (i < n) {
+    cid = cellid[i];
+    x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
+    if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
+  }
   if (cid >= 0) {
     const unsigned myid = id_in ? (unsigned)id_in[i] : (unsigned)i;
     const int ci = g.cs_idx(cid);
     const int s0 = cell_start[ci] - base, s1 = cell_start[ci + 1] - base;
     int slot = s0;
     for (int s = s0; s < s1; s++) slot += ids[s] < myid;
-    const double x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
     const size_t d = 3 * (size_t)slot;
     r_out[d] = x0, r_out[d + 1] = x1, r_out[d + 2] = x2;
     if (v_in) v_out[d] = w0, v_out[d + 1] = w1, v_out[d + 2] = w2;
