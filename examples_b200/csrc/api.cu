@@ -980,7 +980,13 @@ int atlj_force_1(const double *ri_host, const double *r_host, int64_t nj, double
 
 int atlj_force_le(const double *r_host, int64_t n, double box, double r_cut_box_sq, double box_sq, double strain,
                   int sc, int shift, int check_index, double *f_host, double totals[4], int *ovr, int64_t *npair) {
-  (void)shift;  // recomputed as floor(strain*sc) on the host side of the library; the argument documents the contract
+  // the library derives the shift itself (md_lj_llle_module.py:112); the argument states the caller's value and must
+  // agree, otherwise the two sides disagree about the sheared stencil
+  if (sc >= 4 && shift != (int)floor(strain * sc)) {
+    set_error("force_le: shift %d is not floor(strain * sc) = %d (md_lj_llle_module.py:112)", shift,
+              (int)floor(strain * sc));
+    return ATLJ_ERR_ARG;
+  }
   return force_host(ATLJ_MODEL_WCA, r_host, n, box, r_cut_box_sq, box_sq, 0.0, strain, sc, check_index, f_host, totals,
                     ovr, npair);
 }
