@@ -215,7 +215,7 @@ __device__ __forceinline__ double rcp46(double s) {
 template <int MODE>
 __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
     pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, int ncz_max, const int *__restrict__ tab,
-                      int *__restrict__ work_counter, int *__restrict__ rows_out) {
+                      int *__restrict__ work_counter, int *__restrict__ rows_out, double rc2s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
   double *uy = ux + U_STR;
@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const int sc = g.sc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *__restrict__ cs = a.cell_start;
   const double box = p.box;
-  const double rc2s = p.r_cut_box_sq * p.box_sq;
+  // rc2s = r_cut_box_sq * box_sq comes as a kernel argument: a constant-bank operand of the one DADD that uses it in the
+  // phase-2 loop (as a product of two members of `a` the compiler re-loaded both factors in every iteration)
   const double band = 1e-8 * rc2s;
   const double sovr = (1.0 / 1.77) * (1.0 + 1e-6);
   const unsigned band2 = 2u * (unsigned)__double2hiint(band);
@@ -642,7 +643,9 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         // two independent fp64 chains (the kernel is latency-, not fp64-throughput-bound); a dead slot gets
         // s = 1e300, whose sr^6 underflows to exactly 0, so no branch is needed around the arithmetic.
         double fx = 0.0, fy = 0.0, fz = 0.0;
-        const unsigned dummy_addr = ux_s + 8u * (unsigned)U_CAP;
+        // (opaque to the compiler: it re-derived this address - five instructions - in every iteration of the loop)
+        unsigned dummy_addr;
+        asm volatile("add.u32 %0, %1, %2;" : "=r"(dummy_addr) : "r"(ux_s), "n"(8 * U_CAP));
         int nd = 0;
         int defer[4];
         int ww = 0;
@@ -699,8 +702,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           const bool b0 = (((unsigned)e0 << 1) <= band2) | (__double2hiint(s0) <= sovr_hi);
           const bool b1 = (((unsigned)e1 << 1) <= band2) | (__double2hiint(s1) <= sovr_hi);
           const bool in0 = (e0 < 0) & !b0, in1 = (e1 < 0) & !b1;
-          npf += in0 ? 1u : 0u;
-          npf += in1 ? 1u : 0u;
+          if (in0) npf++;
+          if (in1) npf++;
           if (b0 | b1) {
             if (b0) defer[nd++] = (int)((a0 - ux_s) >> 3);
             if (b1) defer[nd++] = (int)((a1 - ux_s) >> 3);
@@ -714,8 +717,9 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
               nd = 0;
             }
           }
-          s0 = in0 ? s0 : 1e300;
-          s1 = in1 ? s1 : 1e300;
+          // out of range: s becomes ~1e300 (only the high word needs replacing), whose sr^6 underflows to exactly 0
+          s0 = __hiloint2double(in0 ? __double2hiint(s0) : 0x7e37e43c, __double2loint(s0));
+          s1 = __hiloint2double(in1 ? __double2hiint(s1) : 0x7e37e43c, __double2loint(s1));
           if constexpr (MODE == T2_HESS) {
             const double ex0 = fix - lds_f64(a0 + 24u * U_STR), ey0 = fiy - lds_f64(a0 + 32u * U_STR),
                          ez0 = fiz - lds_f64(a0 + 40u * U_STR);
@@ -832,13 +836,13 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   const int nblk = grid < bound ? grid : bound;
   if (mode == T2_HESS)
     pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                         work_counter + 4);
+                                                         work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq);
   else
   {
     PairArgs af = a;
     if (mode == T2_FORCE) af.masks = nullptr;
     pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                          work_counter + 4);
+                                                          work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq);
   }
   ATLJ_LAUNCHED();
   return bound;
