@@ -250,7 +250,7 @@ def other_workloads():
 # ---------------------------------------------------------------------------------------------------------------------
 # driver-visible parity records
 # ---------------------------------------------------------------------------------------------------------------------
-def slab_parity(rank, world, dist, nc=20, nsteps=100):
+def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5):
     """The REAL multi-process slab path (CUDA IPC peer buffers, stamps, NCCL all-reduce) against the single-domain run
     of the same system on rank 0's GPU: N = 32,000 (BASELINE config 2), 100 velocity-Verlet steps.  Every rank takes
     part; rank 0 gets the record, the others None.  Forces are per-atom sums in a fixed order, so r, v, f must agree
@@ -265,8 +265,17 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100):
     sim = SlabSimulation(box, R_CUT, r, v, rank, world)
     rec0 = sim.force()
     rec = sim.run_nve(DT, nsteps)
+    # ... and host_steps more through the host-buffer step (the e2e arm's entry point at N > 1): same trajectory
+    rs, vs, fs, ids = sim.download_sorted()
+    n_own, cap = ids.shape[0], sim.own_cap
+    R, V, F = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
+    I = np.zeros(cap, dtype=np.int32)
+    R[:n_own], V[:n_own], F[:n_own], I[:n_own] = rs, vs, fs, ids
+    rec_h = np.zeros((host_steps, rec.shape[1]))
+    for k in range(host_steps):
+        rec_h[k], n_own = sim.nve_step_host(DT, R, V, F, I, n_own)
     parts = [None] * world
-    dist.all_gather_object(parts, sim.download_sorted())
+    dist.all_gather_object(parts, (R[:n_own].copy(), V[:n_own].copy(), F[:n_own].copy(), I[:n_own].copy()))
     sim.close()
     if rank != 0:
         return None
@@ -275,6 +284,7 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100):
     one = Simulation(box, R_CUT, r, v)
     ref0 = one.force()
     ref = one.run_nve(DT, nsteps)
+    ref_h = one.run_nve(DT, host_steps)
     r1, v1, f1 = one.download()
     one.close()
     _lib.set_multi_max(old)
@@ -285,9 +295,14 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100):
         seen[i] += 1
     tot = max(float(np.max(np.abs(rec[:, k] - ref[:, k]) / np.maximum(np.abs(ref[:, k]), 1e-300))) for k in range(6))
     tot = max(tot, float(np.max(np.abs(rec0[:4] - ref0[:4]) / np.abs(ref0[:4]))))
-    return {"world": world, "n": n, "steps": nsteps, "against": "single-domain run of the same system on rank 0",
+    tot = max([tot] + [float(np.max(np.abs(rec_h[:, k] - ref_h[:, k]) / np.maximum(np.abs(ref_h[:, k]), 1e-300)))
+                       for k in range(6)])
+    return {"world": world, "n": n, "steps": nsteps, "host_buffer_steps": host_steps,
+            "against": "single-domain run of the same system on rank 0 (%d device-resident steps, then %d steps "
+                       "through atlj_sim_nve_step_host_mg)" % (nsteps, host_steps),
             "every_atom_owned_once": bool(np.all(seen == 1)), "owned_count_conserved": bool(np.all(rec[:, 11] == n)),
-            "pair_counts_equal": bool(np.array_equal(rec[:, 8], ref[:, 8]) and rec0[8] == ref0[8]),
+            "pair_counts_equal": bool(np.array_equal(rec[:, 8], ref[:, 8]) and rec0[8] == ref0[8]
+                                      and np.array_equal(rec_h[:, 8], ref_h[:, 8])),
             "max_abs_diff_r": float(np.max(np.abs(rm - r1))), "max_abs_diff_v": float(np.max(np.abs(vm - v1))),
             "max_abs_diff_f": float(np.max(np.abs(fm - f1))), "max_rel_diff_step_records": tot}
 
@@ -403,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
     epot = float(np.mean(rec[:, REC_T1])) / n_total
     ovr = bool(rec[:, 7].any())
 
-    # ---- end to end through host buffers (rank-local; single GPU only: the slab path keeps state on the device) --
+    # ---- end to end through host buffers ----------------------------------------------------------------------------
     e2e = None
     if world == 1:
         from examples_b200._lib import PinnedArray
@@ -439,6 +454,38 @@ def run_ours(args, rank, world, local_rank):
                                     "chunk-wise into a page-locked ring, DMA per chunk), f returned in a page-locked "
                                     "NumPy array written by DMA", "ms_per_call": sec * 1e3,
                              "pcie_gb_per_s": 2 * 24 * n / sec / 1e9, "bytes_per_call": 2 * 24 * n}
+        for a in (pr, pv, pf, pi):
+            a.free()
+
+    if world > 1:
+        # every rank's owned atoms live in page-locked host arrays; each step copies them in, runs one exchange step
+        # of the whole system and copies them out again (atoms migrate: the owned count travels with the arrays)
+        from examples_b200._lib import PinnedArray
+        rs, vs, fs, ids = sim.download_sorted()
+        n_own, cap = ids.shape[0], sim.own_cap
+        pr, pv, pf = PinnedArray((cap, 3)), PinnedArray((cap, 3)), PinnedArray((cap, 3))
+        pi = PinnedArray((cap,), np.int32)
+        pr.array[:n_own], pv.array[:n_own], pf.array[:n_own], pi.array[:n_own] = rs, vs, fs, ids
+        del rs, vs, fs, ids
+        ke = max(3, min(args.steps, 50))
+        for _ in range(3):
+            _, n_own = sim.nve_step_host(DT, pr.array, pv.array, pf.array, pi.array, n_own)
+        barrier()
+        t0 = time.perf_counter()
+        sim.timer_start()
+        for _ in range(ke):
+            _, n_own = sim.nve_step_host(DT, pr.array, pv.array, pf.array, pi.array, n_own)
+        ms_e = sim.timer_stop()
+        ms_e = max(ms_e, (time.perf_counter() - t0) * 1e3)  # host-side time counts too
+        barrier()
+        import torch
+        t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+        e2e = {"value": n_total * ke / (ms_e * 1e-3), "unit": "atom-steps/s", "steps": ke,
+               "h2d_bytes_per_step": (3 * 24 + 4) * n_total, "d2h_bytes_per_step": (3 * 24 + 4) * n_total + 8 * _lib.NREC,
+               "api": "atlj_sim_nve_step_host_mg on every rank: the rank's owned r,v,f,id in pinned host memory each "
+                      "step (bytes are the sum over the %d ranks)" % world}
         for a in (pr, pv, pf, pi):
             a.free()
 

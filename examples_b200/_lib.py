@@ -103,6 +103,9 @@ def lib():
     L.atlj_sim_mg_ipc_blob.argtypes = [_vp, C.c_char_p]
     L.atlj_sim_mg_ipc_open.argtypes = [_vp, C.c_char_p, C.c_char_p]
     L.atlj_sim_nve_step_host.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int64, _vp]
+    L.atlj_sim_nve_step_host_mg.argtypes = [_vp, C.c_double, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp]
+    L.atlj_sim_mg_own_cap.argtypes = [_vp]
+    L.atlj_sim_mg_own_cap.restype = C.c_int64
     L.atlj_host_alloc.restype = _vp
     L.atlj_host_alloc.argtypes = [C.c_int64]
     L.atlj_host_free.restype = None

@@ -739,4 +739,35 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
   return rc;
 }
 
+// md_nve_lj.py:178-192 with the rank's state in host memory (bench.py's end-to-end arm at N > 1): what comes in is what
+// the previous call handed out, so the device-side tables of the last sort (boundary tiles, halo regions) still apply
+int64_t atlj_sim_mg_own_cap(const atlj_sim *s) { return s && s->mg.on ? (int64_t)s->mg.own_cap : -1; }
+
+int atlj_sim_nve_step_host_mg(atlj_sim *s, double dt, double *r_host, double *v_host, double *f_host, int32_t *id_host,
+                              int64_t *n_io, double *rec_host) {
+  if (!mg_ready(s) || !s->mg.comm || !r_host || !v_host || !f_host || !id_host || !n_io || *n_io < 0 ||
+      *n_io > (int64_t)s->mg.own_cap) {
+    set_error("nve_step_host_mg: bad arguments (slab enabled, neighbours mapped, ranks connected, n <= owned capacity)");
+    return ATLJ_ERR_ARG;
+  }
+  int64_t n = *n_io;
+  s->n = n;
+  size_t b = sizeof(double) * 3 * (size_t)n;
+  ATLJ_CUDA(cudaMemcpyAsync(s->r[s->cur], r_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->v[s->cur], v_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->f, f_host, b, cudaMemcpyHostToDevice, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(s->id[s->cur], id_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s->st));
+  int rc = atlj_sim_run_nve_mg(s, dt, 1, rec_host);  // ends with the owned count back on the host (synchronised)
+  if (rc) return rc;
+  n = s->n;
+  b = sizeof(double) * 3 * (size_t)n;
+  ATLJ_CUDA(cudaMemcpyAsync(r_host, s->r[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(v_host, s->v[s->cur], b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(f_host, s->f, b, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaMemcpyAsync(id_host, s->id[s->cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->st));
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  *n_io = n;
+  return ATLJ_OK;
+}
+
 }  // extern "C"

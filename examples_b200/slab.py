@@ -118,6 +118,23 @@ class SlabRank(Simulation):
                                                   None if rec is None else rec.ctypes.data))
         return rec
 
+    @property
+    def own_cap(self):
+        """Owned atoms this rank has room for (the size of the host arrays nve_step_host works on)."""
+        return int(_lib.lib().atlj_sim_mg_own_cap(self._h))
+
+    def nve_step_host(self, dt, r, v, f, ids, n):
+        """One velocity-Verlet step of the whole system with this rank's owned atoms in HOST arrays of own_cap rows
+        (the first n are valid; device order); -> (record of global sums, new n)."""
+        rec = np.zeros(NREC)
+        nn = C.c_int64(int(n))
+        for a in (r, v, f):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape[0] >= self.own_cap
+        assert ids.dtype == np.int32 and ids.shape[0] >= self.own_cap
+        _lib.check(_lib.lib().atlj_sim_nve_step_host_mg(self._h, float(dt), r.ctypes.data, v.ctypes.data, f.ctypes.data,
+                                                        ids.ctypes.data, C.byref(nn), rec.ctypes.data))
+        return rec, int(nn.value)
+
     def force(self, strain=0.0, hessian=False):
         """Force evaluation on the current positions = one step with dt = 0 (kick and drift are exact no-ops)."""
         return self.run_nve(0.0, 1)[0]

@@ -225,6 +225,13 @@ int atlj_sim_mg_nhc_finish(atlj_sim *s, int m, double *eta, double *p_eta);
  * Pinned buffers from atlj_host_alloc make the copies asynchronous DMA. */
 int atlj_sim_nve_step_host(atlj_sim *s, double dt, double *r_host, double *v_host, double *f_host, int32_t *id_host,
                            int64_t n, double *rec_host);
+/* The same on a slab rank (the end-to-end path at N > 1 GPUs): *n owned atoms of THIS rank in host memory (device
+ * order of the previous call / atlj_sim_download), one exchange step of the whole system (migration, halo, force,
+ * NCCL all-reduce of the record), then the rank's owned atoms - *n updated: atoms migrate - come back.  The host
+ * arrays must hold the rank's owned capacity (atlj_sim_mg_own_cap).  rec_host: GLOBAL sums, as atlj_sim_run_nve_mg. */
+int atlj_sim_nve_step_host_mg(atlj_sim *s, double dt, double *r_host, double *v_host, double *f_host, int32_t *id_host,
+                              int64_t *n, double *rec_host);
+int64_t atlj_sim_mg_own_cap(const atlj_sim *s);
 void *atlj_host_alloc(int64_t bytes); /* page-locked host memory (cudaHostAlloc); NULL on failure */
 void atlj_host_free(void *p);
 
