@@ -504,7 +504,7 @@ def run_ours(args, rank, world, local_rank):
     flops = FLOP_PER_PAIR * pairs_per_step / world
     ach = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_pair_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_pair_traffic.json")
     if os.path.exists(tp) and wl == "c5" and world == 1:  # dram bytes per launch from the committed ncu capture
         td = json.load(open(tp))
         traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
