@@ -250,7 +250,7 @@ def other_workloads():
 # ---------------------------------------------------------------------------------------------------------------------
 # driver-visible parity records
 # ---------------------------------------------------------------------------------------------------------------------
-def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5):
+def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5, hess_steps=3):
     """The REAL multi-process slab path (CUDA IPC peer buffers, stamps, NCCL all-reduce) against the single-domain run
     of the same system on rank 0's GPU: N = 32,000 (BASELINE config 2), 100 velocity-Verlet steps.  Every rank takes
     part; rank 0 gets the record, the others None.  Forces are per-atom sums in a fixed order, so r, v, f must agree
@@ -274,8 +274,10 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5):
     rec_h = np.zeros((host_steps, rec.shape[1]))
     for k in range(host_steps):
         rec_h[k], n_own = sim.nve_step_host(DT, R, V, F, I, n_own)
+    # ... and hess_steps with the hessian in the loop (forces of the halo atoms fetched from the neighbours)
+    rec_x = sim.run_nve(DT, hess_steps, hessian=True)
     parts = [None] * world
-    dist.all_gather_object(parts, (R[:n_own].copy(), V[:n_own].copy(), F[:n_own].copy(), I[:n_own].copy()))
+    dist.all_gather_object(parts, sim.download_sorted())
     sim.close()
     if rank != 0:
         return None
@@ -285,6 +287,7 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5):
     ref0 = one.force()
     ref = one.run_nve(DT, nsteps)
     ref_h = one.run_nve(DT, host_steps)
+    ref_x = one.run_nve(DT, hess_steps, hessian=True)
     r1, v1, f1 = one.download()
     one.close()
     _lib.set_multi_max(old)
@@ -297,12 +300,18 @@ def slab_parity(rank, world, dist, nc=20, nsteps=100, host_steps=5):
     tot = max(tot, float(np.max(np.abs(rec0[:4] - ref0[:4]) / np.abs(ref0[:4]))))
     tot = max([tot] + [float(np.max(np.abs(rec_h[:, k] - ref_h[:, k]) / np.maximum(np.abs(ref_h[:, k]), 1e-300)))
                        for k in range(6)])
-    return {"world": world, "n": n, "steps": nsteps, "host_buffer_steps": host_steps,
-            "against": "single-domain run of the same system on rank 0 (%d device-resident steps, then %d steps "
-                       "through atlj_sim_nve_step_host_mg)" % (nsteps, host_steps),
+    tot = max([tot] + [float(np.max(np.abs(rec_x[:, k] - ref_x[:, k]) / np.maximum(np.abs(ref_x[:, k]), 1e-300)))
+                       for k in range(6)])
+    hes = float(np.max(np.abs(rec_x[:, 6] - ref_x[:, 6]) / np.abs(ref_x[:, 6])))
+    return {"world": world, "n": n, "steps": nsteps, "host_buffer_steps": host_steps, "hessian_steps": hess_steps,
+            "max_rel_diff_hessian": hes,
+            "against": "single-domain run of the same system on rank 0 (%d device-resident steps, %d steps "
+                       "through atlj_sim_nve_step_host_mg, %d steps with the hessian in the loop)"
+                       % (nsteps, host_steps, hess_steps),
             "every_atom_owned_once": bool(np.all(seen == 1)), "owned_count_conserved": bool(np.all(rec[:, 11] == n)),
             "pair_counts_equal": bool(np.array_equal(rec[:, 8], ref[:, 8]) and rec0[8] == ref0[8]
-                                      and np.array_equal(rec_h[:, 8], ref_h[:, 8])),
+                                      and np.array_equal(rec_h[:, 8], ref_h[:, 8])
+                                      and np.array_equal(rec_x[:, 8], ref_x[:, 8])),
             "max_abs_diff_r": float(np.max(np.abs(rm - r1))), "max_abs_diff_v": float(np.max(np.abs(vm - v1))),
             "max_abs_diff_f": float(np.max(np.abs(fm - f1))), "max_rel_diff_step_records": tot}
 

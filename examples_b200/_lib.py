@@ -87,6 +87,9 @@ def lib():
     L.atlj_nccl_unique_id.argtypes = [C.c_char_p]
     L.atlj_sim_mg_connect.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
     L.atlj_sim_run_nve_mg.argtypes = [_vp, C.c_double, C.c_int, _vp]
+    L.atlj_sim_run_nve_mg_hess.argtypes = [_vp, C.c_double, C.c_int, _vp]
+    L.atlj_sim_mg_phase3_force.argtypes = [_vp]
+    L.atlj_sim_mg_phase4_hess.argtypes = [_vp, C.c_double, _vp]
     L.atlj_sim_mg_phase1.argtypes = [_vp, C.c_double]
     L.atlj_sim_mg_phase2.argtypes = [_vp]
     L.atlj_sim_mg_phase3.argtypes = [_vp, C.c_double, _vp]

@@ -156,6 +156,8 @@ static int ensure_masks(atlj_sim *s) {
   return ATLJ_OK;
 }
 
+int sim_ensure_masks(atlj_sim *s) { return ensure_masks(s); }
+
 // cells of ~1 atom (WCA cut-off): the direct kernel; ATLJ_PAIR_KERNEL=tile1 keeps the tiled one for A/B runs
 static bool sim_direct(const atlj_sim *s) {
   const long long cells = s->g.n_own_cells();
@@ -387,7 +389,11 @@ atlj_sim *atlj_sim_create_ex(int64_t capacity, void *stream, int flags) {
       ok = dev_alloc(&s->r[k], 3 * c) == ATLJ_OK;
     ok = ok && dev_alloc(&s->v[k], 3 * c) == ATLJ_OK && dev_alloc(&s->id[k], c) == ATLJ_OK;
   }
-  ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
+  if (ok && s->ipc_safe)  // (slab ranks read the forces of their halo atoms from the neighbours: hessian)
+    ok = dev_alloc_ipc((void **)&s->f, sizeof(double) * 3 * c, &s->f_alloc_bytes, s->st) == ATLJ_OK;
+  else
+    ok = ok && dev_alloc(&s->f, 3 * c) == ATLJ_OK;
+  ok = ok && dev_alloc(&s->cb.cellid, c) == ATLJ_OK &&
        dev_alloc(&s->cb.rank, c) == ATLJ_OK && dev_alloc(&s->cb.keys, c) == ATLJ_OK &&
        dev_alloc(&s->cb.block_sums, 8192) == ATLJ_OK && dev_alloc(&s->cb.err, 8) == ATLJ_OK &&
        dev_alloc(&s->scal, 64) == ATLJ_OK && dev_alloc(&s->vf_partials, 4 * 4096) == ATLJ_OK;

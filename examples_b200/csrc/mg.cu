@@ -62,6 +62,41 @@ __device__ __forceinline__ void publish(int *hdr, int count, int stamp) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(stamp) : "memory");
 }
 
+// Hessian on slabs (md_nve_lj.py:46 calls hessian(box, r_cut, r, f) every step): the pair terms of a boundary atom need
+// the forces of its halo partners.  After the pair kernel the forces of the first / last owned layer are stored into the
+// neighbours' force arrays at the halo offsets (where their positions went during the sort) and a second stamp
+// (header [2]) is published; the hessian kernel acquires it when it reaches a boundary layer, like the force kernel
+// acquires [1].  No double buffering: a neighbour can only send step s+1's forces after it has received this rank's
+// step s+1 positions, which are sent after this rank's step-s hessian kernel - the last reader - in stream order.
+__global__ void __launch_bounds__(256) halo_force_send_kernel(Geom g, const int *__restrict__ cell_start,
+                                                              const double *__restrict__ f, double *dst_left,
+                                                              double *dst_right, int cap, int *hdr_left,
+                                                              int *hdr_right, const int *xstep, int *done,
+                                                              const int *err) {
+  if (err[5]) return;  // a neighbour's message timed out earlier in this run
+  const int sc2 = g.sc * g.sc;
+  const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+  const int F0 = rowF[0], F1 = min(rowF[sc2], F0 + cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + cap);
+  const long long nF = 3ll * (F1 - F0), nL = 3ll * (L1 - L0);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nF + nL; t += (long long)gridDim.x * blockDim.x) {
+    if (t < nF)
+      dst_left[t] = f[3 * (size_t)F0 + t];
+    else
+      dst_right[t - nF] = f[3 * (size_t)L0 + (t - nF)];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      const int stamp = *xstep;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr_left + 2), "r"(stamp) : "memory");
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr_right + 2), "r"(stamp) : "memory");
+      *done = 0;
+    }
+  }
+}
+
 // consumer side for the pair kernels that cannot wait themselves (first tiled kernel): one thread acquires both stamps
 __global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, const int *xstep, unsigned long long timeout_ns,
                                   int *err) {
@@ -314,16 +349,17 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
 // phase 3: pair kernel over the owned rows; the halo layers 0 and nxl-1 were written by the neighbours, and the kernel
 // itself acquires their stamps when it reaches a boundary layer.  -> rows of partials written (the record is finished by
 // the next phase 1 or by tail())
-static int phase3(atlj_sim *s, cudaStream_t st, bool table_done) {
+static int phase3(atlj_sim *s, cudaStream_t st, bool table_done, bool save_masks = false) {
   MgState &m = s->mg;
   PairArgs a = pair_args(s);
+  if (save_masks) a.masks = s->masks;
   const int *hl = halo_hdr(m.arena, m, 0), *hr = halo_hdr(m.arena, m, 1);
   int nb;
   if (sim_tile2(s)) {
     a.halo.stamp_left = hl, a.halo.stamp_right = hr, a.halo.xstep = m.cnt_dev + 10, a.halo.timeout_ns = m.timeout_ns;
     a.halo.err = s->cb.err;
     Timer::begin(s, 0);
-    nb = launch_pair_tile2(st, a, s->cb.err + 2, 0, table_done ? 2 : 0, true);
+    nb = launch_pair_tile2(st, a, s->cb.err + 2, save_masks ? 1 : 0, table_done ? 2 : 0, true);
     Timer::end(s);
   } else {
     Timer::begin(s, 6);
@@ -349,6 +385,37 @@ static int tail(atlj_sim *s, double dt, double *rec, int nb) {
                         s->mg.cnt_dev + 1);
   Timer::end(s);
   return rc;
+}
+
+// hessian of the step (md_lj_ll_module.py:227-357) after a phase 3 that kept its mask words and whose totals have been
+// finalized (that launch also reset the work counter): boundary forces to the neighbours, then the hessian kernel walks
+// the mask words; its boundary items acquire the neighbours' force stamps.  rec[6] receives this rank's share.
+static int force_send(atlj_sim *s, cudaStream_t st) {
+  MgState &m = s->mg;
+  Timer::begin(s, 5);
+  halo_force_send_kernel<<<148, 256, 0, st>>>(s->g, s->cb.cell_start, s->f,
+                                             m.peer_f[0] + 3 * (size_t)(m.own_cap + m.halo_cap),
+                                             m.peer_f[1] + 3 * (size_t)m.own_cap, (int)m.halo_cap,
+                                             halo_hdr(m.peer_arena[0], m, 1), halo_hdr(m.peer_arena[1], m, 0),
+                                             m.cnt_dev + 10, m.cnt_dev + 9, s->cb.err);
+  ATLJ_LAUNCHED();
+  Timer::end(s);
+  return ATLJ_OK;
+}
+static int hess_launch(atlj_sim *s, cudaStream_t st, double *rec) {
+  MgState &m = s->mg;
+  int rc;
+  PairArgs a = pair_args(s);
+  a.masks = s->masks, a.fin = s->f, a.f = nullptr;
+  // (the kernel reads stamp + 1: header word [2] is the force stamp)
+  a.halo.stamp_left = halo_hdr(m.arena, m, 0) + 1, a.halo.stamp_right = halo_hdr(m.arena, m, 1) + 1;
+  a.halo.xstep = m.cnt_dev + 10, a.halo.timeout_ns = m.timeout_ns, a.halo.err = s->cb.err;
+  Timer::begin(s, 3);
+  const int nb = launch_pair_tile2(st, a, s->cb.err + 2, 2, 0, true);
+  Timer::end(s);
+  if (nb < 0) return nb;
+  if ((rc = launch_finalize(st, s->partials, nb, s->p.model, true, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s)))) return rc;
+  return ATLJ_OK;
 }
 
 // host copy of the owned count <-> device
@@ -407,7 +474,8 @@ static void mg_free(atlj_sim *s) {
   MgState &m = s->mg;
   for (int k = 0; k < m.n_ipc_mapped; k++) cudaIpcCloseMemHandle(m.ipc_mapped[k]);
   m.n_ipc_mapped = 0;
-  for (int d = 0; d < 2; d++) m.peer_arena[d] = nullptr, m.peer_r[d][0] = m.peer_r[d][1] = nullptr, m.peer_cs[d] = nullptr;
+  for (int d = 0; d < 2; d++)
+    m.peer_arena[d] = nullptr, m.peer_r[d][0] = m.peer_r[d][1] = nullptr, m.peer_cs[d] = nullptr, m.peer_f[d] = nullptr;
   cudaFree(m.arena);
   m.arena = nullptr;
   cudaFree(m.cnt_dev);
@@ -434,8 +502,8 @@ struct MgGraphKey {
 
 // what a neighbour needs to write into this rank's memory (exchanged once, by any means)
 struct MgBlob {
-  cudaIpcMemHandle_t arena, r0, r1, cs;
-  unsigned long long arena_bytes, r_bytes, cs_bytes;
+  cudaIpcMemHandle_t arena, r0, r1, cs, f;
+  unsigned long long arena_bytes, r_bytes, cs_bytes, f_bytes;
   long long own_cap, halo_cap, mig_cap;
   int nxl, sc;
 };
@@ -507,7 +575,7 @@ int atlj_sim_mg_set_peers(atlj_sim *s, atlj_sim *left, atlj_sim *right) {
       return ATLJ_ERR_ARG;
     }
     m.peer_arena[d] = pm.arena, m.peer_r[d][0] = peer[d]->r[0], m.peer_r[d][1] = peer[d]->r[1];
-    m.peer_cs[d] = peer[d]->cb.cell_start, m.peer_nxl[d] = peer[d]->g.nxl;
+    m.peer_cs[d] = peer[d]->cb.cell_start, m.peer_nxl[d] = peer[d]->g.nxl, m.peer_f[d] = peer[d]->f;
   }
   return ATLJ_OK;
 }
@@ -528,7 +596,9 @@ int atlj_sim_mg_ipc_blob(atlj_sim *s, char *out) {
   ATLJ_CUDA(cudaIpcGetMemHandle(&b.r0, s->r[0]));
   ATLJ_CUDA(cudaIpcGetMemHandle(&b.r1, s->r[1]));
   ATLJ_CUDA(cudaIpcGetMemHandle(&b.cs, s->cb.cell_start));
+  ATLJ_CUDA(cudaIpcGetMemHandle(&b.f, s->f));
   b.arena_bytes = s->mg.arena_bytes, b.r_bytes = s->r_alloc_bytes, b.cs_bytes = s->cs_alloc_bytes;
+  b.f_bytes = s->f_alloc_bytes;
   b.own_cap = s->mg.own_cap, b.halo_cap = s->mg.halo_cap, b.mig_cap = s->mg.mig_cap, b.nxl = s->g.nxl, b.sc = s->g.sc;
   memcpy(out, &b, sizeof(b));
   return ATLJ_OK;
@@ -541,7 +611,7 @@ int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_b
   for (int d = 0; d < 2; d++) {
     if (d == 1 && same) {
       m.peer_arena[1] = m.peer_arena[0], m.peer_r[1][0] = m.peer_r[0][0], m.peer_r[1][1] = m.peer_r[0][1];
-      m.peer_cs[1] = m.peer_cs[0], m.peer_nxl[1] = m.peer_nxl[0];
+      m.peer_cs[1] = m.peer_cs[0], m.peer_nxl[1] = m.peer_nxl[0], m.peer_f[1] = m.peer_f[0];
       break;
     }
     MgBlob b;
@@ -554,10 +624,11 @@ int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_b
       cudaIpcMemHandle_t *h;
       unsigned long long bytes;
       void **out;
-    } maps[4] = {{&b.arena, b.arena_bytes, (void **)&m.peer_arena[d]},
+    } maps[5] = {{&b.arena, b.arena_bytes, (void **)&m.peer_arena[d]},
                  {&b.r0, b.r_bytes, (void **)&m.peer_r[d][0]},
                  {&b.r1, b.r_bytes, (void **)&m.peer_r[d][1]},
-                 {&b.cs, b.cs_bytes, (void **)&m.peer_cs[d]}};
+                 {&b.cs, b.cs_bytes, (void **)&m.peer_cs[d]},
+                 {&b.f, b.f_bytes, (void **)&m.peer_f[d]}};
     for (auto &mp : maps) {
       void *p = nullptr;
       ATLJ_CUDA(cudaIpcOpenMemHandle(&p, *mp.h, cudaIpcMemLazyEnablePeerAccess));
@@ -577,7 +648,7 @@ int atlj_sim_mg_ipc_open(atlj_sim *s, const char *left_blob, const char *right_b
 
 static bool mg_ready(const atlj_sim *s) {
   return s && s->mg.on && s->mg.peer_arena[0] && s->mg.peer_arena[1] && s->mg.peer_r[0][0] && s->mg.peer_r[1][0] &&
-         s->mg.peer_cs[0] && s->mg.peer_cs[1];
+         s->mg.peer_cs[0] && s->mg.peer_cs[1] && s->mg.peer_f[0] && s->mg.peer_f[1];
 }
 
 int atlj_sim_mg_phase1(atlj_sim *s, double dt) {
@@ -600,6 +671,32 @@ int atlj_sim_mg_phase3(atlj_sim *s, double dt, double *rec_host) {
   const int nb = phase3(s, s->st, false);
   if (nb < 0) return nb;
   int rc = tail(s, dt, s->rec_dev, nb);
+  if (rc) return rc;
+  return sim_copy_rec(s, rec_host, 1);
+}
+
+/* hessian on emulated ranks: phase 3 split in two so that every rank has sent its boundary forces before any rank's
+ * hessian kernel waits for them */
+int atlj_sim_mg_phase3_force(atlj_sim *s) {
+  if (!mg_ready(s) || !sim_tile2(s)) return ATLJ_ERR_ARG;
+  int rc = sim_ensure_masks(s);
+  if (rc) return rc;
+  const int nb = phase3(s, s->st, false, true);
+  if (nb < 0) return nb;
+  if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, s->rec_dev, s->cb.err + 2, nullptr, 0, tile2_rows(s))) ||
+      (rc = force_send(s, s->st)))
+    return rc;
+  ATLJ_CUDA(cudaStreamSynchronize(s->st));
+  return ATLJ_OK;
+}
+int atlj_sim_mg_phase4_hess(atlj_sim *s, double dt, double *rec_host) {
+  if (!mg_ready(s) || !sim_tile2(s)) return ATLJ_ERR_ARG;
+  int rc = hess_launch(s, s->st, s->rec_dev);
+  if (rc) return rc;
+  Timer::begin(s, 2);
+  rc = launch_kick_sums(s->st, 3ll * s->mg.own_cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, s->rec_dev + 4,
+                        s->cb.err + 4, s->mg.cnt_dev + 1);
+  Timer::end(s);
   if (rc) return rc;
   return sim_copy_rec(s, rec_host, 1);
 }
@@ -731,6 +828,51 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
     Timer::end(s);
   }
   if (dt != 0.0) s->step_count += nsteps;  // a dt = 0 "step" is a force evaluation: the RNG counter does not move
+  if ((rc = pull_n(s))) return rc;
+  rc = sim_copy_rec(s, rec_host, nsteps);
+  if (rec_host)
+    for (int k = 0; k < nsteps; k++)
+      if (rec_host[(size_t)k * ATLJ_NREC + 7] > 0.0) rec_host[(size_t)k * ATLJ_NREC + 7] = 1.0;
+  return rc;
+}
+
+// md_nve_lj.py:178-192 with the hessian of md_nve_lj.py:46 in every step's record (rec[6]): the unfused sequence of the
+// single-GPU hessian loop on a slab - integrate, exchange + sort, force (mask words kept), boundary forces to the
+// neighbours, hessian, trailing half kick.  One all-reduce of the records per run.
+int atlj_sim_run_nve_mg_hess(atlj_sim *s, double dt, int nsteps, double *rec_host) {
+  if (!mg_ready(s) || !s->mg.comm || nsteps < 0) {
+    set_error("run_nve_mg_hess: enable the slab, map the neighbours' buffers and connect first");
+    return ATLJ_ERR_ARG;
+  }
+  if (!sim_tile2(s)) {
+    set_error("run_nve_mg_hess: the hessian on slabs runs on the tiled LJ kernels only");
+    return ATLJ_ERR_ARG;
+  }
+  int rc = sim_ensure_rec(s, nsteps > 0 ? nsteps : 1);
+  if (rc || (rc = sim_ensure_masks(s)) || (rc = push_n(s))) return rc;
+  MgState &m = s->mg;
+  ATLJ_CUDA(cudaMemsetAsync(s->rec_dev, 0, sizeof(double) * ATLJ_NREC * (size_t)(nsteps > 0 ? nsteps : 1), s->st));
+  for (int k = 0; k < nsteps; k++) {
+    double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
+    if ((rc = phase1(s, s->st, dt, false, nullptr, 0, false, k > 0)) || (rc = phase2(s, s->st, nullptr, rec, false))) return rc;
+    const int nb = phase3(s, s->st, false, true);
+    if (nb < 0) return nb;
+    if ((rc = launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s))) ||
+        (rc = force_send(s, s->st)) || (rc = hess_launch(s, s->st, rec)))
+      return rc;
+    Timer::begin(s, 2);
+    rc = launch_kick_sums(s->st, 3ll * m.own_cap, s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4, s->cb.err + 4,
+                          m.cnt_dev + 1);
+    Timer::end(s);
+    if (rc) return rc;
+  }
+  if (nsteps > 0) {
+    Timer::begin(s, 3);
+    ATLJ_NCCL(g_nccl.AllReduce(s->rec_dev, s->rec_dev, (size_t)nsteps * ATLJ_NREC, ncclDouble, ncclSum,
+                               (ncclComm_t)m.comm, s->st));
+    Timer::end(s);
+  }
+  if (dt != 0.0) s->step_count += nsteps;
   if ((rc = pull_n(s))) return rc;
   rc = sim_copy_rec(s, rec_host, nsteps);
   if (rec_host)

@@ -19,8 +19,10 @@ struct MgState {
   unsigned char *peer_arena[2] = {nullptr, nullptr};
   double *peer_r[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [left|right][buffer]
   int *peer_cs[2] = {nullptr, nullptr};
+  double *peer_f[2] = {nullptr, nullptr};  // the neighbours' force arrays (hessian on slabs: forces of the halo atoms)
   int peer_nxl[2] = {0, 0};
-  void *ipc_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // to be closed
+  void *ipc_mapped[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // to be closed
   int n_ipc_mapped = 0;
   bool sorted = false;      // the arrays are in cell order and cell_start describes them (false after an upload)
   long long step = 0;                                   // exchange counter: parity selects the buffer, step+1 = stamp
@@ -35,8 +37,9 @@ struct MgState {
 struct atlj_sim {
   cudaStream_t st = nullptr;
   int64_t cap = 0;  // atom capacity of every per-atom buffer
-  bool ipc_safe = false;     // r[0], r[1], cell_start are allocations of their own (exportable with CUDA IPC)
+  bool ipc_safe = false;     // r[0], r[1], f, cell_start are allocations of their own (exportable with CUDA IPC)
   size_t r_alloc_bytes = 0, cs_alloc_bytes = 0;  // their sizes when ipc_safe (a signature sits in the last 256 bytes)
+  size_t f_alloc_bytes = 0;                      // ... and of the force array
   int64_t n = 0;    // owned atoms
   int64_t n_total = 0;       // atoms of the whole system (all ranks); indexes injected noise by global id
   long long step_count = 0;  // steps taken so far (counter of the device RNG)
@@ -103,6 +106,7 @@ int sim_ensure_forces(atlj_sim *s, double strain);  // evaluates s->f when it is
 int sim_check_flags(atlj_sim *s);
 double sim_per_cell(const atlj_sim *s);
 bool sim_tile2(const atlj_sim *s);
+int sim_ensure_masks(atlj_sim *s);  // mask words of pair_tile2 (kept by the force kernel for the hessian kernel)
 int sim_copy_rec(atlj_sim *s, double *rec_host, int nsteps);
 int sim_ensure_rec(atlj_sim *s, int64_t nrec);
 void sim_mg_destroy(atlj_sim *s);

@@ -112,10 +112,11 @@ class SlabRank(Simulation):
         _lib.check(_lib.lib().atlj_sim_mg_connect(self._h, self.rank, self.world, unique_id))
 
     def run_nve(self, dt, nsteps, hessian=False, record=True):
-        assert not hessian, "hessian is not part of the multi-GPU loop"
-        rec = np.zeros((nsteps, NREC)) if record else None
-        _lib.check(_lib.lib().atlj_sim_run_nve_mg(self._h, float(dt), int(nsteps),
-                                                  None if rec is None else rec.ctypes.data))
+        """Velocity-Verlet steps of the whole system (md_nve_lj.py:178-192); hessian=True adds the hessian sum of
+        md_nve_lj.py:46 to every record (REC_HES), with the forces of the halo atoms fetched from the neighbours."""
+        rec = np.zeros((nsteps, NREC)) if (record or hessian) else None
+        fn = _lib.lib().atlj_sim_run_nve_mg_hess if hessian else _lib.lib().atlj_sim_run_nve_mg
+        _lib.check(fn(self._h, float(dt), int(nsteps), None if rec is None else rec.ctypes.data))
         return rec
 
     @property
@@ -137,7 +138,15 @@ class SlabRank(Simulation):
 
     def force(self, strain=0.0, hessian=False):
         """Force evaluation on the current positions = one step with dt = 0 (kick and drift are exact no-ops)."""
-        return self.run_nve(0.0, 1)[0]
+        return self.run_nve(0.0, 1, hessian=hessian)[0]
+
+    def phase3_force(self):
+        _lib.check(_lib.lib().atlj_sim_mg_phase3_force(self._h))
+
+    def phase4_hess(self, dt):
+        rec = np.zeros(NREC)
+        _lib.check(_lib.lib().atlj_sim_mg_phase4_hess(self._h, float(dt), rec.ctypes.data))
+        return rec
 
     def run_baoab(self, dt, gamma, temperature, nsteps, seed=1, noise=None):
         """BAOAB Langevin steps on the slab (bd_nvt_lj.py:221-233); the device noise is keyed by the GLOBAL atom id, so
@@ -195,20 +204,25 @@ class EmulatedSlabs:
         for k, s in enumerate(self.ranks):
             s.set_peers(self.ranks[(k - 1) % world], self.ranks[(k + 1) % world])
 
-    def step(self, dt):
+    def step(self, dt, hessian=False):
         for s in self.ranks:
             s.phase1(dt)
         for s in self.ranks:
             s.phase2()
-        rec = sum(s.phase3(dt) for s in self.ranks)
+        if hessian:   # every rank sends its boundary forces before any rank's hessian kernel waits for them
+            for s in self.ranks:
+                s.phase3_force()
+            rec = sum(s.phase4_hess(dt) for s in self.ranks)
+        else:
+            rec = sum(s.phase3(dt) for s in self.ranks)
         rec[7] = 1.0 if rec[7] > 0 else 0.0
         return rec
 
-    def force(self):
-        return self.step(0.0)
+    def force(self, hessian=False):
+        return self.step(0.0, hessian=hessian)
 
-    def run_nve(self, dt, nsteps):
-        return np.array([self.step(dt) for _ in range(nsteps)])
+    def run_nve(self, dt, nsteps, hessian=False):
+        return np.array([self.step(dt, hessian=hessian) for _ in range(nsteps)])
 
     def _finish(self, dt):
         for s in self.ranks:

@@ -193,6 +193,13 @@ int atlj_sim_mg_connect(atlj_sim *s, int rank, int world, const char *id128);
 /* nsteps velocity-Verlet steps (md_nve_lj.py:178-192) of the whole system, no host synchronisation per step.
  * rec_host (nsteps, ATLJ_NREC) holds the GLOBAL sums on every rank.  dt = 0 gives a plain force evaluation. */
 int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host);
+/* The same with the hessian sum of md_nve_lj.py:46 (hessian(box, r_cut, r, f), md_lj_ll_module.py:227-357) in rec[6] of
+ * every step: after the force kernel each rank stores the forces of its two boundary layers into the neighbours' force
+ * arrays (the halo atoms' forces) and the hessian kernel acquires that second stamp at its boundary layers. */
+int atlj_sim_run_nve_mg_hess(atlj_sim *s, double dt, int nsteps, double *rec_host);
+/* ... on ranks emulated in one process: phase 3 in two halves (force + boundary forces sent | hessian + trailing kick) */
+int atlj_sim_mg_phase3_force(atlj_sim *s);
+int atlj_sim_mg_phase4_hess(atlj_sim *s, double dt, double *rec_host);
 /* The thermostats on slab ranks.  BAOAB (bd_nvt_lj.py:221-233): the noise is keyed by (seed; global atom id, step), so the
  * trajectory does not depend on the decomposition.  Nose-Hoover chain (md_nvt_lj.py:270-288): the chain needs the global
  * sum v^2 once per step - the 12-double step record is all-reduced (NCCL) inside the step; eta, p_eta as in

@@ -130,6 +130,43 @@ def test_emulated_slabs_match_single_domain(nc, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nc,world", [(10, 2), (10, 3), (14, 4)])
+def test_emulated_slabs_hessian_in_the_loop(nc, world):
+    """md_nve_lj.py:46 calls hessian(box, r_cut, r, f) every step (md_lj_ll_module.py:227-357): on slabs the pair terms of
+    a boundary atom need the forces of its halo partners, which the neighbours store into this rank's force array after
+    their pair kernel (second stamp).  The records' hessian column must match the single-domain loop (same per-pair
+    arithmetic, different summation order across ranks), and the trajectory stays bit-identical."""
+    from examples_b200 import _lib
+    from examples_b200.device import REC_HES, Simulation
+    from examples_b200.lattice import ran_velocities
+    from examples_b200.slab import EmulatedSlabs
+    _lib.set_multi_max(0)  # same (tiled) pair kernel on both sides
+    n, box, r = liquid_like(nc, 0.75, 0.06)
+    v = ran_velocities(n, 1.5)
+    one = Simulation(box, 2.5, r, v)
+    rec1 = one.force(hessian=True)
+    many = EmulatedSlabs(box, 2.5, r, v, world)
+    recm = many.force(hessian=True)
+    assert rec1[REC_HES] != 0.0
+    assert rel_err(recm[[0, 1, 2, 3, REC_HES]], rec1[[0, 1, 2, 3, REC_HES]]) < 1e-10 and recm[8] == rec1[8]
+    # against the CPU oracle as well (not only kernel against kernel)
+    from oracle import oracle as O
+    _, fo, _, _ = O.force(np.ascontiguousarray(r - np.rint(r)), box, 2.5, cells=True)
+    hes_o = O.hessian(np.ascontiguousarray(r - np.rint(r)), fo, box, 2.5, cells=True)
+    assert abs(recm[REC_HES] - hes_o) <= 1e-10 * abs(hes_o)
+    nsteps = 30
+    t1 = one.run_nve(0.005, nsteps, hessian=True)
+    tm = many.run_nve(0.005, nsteps, hessian=True)
+    for k in (0, 1, 2, 3, 4, 5, REC_HES):
+        assert rel_err(tm[:, k], t1[:, k]) < 1e-9, k
+    assert np.array_equal(tm[:, 8], t1[:, 8]) and np.all(tm[:, 11] == n)
+    r1, v1, f1 = one.download()
+    rm, vm, fm = many.gather()
+    assert np.array_equal(rm, r1) and np.array_equal(vm, v1) and np.array_equal(fm, f1)
+    one.close(), many.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_emulated_slabs_baoab_and_nose_hoover(world):
     """SURVEY.md 8e widened: the thermostats on slabs.  BAOAB (bd_nvt_lj.py:221-233) draws its noise from Philox keyed
