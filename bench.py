@@ -465,6 +465,14 @@ def run_ours(args, rank, world, local_rank):
                              "pcie_gb_per_s": 2 * 24 * n / sec / 1e9, "bytes_per_call": 2 * 24 * n}
         for a in (pr, pv, pf, pi):
             a.free()
+        # the drop-in on the reference's own configurations (same rows as cpu_baseline.reference_python)
+        if not args.no_cpu:
+            try:
+                p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_dropin.py")], capture_output=True,
+                                   text=True, timeout=600)
+                e2e["dropin_on_reference_configs"] = json.loads(p.stdout.strip().splitlines()[-1])["rows"]
+            except Exception as e:  # noqa: BLE001
+                e2e["dropin_on_reference_configs"] = {"unavailable": str(e)[:200]}
 
     if world > 1:
         # every rank's owned atoms live in page-locked host arrays; each step copies them in, runs one exchange step
