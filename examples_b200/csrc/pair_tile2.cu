@@ -100,7 +100,8 @@ int pair_tile2_tab_ints(const Geom &g) {
 int pair_tile2_items(const Geom &g) { return g.nx_own * ((g.sc + 1) / 2) * (tile2_gstride(g) - 1); }
 
 __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__restrict__ cs, int nyb, int nrp,
-                                                          int gstride, int gk, int ncz_max, int *__restrict__ tab) {
+                                                          int gstride, int gk, int ncz_max, int catoms,
+                                                          int *__restrict__ tab) {
   __shared__ int cnt[4][1024];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int rp = blockIdx.x * 4 + w;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
     if (nch % gk == 0 && ng < gstride - 1) zb[ng] = gpos, zc[ng] = z0, ng++;
     int lim = cum0;
     for (int c = 0; c < ncz_max && z0 + c < sc; c++) lim += cnt[w][z0 + c];
-    gpos = min(gpos + U_NT, lim);  // same rule as the kernel's chunk extent
+    gpos = min(gpos + catoms, lim);  // same rule as the kernel's chunk extent
     nch++;
   }
   zb[ng] = T;
@@ -224,10 +225,10 @@ __device__ __forceinline__ double rcp46(double s) {
     }                                                                                  \
   } while (0)
 
-template <int MODE>
+template <int MODE, bool SPLIT = false>
 __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
     pair_tile2_kernel(PairArgs a, int nyb, int nrp, int gstride, int ncz_max, const int *__restrict__ tab,
-                      int *__restrict__ work_counter, int *__restrict__ rows_out, double rc2s) {
+                      int *__restrict__ work_counter, int *__restrict__ rows_out, double rc2s, int catoms) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *ux = reinterpret_cast<double *>(smem_raw);
   double *uy = ux + U_STR;
@@ -250,6 +251,12 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   const Geom g = a.g;
   const Phys p = a.p;
   const bool save_masks = MODE == T2_FORCE && a.masks != nullptr;  // T2_FORCE_SAVE is T2_FORCE with a mask buffer
+  // Small systems (fewer chunks than CTA slots: the kernel lasts as long as ONE chunk's dependent instruction stream):
+  // chunks of 64 atoms and TWO threads per atom - warps 0, 1 take the lower half of every atom's candidate windows,
+  // warps 2, 3 the upper half - and the two partial forces are added through shared memory in a fixed order.
+  // (a template parameter: as a run-time flag the tests in the loops cost the large systems 0.8 %)
+  constexpr bool split = SPLIT && MODE == T2_FORCE;
+  const int part = split ? (int)(threadIdx.x >> 6) : 0;
   const int sc = g.sc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *__restrict__ cs = a.cell_start;
   const double box = p.box;
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         sBloc[tid] = two ? cs[ownB0 + zz] : 0;
       }
       __syncthreads();
-      int g1 = min(min(g0 + U_NT, gB), cumloc[min(ncz_max, U_MAXC - 2)]);
+      int g1 = min(min(g0 + catoms, gB), cumloc[min(ncz_max, U_MAXC - 2)]);
       int ncz = 1;  // cells that hold atoms [g0, g1)
       while (cumloc[ncz] < g1) ncz++;
 
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
       const __half thr_h = __float2half_ru(thr);
 
       for (int ib = 0; ib < ni; ib += U_NT) {
-        const int il = ib + tid;
+        const int il = ib + (split ? (tid & 63) : tid);
         const bool act = il < ni;
         int myc = 0, self = 0, i = 0, k0 = 0;
         if (act) {
@@ -653,9 +660,17 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
               const int b = S[eb], e = S[eb + 9];
               if (e <= b) continue;
               const int b0 = b & ~1;
-              const int npairs = ((e + 1) >> 1) - (b0 >> 1);
+              int npairs = ((e + 1) >> 1) - (b0 >> 1);
               const uint4 *pp = hp + (b0 >> 1);
-              for (int base = 0; base < npairs; base += 16) {
+              int base = 0;
+              if (split) {  // this thread's share of the window's 16-record groups
+                const int half = 16 * ((((npairs + 15) >> 4) + 1) >> 1);
+                if (part == 0)
+                  npairs = w == 0 ? npairs : (w == 1 ? min(npairs, half) : 0);
+                else
+                  base = w == 2 ? 0 : (w == 1 ? half : npairs);
+              }
+              for (; base < npairs; base += 16) {
                 const int n = min(16, npairs - base);
                 unsigned wd = 0u;
 #pragma unroll U_P1U
@@ -853,7 +868,16 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           else
             U_EXACT(defer[k]);
         }
-        if (MODE != T2_HESS && act) {
+        if (split) {
+          // upper-half threads hand their partial force over through the (now idle) fp16 region; fixed order of the
+          // two-term sum, so the result is reproducible
+          double *fsc = reinterpret_cast<double *>(hp);
+          __syncthreads();  // every warp is past phase 1 (the last reader of that region)
+          if (part == 1 && act) fsc[3 * il] = fx, fsc[3 * il + 1] = fy, fsc[3 * il + 2] = fz;
+          __syncthreads();
+          if (part == 0 && act) fx += fsc[3 * il], fy += fsc[3 * il + 1], fz += fsc[3 * il + 2];
+        }
+        if (MODE != T2_HESS && act && part == 0) {
           a.f[3 * (size_t)i] = 24.0 * fx;  // md_lj_module.py:143
           a.f[3 * (size_t)i + 1] = 24.0 * fy;
           a.f[3 * (size_t)i + 2] = 24.0 * fz;
@@ -923,12 +947,22 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   // least 1 (small systems), at most U_GK_MAX
   const int grid_f = tile2_grid<T2_FORCE>();
   const long long natoms = a.natoms > 0 ? (long long)a.natoms : 12ll * a.g.n_own_cells();
-  const long long chunks = natoms / (U_NT - U_NT / 16) + nrp;
+  const double per_cell =
+      a.per_cell > 0.0 ? a.per_cell : (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
+  // two threads per atom and 64-atom chunks (split mode of the force kernel) while the WHOLE system - all ranks: the
+  // rule must not depend on the decomposition, or slab and single-domain forces would differ in the last bit - has
+  // fewer 64-atom chunks than the GPU has CTA slots; never together with the mask words the hessian kernel walks
+  static long long split_max = -1;
+  if (split_max < 0) {
+    const char *sm = getenv("ATLJ_SPLIT_MAX");
+    split_max = sm ? atoll(sm) : 44000;
+  }
+  const double n_system = per_cell * (double)a.g.sc * (double)a.g.sc * (double)a.g.sc;
+  const int catoms = (mode == T2_FORCE && U_NT == 128 && n_system <= (double)split_max) ? 64 : U_NT;
+  const long long chunks = natoms / (catoms - catoms / 16) + nrp;
   int gk = (int)(chunks / ((long long)ATLJ_U_IPC * (grid_f > 0 ? grid_f : grid)));
   gk = gk < 1 ? 1 : (gk > U_GK_MAX ? U_GK_MAX : gk);
   // cells a chunk may span: the staged cross-section (12 rows per cell, one halo cell at each end) has to fit U_CAP
-  const double per_cell =
-      a.per_cell > 0.0 ? a.per_cell : (double)natoms / (double)(a.g.n_own_cells() > 0 ? a.g.n_own_cells() : 1);
   int ncz_max = (int)(0.96 * U_CAP / (U_K * (per_cell > 0.05 ? per_cell : 0.05))) - 2;
   // fp16 range: the chunk-centred z coordinates stay below 100 sigma
   const double cell = a.p.box / a.g.sc;
@@ -936,7 +970,8 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
   if (mode != T2_HESS && part != 2) {
     if (!tab_zeroed) ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
-    tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, a.tile_tab);
+    tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, catoms,
+                                                      a.tile_tab);
     ATLJ_LAUNCHED();
   }
   const int bound = nrp * (gstride - 1);
@@ -944,13 +979,25 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   const int nblk = grid < bound ? grid : bound;
   if (mode == T2_HESS)
     pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                         work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq);
+                                                         work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, U_NT);
   else
   {
     PairArgs af = a;
     if (mode == T2_FORCE) af.masks = nullptr;
-    pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                          work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq);
+    if (catoms < U_NT) {
+      static bool attr = false;
+      if (!attr) {
+        ATLJ_CUDA(cudaFuncSetAttribute(pair_tile2_kernel<T2_FORCE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        attr = true;
+      }
+      pair_tile2_kernel<T2_FORCE, true><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab,
+                                                                   work_counter, work_counter + 4,
+                                                                   a.p.r_cut_box_sq * a.p.box_sq, catoms);
+    } else {
+      pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
+                                                            work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, catoms);
+    }
   }
   ATLJ_LAUNCHED();
   return bound;
