@@ -15,6 +15,12 @@ namespace atlj {
 
 static thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+static int pdl_default() {
+  const char *e = getenv("ATLJ_PDL");  // bit mask of the kernels launched with the attribute (A/B runs)
+  return e ? atoi(e) : (PDL_SCAN | PDL_SCATTER | PDL_GATHER | PDL_PAIR);
+}
+int g_pdl = pdl_default();
+int g_pdl_off = 0;
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -643,7 +649,9 @@ static int nve_graph_prepare(atlj_sim *s, int kind, double dt, int nb_prev, Body
   const int64_t l0 = g_launches;
   const int cur0 = s->cur;
   ATLJ_CUDA(cudaStreamBeginCapture(s->st_cap, cudaStreamCaptureModeThreadLocal));
+  g_pdl_off = (s->n_total > 0 ? s->n_total : s->n) > 44000;  // (common.cuh: programmatic launches inside a graph)
   int rc = body(s->st_cap, s->st_side);
+  g_pdl_off = 0;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(s->st_cap, &graph);
   s->nve_graph_launches = (int)(g_launches - l0);
@@ -660,6 +668,12 @@ static int nve_graph_prepare(atlj_sim *s, int kind, double dt, int nb_prev, Body
       s->nve_graph = nullptr;
       rc = ATLJ_ERR_CUDA;
     }
+  }
+  if (getenv("ATLJ_DEBUG_GRAPH")) {
+    size_t nn = 0;
+    if (graph) cudaGraphGetNodes(graph, nullptr, &nn);
+    fprintf(stderr, "atlj: graph capture rc=%d (%s), %zu nodes, pdl mask %d: %s\n", rc, cudaGetErrorString(e), nn, g_pdl,
+            rc == ATLJ_OK ? "replayed" : atlj_last_error());
   }
   if (graph) cudaGraphDestroy(graph);
   if (rc == ATLJ_OK) memcpy(s->nve_graph_key, &key, sizeof(key));

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
                                                         int model, SlabArgs sl, const int *__restrict__ pair_rows_dev,
                                                         int *__restrict__ step_ctr, int *__restrict__ tab0,
                                                         int no_assign) {
+  pdl_wait();  // (a no-op by default: this kernel is not launched programmatically, see common.cuh)
+  pdl_launch_dependents();
   if (pair_rows_dev) pair_rows = min(pair_rows, *pair_rows_dev);
   // replayed launches (CUDA graph): the record of the finished step is rec_vf + NREC * *step_ctr; the CTA that finishes
   // last moves the counter on.  tab0: word 0 of the pair kernel's item table, zeroed here for this step's table kernel
@@ -349,9 +351,9 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
   const bool ones = (bits & 0xfffffffffffffull) == 0xfffffffffffffull;
   const double inv_box = (!ones && box > 1e-100 && box < 1e100) ? 1.0 / box : 0.0;
 #define ATLJ_KDK(RCP, SLAB)                                                                                          \
-  kdk_assign_kernel<RCP, SLAB><<<nb, IT, 0, st>>>(g, n, r, v, f, half_dt, dt, box, inv_box, first_kick ? 1 : 0, b.cellid, \
-                                                  b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials,     \
-                                                  pair_rows, model, sl, pair_rows_dev, step_ctr, tab0, no_assign)
+  launch_pdl(PDL_KDK, kdk_assign_kernel<RCP, SLAB>, dim3(nb), dim3(IT), 0, st, g, n, r, v, f, half_dt, dt, box, inv_box,        \
+             first_kick ? 1 : 0, b.cellid, b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows,  \
+             model, sl, pair_rows_dev, step_ctr, tab0, no_assign)
   if (inv_box != 0.0) {
     if (slab)
       ATLJ_KDK(true, true);
@@ -413,6 +415,8 @@ __global__ void __launch_bounds__(SCAN_T) scan_lookback_kernel(const int *__rest
   __shared__ int sm[SCAN_T / 32];
   __shared__ int total;
   __shared__ int s_before;
+  pdl_wait();
+  pdl_launch_dependents();
   const int tile = blockIdx.x;
   const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
@@ -490,8 +494,8 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
     set_error("cell grid too large for the scan (%d cells)", n);
     return ATLJ_ERR_ARG;
   }
-  scan_lookback_kernel<<<ntiles, SCAN_T, 0, st>>>(b.cell_count + first, n, base, b.cell_start, g.sc * g.sc, g.h,
-                                                  reinterpret_cast<unsigned long long *>(b.block_sums));
+  launch_pdl(PDL_SCAN, scan_lookback_kernel, dim3(ntiles), dim3(SCAN_T), 0, st, b.cell_count + first, n, base, b.cell_start,
+             g.sc * g.sc, g.h, reinterpret_cast<unsigned long long *>(b.block_sums));
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }
@@ -505,6 +509,8 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const 
                                                            const int *__restrict__ cell_start,
                                                            const int *__restrict__ id_in,
                                                            unsigned *__restrict__ ids) {
+  pdl_wait();
+  pdl_launch_dependents();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
@@ -539,6 +545,8 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
                                                                 double *__restrict__ v_out,
                                                                 int *__restrict__ id_out, int zero_counts,
                                                                 HaloOut ho) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * RG_T + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
   const int nown = g.n_own_cells(), first = g.first_own_cell(), sc2 = g.sc * g.sc;
@@ -618,7 +626,8 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
                             const int *n_dev, const HaloOut *halo, bool zero_counts) {
   if (n <= 0) return ATLJ_OK;
   unsigned *ids = reinterpret_cast<unsigned *>(b.keys);
-  cell_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, n, n_dev, base, b.cellid, b.rank, b.cell_start, id_in, ids);
+  launch_pdl(PDL_SCATTER, cell_scatter_kernel, dim3((n + 255) / 256), dim3(256), 0, st, g, n, n_dev, base, b.cellid, b.rank,
+             b.cell_start, id_in, ids);
   ATLJ_LAUNCHED();
   HaloOut ho;
   memset(&ho, 0, sizeof(ho));
@@ -626,9 +635,8 @@ int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, i
   int cover = n;  // threads: every source atom, every owned cell (zero_counts), every entry of a halo cell table
   if (zero_counts && g.n_own_cells() > cover) cover = g.n_own_cells();
   if (halo && g.sc * g.sc + 1 > cover) cover = g.sc * g.sc + 1;
-  cell_rankgather_kernel<<<(cover + RG_T - 1) / RG_T, RG_T, 0, st>>>(g, n, n_dev, base, b.cellid, id_in, b.cell_start,
-                                                                      b.cell_count, ids, r_in, v_in, r_out, v_out,
-                                                                      id_out, zero_counts ? 1 : 0, ho);
+  launch_pdl(PDL_GATHER, cell_rankgather_kernel, dim3((cover + RG_T - 1) / RG_T), dim3(RG_T), 0, st, g, n, n_dev, base, b.cellid,
+             id_in, b.cell_start, b.cell_count, ids, r_in, v_in, r_out, v_out, id_out, zero_counts ? 1 : 0, ho);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

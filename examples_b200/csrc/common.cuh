@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/atlj.h"
 
@@ -31,6 +32,42 @@ extern int64_t g_launches;  // kernels launched by this library (atlj_kernel_lau
       return ATLJ_ERR_CUDA;                                                                      \
     }                                                                                            \
   } while (0)
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------
+// The kernels of the step loop are tiny next to the pair kernel and strictly dependent; with the attribute below the
+// next kernel of the stream is launched while its predecessor drains (its CTAs become resident as slots free up) and
+// blocks in pdl_wait() - the first statement of every such kernel - until the predecessor has completed and its
+// memory is visible.  Launched without the attribute (ATLJ_PDL=0, or a kernel that follows a copy), pdl_wait() and
+// pdl_launch_dependents() are no-ops.
+extern int g_pdl;  // bit mask of the kernels that use the attribute (ATLJ_PDL; 0: plain stream order everywhere)
+enum { PDL_KDK = 1, PDL_SCAN = 2, PDL_SCATTER = 4, PDL_GATHER = 8, PDL_TABLE = 16, PDL_PAIR = 32 };
+// Measured (profiles/r2_hbm_kernels.md): stream-launched loops gain 1.5-3.6 %; inside a replayed graph the attribute
+// only pays for systems below ~44,000 atoms and costs ~1.5 us per step above, and on the integration kernel (which
+// would queue up behind the persistent pair kernel) it costs 17 us at 2 M atoms.  Default mask: scan, scatter, gather,
+// pair; switched off while a graph of a larger system is being captured (g_pdl_off).
+extern int g_pdl_off;
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = ((g_pdl & which) && !g_pdl_off) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- local cell grid of one rank ------------------------------------------------------------------------------
 // Global grid: sc x sc x sc cells, id = (c0*sc + c1)*sc + c2 (C order, md_lj_ll_module.py:116).

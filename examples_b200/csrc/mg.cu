@@ -779,6 +779,7 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
       const int cur0 = s->cur;
       const long long step0 = m.step;
       ATLJ_CUDA(cudaStreamBeginCapture(s->st_cap, cudaStreamCaptureModeThreadLocal));
+      g_pdl_off = s->n_total > 44000;  // (common.cuh: programmatic launches inside a graph)
       int nbc = nb;
       for (int j = 0; j < 2 && rc == ATLJ_OK; j++) {
         if ((rc = phase1(s, s->st_cap, dt, true, s->rec_dev, nbc, true, true)) ||
@@ -786,6 +787,7 @@ int atlj_sim_run_nve_mg(atlj_sim *s, double dt, int nsteps, double *rec_host) {
           break;
         if ((nbc = phase3(s, s->st_cap, sim_tile2(s))) < 0) rc = nbc;
       }
+      g_pdl_off = 0;
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(s->st_cap, &graph);
       s->nve_graph_launches = (int)(g_launches - l0);

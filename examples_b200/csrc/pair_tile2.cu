@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(128) tile2_table_kernel(Geom g, const int *__r
                                                           int gstride, int gk, int ncz_max, int catoms,
                                                           int *__restrict__ tab) {
   __shared__ int cnt[4][1024];
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int rp = blockIdx.x * 4 + w;
   if (rp >= nrp) return;
@@ -248,6 +250,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
 #endif
   __shared__ int s_item, s_halo;
 
+  pdl_wait();  // launched while the sort drains (common.cuh)
+  pdl_launch_dependents();
   const Geom g = a.g;
   const Phys p = a.p;
   const bool save_masks = MODE == T2_FORCE && a.masks != nullptr;  // T2_FORCE_SAVE is T2_FORCE with a mask buffer
@@ -970,16 +974,16 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
   ncz_max = ncz_max < 1 ? 1 : (ncz_max > U_MAXC - 2 ? U_MAXC - 2 : ncz_max);
   if (mode != T2_HESS && part != 2) {
     if (!tab_zeroed) ATLJ_CUDA(cudaMemsetAsync(a.tile_tab, 0, sizeof(int), st));
-    tile2_table_kernel<<<(nrp + 3) / 4, 128, 0, st>>>(a.g, a.cell_start, nyb, nrp, gstride, gk, ncz_max, catoms,
-                                                      a.tile_tab);
+    launch_pdl(PDL_TABLE, tile2_table_kernel, dim3((nrp + 3) / 4), dim3(128), 0, st, a.g, a.cell_start, nyb, nrp, gstride, gk,
+               ncz_max, catoms, a.tile_tab);
     ATLJ_LAUNCHED();
   }
   const int bound = nrp * (gstride - 1);
   if (part == 1) return bound;
   const int nblk = grid < bound ? grid : bound;
   if (mode == T2_HESS)
-    pair_tile2_kernel<T2_HESS><<<nblk, U_NT, smem, st>>>(a, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                         work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, U_NT);
+    launch_pdl(PDL_PAIR, pair_tile2_kernel<T2_HESS>, dim3(nblk), dim3(U_NT), smem, st, a, nyb, nrp, gstride, ncz_max, a.tile_tab,
+               work_counter, work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, U_NT);
   else
   {
     PairArgs af = a;
@@ -991,12 +995,11 @@ int launch_pair_tile2(cudaStream_t st, const PairArgs &a, int *work_counter, int
                                        (int)smem));
         attr = true;
       }
-      pair_tile2_kernel<T2_FORCE, true><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab,
-                                                                   work_counter, work_counter + 4,
-                                                                   a.p.r_cut_box_sq * a.p.box_sq, catoms);
+      launch_pdl(PDL_PAIR, pair_tile2_kernel<T2_FORCE, true>, dim3(nblk), dim3(U_NT), smem, st, af, nyb, nrp, gstride, ncz_max,
+                 a.tile_tab, work_counter, work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, catoms);
     } else {
-      pair_tile2_kernel<T2_FORCE><<<nblk, U_NT, smem, st>>>(af, nyb, nrp, gstride, ncz_max, a.tile_tab, work_counter,
-                                                            work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, catoms);
+      launch_pdl(PDL_PAIR, pair_tile2_kernel<T2_FORCE>, dim3(nblk), dim3(U_NT), smem, st, af, nyb, nrp, gstride, ncz_max,
+                 a.tile_tab, work_counter, work_counter + 4, a.p.r_cut_box_sq * a.p.box_sq, catoms);
     }
   }
   ATLJ_LAUNCHED();
