@@ -33,7 +33,30 @@ def staged_reference():
     return d if os.path.isfile(os.path.join(d, "md_nve_lj.py")) else None
 
 
+_WRAP = r"""
+import io, json, runpy, sys, time
+script, nstep = sys.argv[1], int(sys.argv[2])
+sys.argv = [script]
+def run(ns):
+    sys.stdin = io.StringIO('{"nblock":1,"nstep":%d}' % ns)
+    out, old = io.StringIO(), sys.stdout
+    sys.stdout = out
+    t0 = time.perf_counter()
+    try:
+        runpy.run_path(script, run_name='__main__')
+    finally:
+        sys.stdout = old
+    return time.perf_counter() - t0, out.getvalue()
+run(10)                      # imports, CUDA context, buffers
+a, _ = run(10)
+b, text = run(10 + nstep)
+print(json.dumps({"short": a, "long": b, "ok": "Program ends" in text and "CUDA force routine" in text}))
+"""
+
+
 def time_driver(ref, nstep=2000):
+    """The unmodified script, run three times IN ONE PROCESS (runpy): the difference between a 10-step and a
+    (10 + nstep)-step run is the time of nstep steps of its loop, free of interpreter and CUDA start-up."""
     n, box, r = fcc_positions(4, 0.75)
     r = perturb(r, box, 0.05)
     v = ran_velocities(n, 1.0, seed=1)
@@ -43,17 +66,16 @@ def time_driver(ref, nstep=2000):
             np.savetxt(fh, np.concatenate((r * box, v), axis=1), fmt="%15.10f")
         # PYTHONSAFEPATH: the script's own directory must not shadow the drop-in (same as tests/test_reference_driver.py)
         env = dict(os.environ, PYTHONPATH=os.pathsep.join([DROPIN, ROOT, ref]), PYTHONSAFEPATH="1")
-        t = []
-        # the difference of two run lengths removes start-up, imports and CUDA context creation (~0.5 s, more than the
-        # steps themselves); a first run warms the file cache up
-        for ns in (10, 10, 10 + nstep):
-            t0 = time.perf_counter()
-            p = subprocess.run([sys.executable, os.path.join(ref, "md_nve_lj.py")], input='{"nblock":1,"nstep":%d}' % ns,
-                               capture_output=True, text=True, cwd=tmp, env=env, timeout=600)
-            t.append(time.perf_counter() - t0)
-            if p.returncode != 0 or "Program ends" not in p.stdout or "CUDA force routine" not in p.stdout:
-                raise RuntimeError("md_nve_lj.py on the drop-in failed: " + (p.stderr or p.stdout)[-400:])
-        return n, t[2], (t[2] - t[1]) / nstep
+        t0 = time.perf_counter()
+        p = subprocess.run([sys.executable, "-c", _WRAP, os.path.join(ref, "md_nve_lj.py"), str(nstep)],
+                           capture_output=True, text=True, cwd=tmp, env=env, timeout=600)
+        wall = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError("md_nve_lj.py on the drop-in failed: " + (p.stderr or p.stdout)[-400:])
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+        if not d["ok"]:
+            raise RuntimeError("md_nve_lj.py did not run on the drop-in module")
+        return n, wall, (d["long"] - d["short"]) / nstep
 
 
 def main():
