@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
             double *d = reinterpret_cast<double *>((dir ? to_right : to_left) + 64) + 7 * (size_t)slot;
             d[0] = w0, d[1] = w1, d[2] = w2;
             d[3] = vs[3 * threadIdx.x], d[4] = vs[3 * threadIdx.x + 1], d[5] = vs[3 * threadIdx.x + 2];
-            d[6] = (double)sl.id[i];
-            __threadfence_system();
+            d[6] = (double)sl.id[i];  // (no fence here: mig_publish_kernel, mg.cu, publishes after this kernel)
           }
           cellid[i] = -1;
           rank[i] = 0;
@@ -244,20 +243,6 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
       }
     }
     __syncthreads();
-    if (btile && threadIdx.x == 0) {
-      // the leavers' stores were fenced at system scope by their threads, before the barrier; the tile that completes
-      // the two boundary layers publishes: header [0] = number of atoms, [1] = step stamp (system-scope release)
-      __threadfence();
-      if (atomicAdd(&sl.mig_cnt[2], 1) == nbt - 1) {
-        __threadfence();
-        for (int dir = 0; dir < 2; dir++) {
-          int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
-          hdr[0] = min(atomicAdd(&sl.mig_cnt[dir], 0), sl.mig_cap);
-          __threadfence_system();
-          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
-        }
-      }
-    }
   }
   if (!first_kick && !slab) return;
   // ---- finish the record of the step that just ended; publish the migration messages ------------------------------
@@ -283,18 +268,10 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (slab && threadIdx.x == 0) {
-    if (nbt == 0) {  // no atoms at all: empty messages
-      for (int dir = 0; dir < 2; dir++) {
-        int *hdr = reinterpret_cast<int *>(dir ? to_right : to_left);
-        hdr[0] = 0;
-        __threadfence_system();
-        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(xstep + 1) : "memory");
-      }
-    }
-    sl.mig_cnt[0] = sl.mig_cnt[1] = sl.mig_cnt[2] = 0;
-    *sl.xstep = xstep + 1;
-  }
+  // (the migration messages - header counts and stamps - are published by mig_publish_kernel right after this kernel:
+  // system-scope fences inside it, one per leaving atom's thread plus two in the tile that completed the boundary
+  // layers, kept those CTAs waiting for ~15 us each: 70 us on a slab against 63.5 us for the single domain)
+  if (slab && threadIdx.x == 0) *sl.xstep = xstep + 1;
   if (first_kick) {
     double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
@@ -511,12 +488,12 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const 
                                                            unsigned *__restrict__ ids) {
   pdl_wait();
   pdl_launch_dependents();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  int cid = cellid[i];
-  if (cid < 0) return;
-  ids[cell_start[g.cs_idx(cid)] - base + rank[i]] = id_in ? (unsigned)id_in[i] : (unsigned)i;
+  // (grid-stride: on a slab the grid is sized from the host's last known atom count, not from the capacity)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int cid = cellid[i];
+    if (cid >= 0) ids[cell_start[g.cs_idx(cid)] - base + rank[i]] = id_in ? (unsigned)id_in[i] : (unsigned)i;
+  }
 }
 
 // ---- 4. rank inside the cell + gather --------------------------------------------------------------------------------
@@ -533,7 +510,8 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const 
 // positions land - into the halo rows of the neighbours' cell_start, and the CTA that finishes last publishes the step
 // stamp in both neighbours' headers.
 constexpr int RG_T = 256;
-__global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
+template <bool HALO>
+__global__ void __launch_bounds__(RG_T, 8) cell_rankgather_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
                                                                 const int *__restrict__ cellid,
                                                                 const int *__restrict__ id_in,
                                                                 const int *__restrict__ cell_start,
@@ -547,75 +525,84 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
                                                                 HaloOut ho) {
   pdl_wait();
   pdl_launch_dependents();
-  const int i = blockIdx.x * RG_T + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
   const int nown = g.n_own_cells(), first = g.first_own_cell(), sc2 = g.sc * g.sc;
-  if (zero_counts && i < nown) cell_count[first + i] = 0;  // ready for the next step's histogram
-  const bool halo = ho.dst_r_left != nullptr;
+  constexpr bool halo = HALO;
+  // threads needed: every source atom, every owned cell (zero_counts), every entry of a halo cell table.  On a slab
+  // the atom count lives on the device and the grid is sized from the host's last known count: a grid-stride loop
+  // takes whatever lies beyond (a grid over the CAPACITY was 2,300 idle CTAs)
+  int cover = n;
+  if (zero_counts && nown > cover) cover = nown;
+  if (halo && sc2 + 1 > cover) cover = sc2 + 1;
   int F0 = 0, F1 = 0, L0 = 0, L1 = 0;
-  if (halo) {
-    const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
-    F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
-    if (i <= sc2) {  // the two layers' cell tables, rebased (entry sc2 = end sentinel)
-      ho.dst_cs_left[i] = ho.base_left + min(rowF[i] - F0, F1 - F0);
-      ho.dst_cs_right[i] = ho.base_right + min(rowL[i] - L0, L1 - L0);
+  for (int i = blockIdx.x * RG_T + threadIdx.x; i < cover; i += gridDim.x * RG_T) {
+    if (zero_counts && i < nown) cell_count[first + i] = 0;  // ready for the next step's histogram
+    int cid = -1;
+    // the atom's own data is requested first: those loads are in flight while the rank is being counted
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    if (i < n) {
+      cid = cellid[i];
+      x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
+      if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
     }
-    if (i == 0) {
-      const int n_own = rowL[sc2];  // end of the last owned layer = owned atoms after the sort
-      *ho.n_own = n_own;
-      if (ho.rec) ho.rec[(ho.rec_ctr ? (size_t)ATLJ_NREC * (size_t)*ho.rec_ctr : 0) + 11] = (double)n_own;
-      if (n_own > ho.own_cap || rowL[sc2] - L0 > ho.cap || rowF[sc2] - F0 > ho.cap)
-        atomicOr(ho.err + 1, 1);  // more atoms than the owned region / the neighbours' halo regions hold
-    }
-  }
-  int cid = -1, sent = 0;
-  // the atom's own data is requested first: those loads are in flight while the rank is being counted
-  double x0 = 0.0, x1 = 0.0, x2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  if (i < n) {
-    cid = cellid[i];
-    x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
-    if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
-  }
-  if (cid >= 0) {
-    const unsigned myid = id_in ? (unsigned)id_in[i] : (unsigned)i;
-    const int ci = g.cs_idx(cid);
-    const int s0 = cell_start[ci] - base, s1 = cell_start[ci + 1] - base;
-    int slot = s0;
-    for (int s = s0; s < s1; s++) slot += ids[s] < myid;
-    const size_t d = 3 * (size_t)slot;
-    r_out[d] = x0, r_out[d + 1] = x1, r_out[d + 2] = x2;
-    if (v_in) v_out[d] = w0, v_out[d + 1] = w1, v_out[d + 2] = w2;
-    if (id_out) id_out[slot] = (int)myid;
     if (halo) {
-      const int gs = slot + base;
-      if (gs >= F0 && gs < F1) {
-        double *p = ho.dst_r_left + 3 * (size_t)(gs - F0);
-        p[0] = x0, p[1] = x1, p[2] = x2;
-        sent = 1;
+      // (after the atom's loads have been issued: these four values gate nothing but the peer stores further down)
+      const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+      F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
+      if (i <= sc2) {  // the two layers' cell tables, rebased (entry sc2 = end sentinel)
+        ho.dst_cs_left[i] = ho.base_left + min(rowF[i] - F0, F1 - F0);
+        ho.dst_cs_right[i] = ho.base_right + min(rowL[i] - L0, L1 - L0);
       }
-      if (gs >= L0 && gs < L1) {
-        double *p = ho.dst_r_right + 3 * (size_t)(gs - L0);
-        p[0] = x0, p[1] = x1, p[2] = x2;
-        sent = 1;
+      if (i == 0) {
+        const int n_own = rowL[sc2];  // end of the last owned layer = owned atoms after the sort
+        *ho.n_own = n_own;
+        if (ho.rec) ho.rec[(ho.rec_ctr ? (size_t)ATLJ_NREC * (size_t)*ho.rec_ctr : 0) + 11] = (double)n_own;
+        if (n_own > ho.own_cap || rowL[sc2] - L0 > ho.cap || rowF[sc2] - F0 > ho.cap)
+          atomicOr(ho.err + 1, 1);  // more atoms than the owned region / the neighbours' halo regions hold
+      }
+    }
+    if (cid >= 0) {
+      const unsigned myid = id_in ? (unsigned)id_in[i] : (unsigned)i;
+      const int ci = g.cs_idx(cid);
+      const int s0 = cell_start[ci] - base, s1 = cell_start[ci + 1] - base;
+      int slot = s0;
+      for (int s = s0; s < s1; s++) slot += ids[s] < myid;
+      const size_t d = 3 * (size_t)slot;
+      r_out[d] = x0, r_out[d + 1] = x1, r_out[d + 2] = x2;
+      if (v_in) v_out[d] = w0, v_out[d + 1] = w1, v_out[d + 2] = w2;
+      if (id_out) id_out[slot] = (int)myid;
+      if (halo) {
+        const int gs = slot + base;
+        if (gs >= F0 && gs < F1) {
+          double *p = ho.dst_r_left + 3 * (size_t)(gs - F0);
+          p[0] = x0, p[1] = x1, p[2] = x2;
+        }
+        if (gs >= L0 && gs < L1) {
+          double *p = ho.dst_r_right + 3 * (size_t)(gs - L0);
+          p[0] = x0, p[1] = x1, p[2] = x2;
+        }
       }
     }
   }
-  if (!halo) return;
-  // one system-scope fence per CTA THAT STORED TO A NEIGHBOUR (a few per cent of them), by the thread that counts the
-  // CTA as done: the barrier orders the other threads' peer stores before it (cumulativity); the last CTA publishes the
-  // stamp (the exchange step counter, which the integration kernel has already moved on) in both neighbours' headers
-  sent = __syncthreads_or(sent | (i <= sc2));
-  if (threadIdx.x == 0) {
-    if (sent) __threadfence_system();
-    if (atomicAdd(ho.done, 1) == (int)gridDim.x - 1) {
-      const int stamp = *ho.xstep;
-      ho.hdr_left[0] = F1 - F0, ho.hdr_right[0] = L1 - L0;
-      __threadfence_system();
-      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_left + 1), "r"(stamp) : "memory");
-      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_right + 1), "r"(stamp) : "memory");
-      ho.done[0] = 0;
-    }
-  }
+}
+
+// Slab ranks: the stamps of the two halo messages.  The rank + gather kernel stores the boundary layers into the
+// neighbours' arrays with plain stores and NO fence: a system-scope fence inside that kernel (one per CTA that had stored
+// to a neighbour in round 1, one per warp in a later attempt) kept every fencing warp resident for ~15 us - ncu showed
+// 27 % of the kernel's stall samples on MEMBAR.SYS/ERRBAR and the slab form of the kernel at 57 us against 38 us for
+// the single domain.  The kernel boundary orders those stores before this one-warp kernel, which fences once and
+// publishes (release, system scope) the exchange step counter - already moved on by the integration kernel - as the
+// stamp in both neighbours' headers.
+__global__ void halo_publish_kernel(Geom g, const int *__restrict__ cell_start, HaloOut ho) {
+  if (threadIdx.x != 0) return;
+  const int sc2 = g.sc * g.sc;
+  const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+  const int F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
+  const int stamp = *ho.xstep;
+  ho.hdr_left[0] = F1 - F0, ho.hdr_right[0] = L1 - L0;
+  __threadfence_system();  // ONE release fence for both stamps
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_left + 1), "r"(stamp) : "memory");
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ho.hdr_right + 1), "r"(stamp) : "memory");
 }
 
 // n: atoms before the sort, or an upper bound when the count lives on the device (n_dev)
@@ -623,20 +610,35 @@ __global__ void __launch_bounds__(RG_T) cell_rankgather_kernel(Geom g, int n, co
 // zero_counts: cell_count is left zeroed for the next step's histogram
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev, const HaloOut *halo, bool zero_counts) {
+                            const int *n_dev, const HaloOut *halo, bool zero_counts, int n_hint) {
   if (n <= 0) return ATLJ_OK;
   unsigned *ids = reinterpret_cast<unsigned *>(b.keys);
-  launch_pdl(PDL_SCATTER, cell_scatter_kernel, dim3((n + 255) / 256), dim3(256), 0, st, g, n, n_dev, base, b.cellid, b.rank,
-             b.cell_start, id_in, ids);
+  // threads to launch: n when it is exact; when the count lives on the device, the host's last known count plus a
+  // margin (the kernels loop grid-stride over anything beyond), never more than the upper bound n
+  int nt = n;
+  if (n_dev && n_hint > 0) {
+    const long long want = (long long)n_hint + n_hint / 64 + 4096;
+    if (want < nt) nt = (int)want;
+  }
+  launch_pdl(PDL_SCATTER, cell_scatter_kernel, dim3((nt + 255) / 256), dim3(256), 0, st, g, n, n_dev, base, b.cellid,
+             b.rank, b.cell_start, id_in, ids);
   ATLJ_LAUNCHED();
   HaloOut ho;
   memset(&ho, 0, sizeof(ho));
   if (halo) ho = *halo;
-  int cover = n;  // threads: every source atom, every owned cell (zero_counts), every entry of a halo cell table
+  int cover = nt;  // threads: every source atom, every owned cell (zero_counts), every entry of a halo cell table
   if (zero_counts && g.n_own_cells() > cover) cover = g.n_own_cells();
   if (halo && g.sc * g.sc + 1 > cover) cover = g.sc * g.sc + 1;
-  launch_pdl(PDL_GATHER, cell_rankgather_kernel, dim3((cover + RG_T - 1) / RG_T), dim3(RG_T), 0, st, g, n, n_dev, base, b.cellid,
-             id_in, b.cell_start, b.cell_count, ids, r_in, v_in, r_out, v_out, id_out, zero_counts ? 1 : 0, ho);
+  if (halo) {
+    launch_pdl(PDL_GATHER, cell_rankgather_kernel<true>, dim3((cover + RG_T - 1) / RG_T), dim3(RG_T), 0, st, g, n, n_dev,
+               base, b.cellid, id_in, b.cell_start, b.cell_count, ids, r_in, v_in, r_out, v_out, id_out,
+               zero_counts ? 1 : 0, ho);
+    ATLJ_LAUNCHED();
+    halo_publish_kernel<<<1, 32, 0, st>>>(g, b.cell_start, ho);
+  } else
+    launch_pdl(PDL_GATHER, cell_rankgather_kernel<false>, dim3((cover + RG_T - 1) / RG_T), dim3(RG_T), 0, st, g, n, n_dev,
+               base, b.cellid, id_in, b.cell_start, b.cell_count, ids, r_in, v_in, r_out, v_out, id_out,
+               zero_counts ? 1 : 0, ho);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -223,7 +223,7 @@ struct HaloOut {
   const int *xstep;                  // device counter of exchange steps (already moved on by the integration kernel):
                                      // its value is the stamp published when a layer is complete
   const int *rec_ctr;                // when not null, rec is the base of the records and the row is *rec_ctr
-  int *done;                         // finished CTAs (left 0 by the kernel)
+  int *done;                         // units (atoms + table entries) stored so far (left 0 by the kernel)
   int *n_own;                        // device copy of the owned-atom count after the sort
   long long own_cap;
   double *rec;                       // step record: [11] = owned atoms (may be null)
@@ -232,7 +232,8 @@ struct HaloOut {
 // scatter ids into cells, sort each cell by id, gather r (and v) into the sorted arrays
 int launch_cell_sort_gather(cudaStream_t st, const Geom &g, const CellBufs &b, int n, int base, const int *id_in,
                             const double *r_in, const double *v_in, double *r_out, double *v_out, int *id_out,
-                            const int *n_dev = nullptr, const HaloOut *halo = nullptr, bool zero_counts = false);
+                            const int *n_dev = nullptr, const HaloOut *halo = nullptr, bool zero_counts = false,
+                            int n_hint = 0);
 
 // slab ranks: the halo layers are written by the neighbours; a pair kernel that reaches a boundary x layer acquires
 // their stamps first (null pointers: nothing to wait for)

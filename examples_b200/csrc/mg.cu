@@ -97,6 +97,22 @@ __global__ void __launch_bounds__(256) halo_force_send_kernel(Geom g, const int 
   }
 }
 
+// The migration messages of a step: the integration kernel has stored the leavers (r, v, id) straight into the
+// neighbours' receive buffers with plain stores and counted them; this one-warp kernel, ordered after it by the kernel
+// boundary, writes the counts into the headers, fences ONCE at system scope and publishes the stamps.
+__global__ void mig_publish_kernel(SlabArgs sl, const int *err) {
+  if (threadIdx.x != 0 || err[5]) return;
+  const int stamp = *sl.xstep;  // already moved on by the integration kernel: its value is this step's stamp
+  const bool odd = (stamp - 1) & 1;
+  int *hl = reinterpret_cast<int *>(odd ? sl.to_left1 : sl.to_left0);
+  int *hr = reinterpret_cast<int *>(odd ? sl.to_right1 : sl.to_right0);
+  hl[0] = min(sl.mig_cnt[0], sl.mig_cap), hr[0] = min(sl.mig_cnt[1], sl.mig_cap);
+  sl.mig_cnt[0] = sl.mig_cnt[1] = sl.mig_cnt[2] = 0;
+  __threadfence_system();
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(hl + 1), "r"(stamp) : "memory");
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(hr + 1), "r"(stamp) : "memory");
+}
+
 // consumer side for the pair kernels that cannot wait themselves (first tiled kernel): one thread acquires both stamps
 __global__ void wait_stamp_kernel(const int *hdr_a, const int *hdr_b, const int *xstep, unsigned long long timeout_ns,
                                   int *err) {
@@ -278,6 +294,10 @@ static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, doub
   const int nb = launch_kdk_assign(st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
                                    first_kick, s->cb, s->vf_partials, rec, s->partials, nb_prev, s->p.model, &sl,
                                    tile2_rows(s), &loop);
+  if (nb >= 0) {
+    mig_publish_kernel<<<1, 32, 0, st>>>(sl, s->cb.err);
+    ATLJ_LAUNCHED();
+  }
   Timer::end(s);
   trace_mark(s, st, 1);
   return nb < 0 ? nb : ATLJ_OK;
@@ -335,8 +355,9 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
     if ((rc = launch_pair_tile2(side, a, s->cb.err + 2, 0, 1, true)) < 0) return rc;
     ATLJ_CUDA(cudaEventRecord(s->ev_join, side));
   }
+  // (s->n: the owned count the host saw last, at the end of the previous run; migration changes it by ~1e-4 per step)
   if ((rc = launch_cell_sort_gather(st, s->g, s->cb, nup, 0, s->id[cur], s->r[cur], s->v[cur], s->r[alt], s->v[alt],
-                                    s->id[alt], m.cnt_dev, &ho, true)))
+                                    s->id[alt], m.cnt_dev, &ho, true, (int)s->n)))
     return rc;
   Timer::end(s);
   trace_mark(s, st, 4);
