@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(Geom g, int n, const 
 // stamp in both neighbours' headers.
 constexpr int RG_T = 256;
 template <bool HALO>
-__global__ void __launch_bounds__(RG_T, 8) cell_rankgather_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
+__global__ void __launch_bounds__(RG_T, HALO ? 6 : 8) cell_rankgather_kernel(Geom g, int n, const int *__restrict__ n_dev, int base,
                                                                 const int *__restrict__ cellid,
                                                                 const int *__restrict__ id_in,
                                                                 const int *__restrict__ cell_start,
@@ -545,9 +545,11 @@ __global__ void __launch_bounds__(RG_T, 8) cell_rankgather_kernel(Geom g, int n,
       x0 = r_in[3 * (size_t)i], x1 = r_in[3 * (size_t)i + 1], x2 = r_in[3 * (size_t)i + 2];
       if (v_in) w0 = v_in[3 * (size_t)i], w1 = v_in[3 * (size_t)i + 1], w2 = v_in[3 * (size_t)i + 2];
     }
-    if (halo) {
-      // (after the atom's loads have been issued: these four values gate nothing but the peer stores further down)
-      const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+    const int *rowF = cell_start + (size_t)g.h * (sc2 + 1), *rowL = cell_start + (size_t)(g.h + g.nx_own - 1) * (sc2 + 1);
+    // slab: only atoms of the first / last owned layer (6 % of them: one comparison on the cell id tells) and the
+    // threads that copy the cell tables need the extent of those layers in the sorted arrays
+    const bool inF = halo && cid >= 0 && cid < (g.h + 1) * sc2, inL = halo && cid >= (g.h + g.nx_own - 1) * sc2;
+    if (halo && (inF || inL || i <= sc2)) {
       F0 = rowF[0], F1 = min(rowF[sc2], F0 + ho.cap), L0 = rowL[0], L1 = min(rowL[sc2], L0 + ho.cap);
       if (i <= sc2) {  // the two layers' cell tables, rebased (entry sc2 = end sentinel)
         ho.dst_cs_left[i] = ho.base_left + min(rowF[i] - F0, F1 - F0);
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(RG_T, 8) cell_rankgather_kernel(Geom g, int n,
       r_out[d] = x0, r_out[d + 1] = x1, r_out[d + 2] = x2;
       if (v_in) v_out[d] = w0, v_out[d + 1] = w1, v_out[d + 2] = w2;
       if (id_out) id_out[slot] = (int)myid;
-      if (halo) {
+      if (inF || inL) {
         const int gs = slot + base;
         if (gs >= F0 && gs < F1) {
           double *p = ho.dst_r_left + 3 * (size_t)(gs - F0);
