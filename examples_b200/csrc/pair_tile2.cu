@@ -23,13 +23,7 @@
 
 namespace atlj {
 
-// A/B switches (make variant TAG=... XFLAGS=-D...): the adopted forms are on by default
-#if !defined(ATLJ_U_ADV2) && !defined(ATLJ_U_NO_ADV2)
-#define ATLJ_U_ADV2  // mask walk with bfind + sentinel words, pair count from the sign of s - rc2s (0.670 -> 0.659 ms)
-#endif
-#if !defined(ATLJ_U_STG2) && !defined(ATLJ_U_NO_STG2)
-#define ATLJ_U_STG2  // staging: centre of the region from shared memory, no minimum image away from the periodic edge,
-#endif               // fp16 bound from the region's geometry (0.659 -> 0.653 ms)
+// Tunables (A/B builds: make variant TAG=... XFLAGS=-DATLJ_U_...; measured values in profiles/r*_pair_kernel_history.md)
 #ifndef ATLJ_U_NT
 #define ATLJ_U_NT 128
 #endif
@@ -51,11 +45,7 @@ constexpr int U_NWORDS = 3 * U_WW;
 // the unused slot of a phase-2 iteration reads: its separation (3e300) is classified out of range by the same tests as
 // a real pair and contributes exactly 0 (sr^6 underflows), so a dead slot needs no instructions of its own
 constexpr int U_STR = U_CAP + 2;
-#ifdef ATLJ_U_ADV2
 constexpr unsigned U_YOFF = 8u * 31u;  // mask words carry the address of the candidate of bit 0 (walked with bfind)
-#else
-constexpr unsigned U_YOFF = 0u;        // ... of the candidate of bit 31 (walked with a leading-zero count)
-#endif
 
 // Kernel modes.  T2_FORCE: forces + totals.  T2_FORCE_SAVE: the same launch with a mask buffer - every atom's mask
 // words (the filter's survivors) are kept in global memory.  T2_HESS: the hessian sum (md_lj_module.py:176-191) from those mask words - no
@@ -244,10 +234,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   __shared__ int rowcell0[U_K];
   __shared__ int cumloc[U_MAXC], sAloc[U_MAXC], sBloc[U_MAXC];  // cells z0 .. of the chunk: atoms before, row starts
   __shared__ int wsum[U_NT / 32];
-  __shared__ unsigned s_q2max;
-#ifdef ATLJ_U_STG2
   __shared__ double s_ctr[3];  // centre of the staged region (the compiler re-derived it for every staged entry)
-#endif
   __shared__ int s_item, s_halo;
 
   pdl_wait();  // launched while the sort drains (common.cuh)
@@ -288,7 +275,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
   for (;;) {
     // ---- next work item ----------------------------------------------------------------------------------------
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(work_counter, 1), s_q2max = 0u;
+    if (tid == 0) s_item = atomicAdd(work_counter, 1);
     const int halo_ok = s_halo;  // read between the two barriers: thread 0 only writes it after the second one
     __syncthreads();
     const int item = s_item;
@@ -356,14 +343,12 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
     }
     const double ctrx = ((lx - g.h + g.x_lo) + 0.5) * sci - 0.5;
     const double ctry = (y0 + (two ? 1.0 : 0.5)) * sci - 0.5;
-#ifdef ATLJ_U_STG2
     // the staged x / y range crosses the periodic boundary only for the outermost layers / rows: elsewhere the minimum
     // image of a centred coordinate is the coordinate itself (|x - ctrx| <= 1.5 cells, |y - ctry| <= 2 cells) and
     // x -= rint(x) is skipped - bit-identical, rint is exactly 0 there
     const int glx = lx - g.h + g.x_lo;
     const bool wrapxy = glx == 0 || glx == sc - 1 || y0 == 0 || y0 + 2 >= sc;
     if (tid == 0) s_ctr[0] = ctrx, s_ctr[1] = ctry;  // (read after the barriers of the chunk's entry table)
-#endif
 
     // sums of sr^6, sr^12, sr^8, sr^14 over this thread's pairs; cut, vir, lap follow at the end of the item
     double a6 = 0.0, a12 = 0.0, a8 = 0.0, a14 = 0.0, hs = 0.0;
@@ -435,9 +420,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         ncz = max(1, min(ncz - 1, (int)((long long)ncz * U_CAP / total)));
       }
       g1 = min(g1, cumloc[ncz]);  // ncz may have been cut to fit U_CAP
-#ifdef ATLJ_U_STG2
       if (tid == 0) s_ctr[2] = (z + 0.5 * ncz) * sci - 0.5;  // (the barrier of the window check follows)
-#endif
       const int ni = g1 - g0;
       // atom il of the chunk -> (cell myc of the chunk, row, global index i, offset in its cell row)
       auto locate = [&](int il, int &myc, int &i, int &k0, int &off) {
@@ -516,8 +499,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
       // ---- stage the candidates: half a warp per (cell,row) entry, two entries in flight ------------------------------
       {
         const int hw = tid >> 4, hl = tid & 15;
-        float q2m = 0.f;
-#ifdef ATLJ_U_STG2
         const double ctrz = s_ctr[2];
         auto put = [&](int s, double x, double y, double zz, double wz) {
           x -= s_ctr[0], y -= s_ctr[1], zz = (zz + wz) - ctrz;
@@ -533,22 +514,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             d[0] = __float2half_rn((float)x), d[2] = __float2half_rn((float)y), d[4] = __float2half_rn((float)zz);
           }
         };
-#else
-        const double ctrz = (z + 0.5 * ncz) * sci - 0.5;
-        auto put = [&](int s, double x, double y, double zz, double wz) {
-          x -= ctrx, y -= ctry, zz = (zz + wz) - ctrz;
-          x -= rint(x);
-          y -= rint(y);
-          x *= box, y *= box, zz *= box;
-          ux[s] = x, uy[s] = y, uz[s] = zz;
-          if (MODE != T2_HESS) {
-            const float fx = (float)x, fy = (float)y, fz = (float)zz;
-            __half *d = reinterpret_cast<__half *>(hp + (s >> 1)) + (s & 1);
-            d[0] = __float2half_rn(fx), d[2] = __float2half_rn(fy), d[4] = __float2half_rn(fz);
-            q2m = fmaxf(q2m, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));  // largest coordinate of the chunk
-          }
-        };
-#endif
         auto putf = [&](int s, size_t j) {  // T2_HESS: the candidate's force next to its position
           gx[s] = a.fin[3 * j], gy[s] = a.fin[3 * j + 1], gz[s] = a.fin[3 * j + 2];
         };
@@ -591,14 +556,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             }
           }
         }
-#ifndef ATLJ_U_STG2
-        if (MODE != T2_HESS) {
-          unsigned qb = __reduce_max_sync(FULL, __float_as_uint(q2m));
-          if (lane == 0) atomicMax(&s_q2max, qb);
-        }
-#else
-        (void)q2m;
-#endif
       }
       __syncthreads();
       // Filter threshold.  The filter evaluates d^2 = dx^2 + dy^2 + dz^2 in fp16 (unit roundoff u = 2^-11) on fp16 copies
@@ -607,13 +564,9 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
       // 2 sqrt(3) R ec + 3 ec^2, and the three fp16 operations that form it by at most 6 u R^2 more.  With 10 % on
       // top and rounded up to fp16, no pair with d^2 < R^2 can fail the test; what passes in excess (about 3 % at
       // Q = 11 sigma) is rejected by the fp64 evaluation.
-#ifdef ATLJ_U_STG2
       // Q from the geometry of the staged region instead of a running maximum over the staged atoms: x within 1.5 cells of
       // the centre, y within 2, z within ncz / 2 + 1 (one halo plane at each end)
       const float Qm = (float)(box * sci) * fmaxf(2.0f, 0.5f * (float)ncz + 1.0f) * 1.001f;
-#else
-      const float Qm = __uint_as_float(s_q2max) * 1.001f;
-#endif
       float thr;
       {
         const float u = 4.8828125e-4f, R = sqrtf((float)rc2s) * 1.0001f;
@@ -635,11 +588,7 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         const double uix = ux[self], uiy = uy[self], uiz = uz[self];
         // ---- phase 1: packed fp16 filter -> left-aligned mask words --------------------------------------------
         // (mask word, shared-memory address of ux[c] for the candidate c of bit 31); bit p <-> candidate c + 31 - p
-#ifdef ATLJ_U_ADV2
         uint2 mw[U_NWORDS + 2];  // closed by two zero words: the walk needs no end test of its own
-#else
-        uint2 mw[U_NWORDS];
-#endif
         int nw = 0;
         double fix = 0.0, fiy = 0.0, fiz = 0.0;  // T2_HESS: this atom's force
         if constexpr (MODE == T2_HESS) {
@@ -727,13 +676,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         int defer[4];
         int ww = 0;
         uint2 cur = make_uint2(0u, 0u), nxt = make_uint2(0u, 0u);  // (mask, address of the candidate a leading-zero count of 0 stands for)
-#ifdef ATLJ_U_ADV2
         mw[nw] = make_uint2(0u, 0u), mw[nw + 1] = make_uint2(0u, 0u);
         cur = mw[0], nxt = mw[1];
-#else
-        if (nw > 0) cur = mw[0];
-        if (nw > 1) nxt = mw[1];
-#endif
 #ifdef ATLJ_TILE2_STATS
         {
           int pc = 0, emp = 0, half = 0;
@@ -752,26 +696,16 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         int iters = 0;
 #endif
         // (the loop ends with the last bit of the last word: testing ww < nw alone costs every warp one dead iteration)
-#ifdef ATLJ_U_ADV2
         while ((cur.x | nxt.x) != 0u) {  // only words with survivors are stored: nxt.x == 0 <=> no further word
-#else
-        while (cur.x != 0u || ww + 1 < nw) {
-#endif
 #ifdef ATLJ_TILE2_STATS
           iters++;
 #endif
           const bool adv = cur.x == 0u;
           if (adv) ww++;
-#ifdef ATLJ_U_ADV2
           if (adv) cur = nxt;
           nxt = mw[ww + 1];  // re-read every iteration (the same word unless the walk has just moved on): no selects
-#else
-          const uint2 ld = mw[min(ww + 1, U_NWORDS - 1)];
-          if (adv) cur = nxt;
-#endif
           unsigned cm = cur.x;
           bool live0 = cm != 0u;
-#ifdef ATLJ_U_ADV2
           // cur.y is the address of the candidate of bit 0 + 8 * 31: the candidate of bit p sits at cur.y - 8 p, so the
           // position of the highest set bit is used as it comes (bfind; -1 for an empty word, whose shift clamps to 0)
           unsigned p0, p1, b0m, b1m;
@@ -785,17 +719,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           cur.x = cm;
           const unsigned a0 = live0 ? cur.y - 8u * p0 : dummy_addr;
           const unsigned a1 = live1 ? cur.y - 8u * p1 : dummy_addr;
-#else
-          const int z0 = __clz(cm | 1u);
-          cm &= ~(0x80000000u >> z0);
-          bool live1 = cm != 0u;
-          const int z1 = __clz(cm | 1u);
-          cm &= ~(0x80000000u >> z1);
-          cur.x = cm;
-          // a dead slot reads the dummy candidate: out of range by the same tests as a real pair
-          const unsigned a0 = live0 ? cur.y + 8u * (unsigned)z0 : dummy_addr;
-          const unsigned a1 = live1 ? cur.y + 8u * (unsigned)z1 : dummy_addr;
-#endif
           const double dx0 = uix - lds_f64(a0), dy0 = uiy - lds_f64(a0 + 8u * U_STR),
                        dz0 = uiz - lds_f64(a0 + 16u * U_STR);
           const double dx1 = uix - lds_f64(a1), dy1 = uiy - lds_f64(a1 + 8u * U_STR),
@@ -808,23 +731,12 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
           // and leaves the hot path: such pairs are set aside and decided with the reference's exact operation sequence.
           const bool b0 = (((unsigned)e0 << 1) <= band2) | (__double2hiint(s0) <= sovr_hi);
           const bool b1 = (((unsigned)e1 << 1) <= band2) | (__double2hiint(s1) <= sovr_hi);
-#ifdef ATLJ_U_ADV2
           // (a deferred pair is switched off in the rare branch below: the hot path selects on the sign alone)
-#else
-          const bool in0 = (e0 < 0) & !b0, in1 = (e1 < 0) & !b1;
-#endif
-#ifdef ATLJ_U_ADV2
           // counted by the sign of s - rc2s alone (one add per slot); a deferred pair is taken back below
           npf += ((unsigned)e0 >> 31) + ((unsigned)e1 >> 31);
-#else
-          if (in0) npf++;
-          if (in1) npf++;
-#endif
           if (b0 | b1) {
-#ifdef ATLJ_U_ADV2
             if (b0) npf -= (unsigned)e0 >> 31, s0 = 3e300;
             if (b1) npf -= (unsigned)e1 >> 31, s1 = 3e300;
-#endif
             if (b0) defer[nd++] = (int)((a0 - ux_s) >> 3);
             if (b1) defer[nd++] = (int)((a1 - ux_s) >> 3);
             if (nd >= 3) {
@@ -838,13 +750,8 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             }
           }
           // out of range: s becomes ~1e300 (only the high word needs replacing), whose sr^6 underflows to exactly 0
-#ifdef ATLJ_U_ADV2
           s0 = __hiloint2double(e0 < 0 ? __double2hiint(s0) : 0x7e37e43c, __double2loint(s0));
           s1 = __hiloint2double(e1 < 0 ? __double2hiint(s1) : 0x7e37e43c, __double2loint(s1));
-#else
-          s0 = __hiloint2double(in0 ? __double2hiint(s0) : 0x7e37e43c, __double2loint(s0));
-          s1 = __hiloint2double(in1 ? __double2hiint(s1) : 0x7e37e43c, __double2loint(s1));
-#endif
           if constexpr (MODE == T2_HESS) {
             const double ex0 = fix - lds_f64(a0 + 24u * U_STR), ey0 = fiy - lds_f64(a0 + 32u * U_STR),
                          ez0 = fiz - lds_f64(a0 + 40u * U_STR);
@@ -856,9 +763,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
             U_ACCUM(dx0, dy0, dz0, s0);
             U_ACCUM(dx1, dy1, dz1, s1);
           }
-#ifndef ATLJ_U_ADV2
-          if (adv) nxt = (ww + 1 < nw) ? ld : make_uint2(0u, 0u);
-#endif
         }
 #ifdef ATLJ_TILE2_STATS
         {
@@ -888,7 +792,6 @@ __global__ void __launch_bounds__(U_NT, MODE == T2_HESS ? 3 : U_CTAS)
         }
       }
       __syncthreads();
-      if (tid == 0) s_q2max = 0u;
       g0 = g1;
       // the cell that holds the next chunk's first atom (skipping empty cells): cumloc[k] = cumf(z + k), k < U_MAXC,
       // is still this chunk's table (it is rewritten after the barrier at the top of the chunk loop)
