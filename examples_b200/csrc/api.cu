@@ -561,6 +561,7 @@ static int nve_fused_step(atlj_sim *s, cudaStream_t st, cudaStream_t side, doubl
   loop.tab0 = tile2 ? s->tile_tab : nullptr;
   loop.counts_zeroed = true;
   loop.no_assign = !s->use_cells;
+  loop.tail_in_scan = s->use_cells;  // the scan launch below finishes the record of the step that just ended
   Timer::begin(s, 2);
   const int nvf = launch_kdk_assign(st, s->g, n, s->r[cur], s->v[cur], s->f, 0.5 * dt, dt, p.box, first_kick, s->cb,
                                     s->vf_partials, rec, s->partials, nb_prev, p.model, nullptr,
@@ -584,7 +585,12 @@ static int nve_fused_step(atlj_sim *s, cudaStream_t st, cudaStream_t side, doubl
     return ATLJ_OK;
   }
   Timer::begin(s, 1);
-  if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
+  RecTail tail;
+  if (first_kick) {
+    tail.rows = s->vf_partials, tail.nrows = nvf, tail.rec = rec, tail.step_ctr = loop.step_ctr, tail.model = p.model;
+    tail.has_pair = 1, tail.err = s->cb.err;
+  }
+  if ((rc = launch_cell_scan(st, s->g, s->cb, 0, first_kick ? &tail : nullptr))) return rc;
   PairArgs a;
   a.r = s->r[alt], a.fin = nullptr, a.cell_start = s->cb.cell_start, a.cell_count = s->cb.cell_count;
   a.f = s->f, a.partials = s->partials, a.tile_tab = s->tile_tab, a.natoms = (int)s->n, a.g = s->g, a.p = p;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
                                                         const double *__restrict__ pair_partials, int pair_rows,
                                                         int model, SlabArgs sl, const int *__restrict__ pair_rows_dev,
                                                         int *__restrict__ step_ctr, int *__restrict__ tab0,
-                                                        int no_assign) {
+                                                        int no_assign, int tail_in_scan) {
   pdl_wait();  // (a no-op by default: this kernel is not launched programmatically, see common.cuh)
   pdl_launch_dependents();
   if (pair_rows_dev) pair_rows = min(pair_rows, *pair_rows_dev);
@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(IT, ATLJ_KDK_CTAS) kdk_assign_kernel(Geom g, i
   // system-scope fences inside it, one per leaving atom's thread plus two in the tile that completed the boundary
   // layers, kept those CTAs waiting for ~15 us each: 70 us on a slab against 63.5 us for the single domain)
   if (slab && threadIdx.x == 0) *sl.xstep = xstep + 1;
+  if (tail_in_scan) {  // level 2, the pair kernel's work counter and the step counter: the scan launch (RecTail)
+    if (threadIdx.x == 0) err[4] = 0;
+    return;
+  }
   if (first_kick) {
     double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
@@ -330,7 +334,7 @@ int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *
 #define ATLJ_KDK(RCP, SLAB)                                                                                          \
   launch_pdl(PDL_KDK, kdk_assign_kernel<RCP, SLAB>, dim3(nb), dim3(IT), 0, st, g, n, r, v, f, half_dt, dt, box, inv_box,        \
              first_kick ? 1 : 0, b.cellid, b.rank, b.cell_count, b.err, vf_partials, rec_vf, pair_partials, pair_rows,  \
-             model, sl, pair_rows_dev, step_ctr, tab0, no_assign)
+             model, sl, pair_rows_dev, step_ctr, tab0, no_assign, (loop && loop->tail_in_scan && first_kick) ? 1 : 0)
   if (inv_box != 0.0) {
     if (slab)
       ATLJ_KDK(true, true);
@@ -388,12 +392,49 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *smem /*[SCAN_T/3
 constexpr int SCAN_STATE_CTR = 4095;  // CellBufs::block_sums holds 4096 64-bit words
 __global__ void __launch_bounds__(SCAN_T) scan_lookback_kernel(const int *__restrict__ cnt, int n, int base_off,
                                                                 int *__restrict__ start, int sc2, int h,
-                                                                unsigned long long *__restrict__ state) {
+                                                                unsigned long long *__restrict__ state, RecTail tail) {
   __shared__ int sm[SCAN_T / 32];
   __shared__ int total;
   __shared__ int s_before;
   pdl_wait();
   pdl_launch_dependents();
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if ((int)blockIdx.x == ntiles) {
+    // the extra CTA: second level of the step record's reduction (RecTail), same order of summation as the last CTA
+    // of the integration kernel used (IT threads stride over the rows, xor-shuffles, warps in index order)
+    constexpr int ROW = 12;
+    __shared__ double fin[IT / 32][9];
+    double *rec = tail.rec + (tail.step_ctr ? (size_t)ATLJ_NREC * (size_t)*tail.step_ctr : 0);
+    double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x < IT) {
+      for (int b = threadIdx.x; b < tail.nrows; b += IT) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[k] += __ldcg(tail.rows + ROW * (size_t)b + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) fin[threadIdx.x >> 5][k] = t[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 9; k++) {
+        double a = 0.0;
+        for (int w = 0; w < IT / 32; w++) a += fin[w][k];
+        t[k] = a;
+      }
+      rec[4] = t[0], rec[5] = t[1];
+      if (tail.has_pair) finalize_totals(t + 2, tail.model, false, rec);
+      tail.err[2] = 0;  // work counter of the tiled pair kernel
+      if (tail.step_ctr) *tail.step_ctr += 1;
+    }
+    return;
+  }
   const int tile = blockIdx.x;
   const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
@@ -454,16 +495,16 @@ __global__ void __launch_bounds__(SCAN_T) scan_lookback_kernel(const int *__rest
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(state + SCAN_STATE_CTR, 1ull) == (unsigned long long)gridDim.x - 1ull) s_before = -1;
+    if (atomicAdd(state + SCAN_STATE_CTR, 1ull) == (unsigned long long)ntiles - 1ull) s_before = -1;
   }
   __syncthreads();
   if (s_before == -1) {
-    for (int t = threadIdx.x; t < (int)gridDim.x; t += SCAN_T) state[t] = 0ull;
+    for (int t = threadIdx.x; t < ntiles; t += SCAN_T) state[t] = 0ull;
     if (threadIdx.x == 0) state[SCAN_STATE_CTR] = 0ull;
   }
 }
 
-int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base) {
+int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base, const RecTail *tail) {
   int n = g.n_own_cells();
   int first = g.first_own_cell();
   int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -471,8 +512,11 @@ int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base
     set_error("cell grid too large for the scan (%d cells)", n);
     return ATLJ_ERR_ARG;
   }
-  launch_pdl(PDL_SCAN, scan_lookback_kernel, dim3(ntiles), dim3(SCAN_T), 0, st, b.cell_count + first, n, base, b.cell_start,
-             g.sc * g.sc, g.h, reinterpret_cast<unsigned long long *>(b.block_sums));
+  RecTail rt;
+  if (tail) rt = *tail;
+  launch_pdl(PDL_SCAN, scan_lookback_kernel, dim3(ntiles + (rt.nrows > 0 ? 1 : 0)), dim3(SCAN_T), 0, st,
+             b.cell_count + first, n, base, b.cell_start, g.sc * g.sc, g.h,
+             reinterpret_cast<unsigned long long *>(b.block_sums), rt);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

@@ -206,13 +206,26 @@ struct KdkLoop {
                        // pair kernel does it)
   bool counts_zeroed;  // cell_count was left zeroed by the previous step's launch_cell_sort_gather(zero_counts)
   bool no_assign = false;  // all-pairs route (sc < 4): kick + sums + kick + drift + wrap only, no cell assignment
+  bool tail_in_scan = false;  // the record's final fixed-order sum is left to the scan launch that follows (RecTail)
+};
+// The second level of the step record's reduction (the per-CTA rows of the integration kernel -> the record), done by
+// one extra CTA of the scan launch that follows it: in the integration kernel's last CTA it was 8 us with one SM
+// working; beside the scan it costs nothing.  Same fixed order of summation, so the records keep their bits.
+struct RecTail {
+  const double *rows = nullptr;  // [nrows][12] rows the integration kernel's CTAs left behind
+  int nrows = 0;                 // 0: no tail
+  double *rec = nullptr;         // the record, or the base of the records when step_ctr is given
+  int *step_ctr = nullptr;       // device counter of replayed steps: row of the record; moved on by the tail
+  int model = 0;
+  int has_pair = 0;              // the rows carry the pair kernel's totals as well
+  int *err = nullptr;            // device flags: [2] = work counter of the tiled pair kernel, reset here
 };
 int launch_kdk_assign(cudaStream_t st, const Geom &g, int n, double *r, double *v, const double *f, double half_dt,
                       double dt, double box, bool first_kick, const CellBufs &b, double *vf_partials, double *rec_vf,
                       const double *pair_partials, int pair_rows, int model, const SlabArgs *slab = nullptr,
                       const int *pair_rows_dev = nullptr, const KdkLoop *loop = nullptr);
 // exclusive scan of cell_count over the OWNED cells -> cell_start (offset by base)
-int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base);
+int launch_cell_scan(cudaStream_t st, const Geom &g, const CellBufs &b, int base, const RecTail *tail = nullptr);
 // slab ranks: where the sort + gather kernel sends the first / last owned layer (the neighbours' halo regions, mg.cu)
 struct HaloOut {
   double *dst_r_left, *dst_r_right;  // the neighbours' position arrays at their halo regions (peer memory)

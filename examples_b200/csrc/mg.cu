@@ -289,14 +289,20 @@ static int phase1(atlj_sim *s, cudaStream_t st, double dt, bool first_kick, doub
   loop.step_ctr = replay ? m.cnt_dev + 11 : nullptr;
   loop.tab0 = sim_tile2(s) ? s->tile_tab : nullptr;
   loop.counts_zeroed = counts_zeroed;
+  loop.tail_in_scan = first_kick;  // phase 2's scan launch finishes the record of the step that just ended
   trace_mark(s, st, 0);
   Timer::begin(s, 2);
   const int nb = launch_kdk_assign(st, s->g, (int)m.own_cap, s->r[s->cur], s->v[s->cur], s->f, 0.5 * dt, dt, s->p.box,
                                    first_kick, s->cb, s->vf_partials, rec, s->partials, nb_prev, s->p.model, &sl,
                                    tile2_rows(s), &loop);
+  m.tail = RecTail();
   if (nb >= 0) {
     mig_publish_kernel<<<1, 32, 0, st>>>(sl, s->cb.err);
     ATLJ_LAUNCHED();
+    if (first_kick) {
+      m.tail.rows = s->vf_partials, m.tail.nrows = nb, m.tail.rec = rec, m.tail.step_ctr = loop.step_ctr;
+      m.tail.model = s->p.model, m.tail.has_pair = 1, m.tail.err = s->cb.err;
+    }
   }
   Timer::end(s);
   trace_mark(s, st, 1);
@@ -345,7 +351,8 @@ static int phase2(atlj_sim *s, cudaStream_t st, cudaStream_t side, double *rec, 
   ho.done = m.cnt_dev + 8, ho.n_own = m.cnt_dev + 1;
   ho.own_cap = (long long)m.own_cap, ho.rec = rec, ho.err = s->cb.err;
   Timer::begin(s, 1);
-  if ((rc = launch_cell_scan(st, s->g, s->cb, 0))) return rc;
+  if ((rc = launch_cell_scan(st, s->g, s->cb, 0, m.tail.nrows > 0 ? &m.tail : nullptr))) return rc;
+  m.tail = RecTail();
   trace_mark(s, st, 3);
   const bool fork = side != nullptr && sim_tile2(s);
   if (fork) {  // the item table needs cell_start only: beside the sort + gather

@@ -25,6 +25,7 @@ struct MgState {
                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // to be closed
   int n_ipc_mapped = 0;
   bool sorted = false;      // the arrays are in cell order and cell_start describes them (false after an upload)
+  atlj::RecTail tail;       // phase 1 -> phase 2: the record the scan launch has to finish (nrows = 0: none)
   long long step = 0;                                   // exchange counter: parity selects the buffer, step+1 = stamp
   int *cnt_dev = nullptr;   // [0] atoms held after the arrivals were appended, [1] owned atoms (after the sort),
                             // [4..6] migration slot counters + CTAs done, [8], [9] halo pack CTAs done
