@@ -535,7 +535,9 @@ def run_ours(args, rank, world, local_rank):
                             "launching stream (%.4f ms/step; the headline pass replays the step as a CUDA graph)"
                             % (args.steps, ms_events / args.steps)}
     ach_h = HBM_BYTES_NON_PAIR * n_rank / (other_ms * 1e-3) / 1e9 if other_ms > 0 else 0.0
-    roofline_hbm = {"kernel": "cell build (5 kernels) + kick_drift + kick_sums", "bound": "hbm", "achieved": ach_h,
+    roofline_hbm = {"kernel": "kdk_assign (integration + cell assignment) + scan + scatter + rank/gather: the step "
+                              "without the pair kernel and its item table",
+                    "bound": "hbm", "achieved": ach_h,
                     "peak": hbm_peak, "unit": "GB/s", "frac": ach_h / hbm_peak, "traffic": None,
                     "peak_source": hbm_src, "ms_per_step": other_ms, "bytes_per_step": HBM_BYTES_NON_PAIR * n_rank}
 
