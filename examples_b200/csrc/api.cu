@@ -242,9 +242,15 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       nb = launch_pair_tile(s->st, a, false);
     Timer::end(s);
     if (nb < 0) return nb;
-    if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2, nullptr, 0,
-                              tile2 ? s->cb.err + 6 : nullptr)))
+    s->fin = FinTail();
+    if (s->defer_fin && !with_hessian) {  // the caller's next kernel finishes the totals (FinTail, pair_math.cuh)
+      s->fin.partials = s->partials, s->fin.nb = nb, s->fin.model = p.model, s->fin.rec = rec_dev;
+      s->fin.reset_counter = s->cb.err + 2, s->fin.rows_dev = tile2 ? s->cb.err + 6 : nullptr;
+    } else if ((rc = launch_finalize(s->st, s->partials, nb, p.model, false, rec_dev, s->cb.err + 2, nullptr, 0,
+                                     tile2 ? s->cb.err + 6 : nullptr))) {
       return rc;
+    }
+    s->defer_fin = false;
     if (with_hessian) {
       a.fin = s->f;
       a.f = nullptr;
@@ -290,6 +296,7 @@ int sim_force(atlj_sim *s, double strain, bool with_hessian, double *rec_dev, bo
       if ((rc = launch_finalize(s->st, s->partials, nb, p.model, true, rec_dev))) return rc;
     }
   }
+  s->defer_fin = false;
   s->forces_valid = true;
   return ATLJ_OK;
 }

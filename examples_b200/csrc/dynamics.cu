@@ -216,9 +216,15 @@ __global__ void __launch_bounds__(IT) sllod_ab1_kernel(int n, double *__restrict
 // sums for b2: sum f.v, sum f^2, sum v^2
 __global__ void __launch_bounds__(IT) sllod_fv_sums_kernel(long long n3, const double *__restrict__ v,
                                                            const double *__restrict__ f,
-                                                           double *__restrict__ partials) {
+                                                           double *__restrict__ partials, FinTail fin) {
+  // the extra CTA (fin.nb > 0): the pair totals of the force evaluation that has just ended
+  const int nblk = (int)gridDim.x - (fin.nb > 0 ? 1 : 0);
+  if ((int)blockIdx.x == nblk) {
+    finalize_rows_block<IT>(fin);
+    return;
+  }
   double s[3] = {0.0, 0.0, 0.0};
-  for (long long t = (long long)blockIdx.x * IT + threadIdx.x; t < n3; t += (long long)gridDim.x * IT) {
+  for (long long t = (long long)blockIdx.x * IT + threadIdx.x; t < n3; t += (long long)nblk * IT) {
     const double vv = v[t], ff = f[t];
     s[0] += ff * vv;
     s[1] += ff * ff;
@@ -291,9 +297,13 @@ static int baoab_run(atlj_sim *s, double dt, double decay, double amp, const dou
                                                    seed, (unsigned)(s->step_count + k), nullptr);
     ATLJ_LAUNCHED();
     Timer::end(s);
+    s->defer_fin = true;  // the half kick below finishes the force totals in an extra CTA (FinTail)
     if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
     Timer::begin(s, 2);
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, t, s->partials, rec + 4, s->cb.err + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, t, s->vf_partials, rec + 4, s->cb.err + 4, nullptr, nullptr,
+                               s->fin.nb > 0 ? &s->fin : nullptr)))
+      return rc;
+    s->fin = FinTail();
     Timer::end(s);
   }
   s->step_count += nsteps;
@@ -565,11 +575,13 @@ int atlj_sim_run_sllod(atlj_sim *s, double dt, double strain_rate, double *strai
     sllod_ab1_kernel<<<nb, IT, 0, s->st>>>(n, s->r[s->cur], s->v[s->cur], t, x, st, bd, rowsA, nb, 0, rowsB);
     ATLJ_LAUNCHED();
     Timer::end(s);
+    s->defer_fin = true;  // the sums kernel below finishes the force totals in an extra CTA (FinTail)
     if ((rc = sim_force(s, st, false, rec, false))) return rc;
     Timer::begin(s, 2);
     // b2(dt): sums of f.v, f^2, v^2 -> rowsA; the kernel that applies b2 forms its coefficients from them
-    sllod_fv_sums_kernel<<<nb3, IT, 0, s->st>>>(n3, s->v[s->cur], s->f, rowsA);
+    sllod_fv_sums_kernel<<<nb3 + (s->fin.nb > 0 ? 1 : 0), IT, 0, s->st>>>(n3, s->v[s->cur], s->f, rowsA, s->fin);
     ATLJ_LAUNCHED();
+    s->fin = FinTail();
     sllod_b2_kernel<<<nb, IT, 0, s->st>>>(n, s->v[s->cur], s->f, rowsA, nb3, dt, rowsB, sumf);
     ATLJ_LAUNCHED();
     // b1(dt/2) then a(dt/2); g from rowsB, the sums of the velocities it leaves behind -> rowsA

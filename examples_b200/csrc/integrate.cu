@@ -9,6 +9,7 @@
 // Global sums are two-stage (per-CTA partials, then one CTA in fixed order) => run-to-run deterministic.
 #include "common.cuh"
 #include "integrate.cuh"
+#include "pair_math.cuh"
 
 namespace atlj {
 
@@ -39,13 +40,19 @@ __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__r
                                                        const double *__restrict__ f, double half_dt,
                                                        double *__restrict__ partials, const int *__restrict__ n_dev,
                                                        int *__restrict__ done, double *__restrict__ out2,
-                                                       int *__restrict__ step_ctr) {
+                                                       int *__restrict__ step_ctr, FinTail fin) {
+  // the extra CTA (fin.nb > 0): the pair totals of the force evaluation that has just ended
+  const int nblk = (int)gridDim.x - (fin.nb > 0 ? 1 : 0);
+  if ((int)blockIdx.x == nblk) {
+    finalize_rows_block<IT>(fin);
+    return;
+  }
   if (n_dev) n3 = min(n3, 3ll * *n_dev);
   // replayed launches: out2 is relative to the record of step *step_ctr; this kernel ends the step and moves the
   // counter on (its last CTA, after every CTA has read it)
   if (step_ctr) out2 += (size_t)ATLJ_NREC * (size_t)*step_ctr;
   long long t = (long long)blockIdx.x * IT + threadIdx.x;
-  long long stride = (long long)gridDim.x * IT;
+  long long stride = (long long)nblk * IT;
   double s[2] = {0.0, 0.0};
   for (; t < n3; t += stride) {
     double ff = f[t];
@@ -58,12 +65,12 @@ __global__ void __launch_bounds__(IT) kick_sums_kernel(long long n3, double *__r
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == nblk - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   double a[2] = {0.0, 0.0};
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += IT) {
+  for (int b = threadIdx.x; b < nblk; b += IT) {
     a[0] += __ldcg(partials + 4 * (size_t)b);
     a[1] += __ldcg(partials + 4 * (size_t)b + 1);
   }
@@ -112,9 +119,11 @@ int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const
 }
 
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
-                     double *out2, int *done, const int *n_dev, int *step_ctr) {
+                     double *out2, int *done, const int *n_dev, int *step_ctr, const FinTail *fin) {
   int nb = integ_blocks(n3);
-  kick_sums_kernel<<<nb, IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev, done, out2, step_ctr);
+  FinTail ft;
+  if (fin) ft = *fin;  // (its rows must not be `partials`: this kernel's CTAs write theirs there)
+  kick_sums_kernel<<<nb + (ft.nb > 0 ? 1 : 0), IT, 0, st>>>(n3, v, f, half_dt, partials, n_dev, done, out2, step_ctr, ft);
   ATLJ_LAUNCHED();
   return ATLJ_OK;
 }

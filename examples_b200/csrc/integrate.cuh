@@ -64,7 +64,8 @@ int launch_kick_drift(cudaStream_t st, long long n3, double *r, double *v, const
                       double box, const double *vscale, const int *n_dev = nullptr);  // box: plain length
 // done: a device int that is 0 on entry (the kernel leaves it 0): counts finished CTAs for the in-kernel final sum
 int launch_kick_sums(cudaStream_t st, long long n3, double *v, const double *f, double half_dt, double *partials,
-                     double *out2, int *done, const int *n_dev = nullptr, int *step_ctr = nullptr);
+                     double *out2, int *done, const int *n_dev = nullptr, int *step_ctr = nullptr,
+                     const struct FinTail *fin = nullptr);
 int launch_vf_sums(cudaStream_t st, long long n3, const double *v, const double *f, double *partials, double *out2);
 int launch_unsort(cudaStream_t st, int n, const int *id, const double *in, double *out);
 int launch_iota(cudaStream_t st, int n, int *id);

@@ -132,6 +132,51 @@ __device__ __forceinline__ void finalize_totals(const double *t, int model, bool
   rec[8] = t[5] * 0.5;              // in-range pairs, counted once
 }
 
+// Fixed-order reduction of the pair kernels' per-CTA rows [nblocks][8] into the step record by ONE CTA of BT threads
+// (md_lj_module.py:143-147 scaling included).  finalize_kernel is this and nothing else; the loops that launch an
+// elementwise kernel right after the force evaluation (BAOAB's half kick, SLLOD's sums) run it as an extra CTA of that
+// kernel instead (FinTail): 9 us with one SM working otherwise.
+struct FinTail {
+  const double *partials = nullptr;
+  int nb = 0;                   // 0: nothing pending
+  int model = 0;
+  double *rec = nullptr;
+  int *reset_counter = nullptr;
+  const int *rows_dev = nullptr;
+};
+template <int BT>
+__device__ __forceinline__ void finalize_rows_block(const FinTail &t) {
+  int nblocks = t.nb;
+  if (t.rows_dev) nblocks = min(nblocks, *t.rows_dev);
+  if (threadIdx.x == 0 && t.reset_counter) *t.reset_counter = 0;
+  __shared__ double fsm[BT / 32][7];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblocks; b += BT) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) v[k] += t.partials[8 * (size_t)b + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) fsm[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt[7];
+    for (int k = 0; k < 7; k++) {
+      double a = 0.0;
+      for (int w = 0; w < BT / 32; w++) a += fsm[w][k];
+      tt[k] = a;
+    }
+    finalize_totals(tt, t.model, false, t.rec);
+  }
+}
+
 // 1/x to ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + two Newton steps; used only where no predicate depends on it
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pair_math.cuh"
 
 // slab decomposition state (mg.cu)
 // Per-atom arrays of a slab rank: [0, own_cap) owned atoms (cell order), [own_cap, own_cap + halo_cap) the left
@@ -45,6 +46,8 @@ struct atlj_sim {
   int64_t n_total = 0;       // atoms of the whole system (all ranks); indexes injected noise by global id
   long long step_count = 0;  // steps taken so far (counter of the device RNG)
   bool configured = false;
+  bool defer_fin = false;   // set by a loop before sim_force: leave the totals' final reduction to my next kernel ...
+  atlj::FinTail fin;        // ... which finds it here (nb = 0: sim_force has launched finalize_kernel itself)
   bool forces_valid = false;  // s->f belongs to the current positions (cleared by upload / configure, set by sim_force)
   bool use_cells = false;  // sc >= 4: link-cell route; otherwise all pairs
   atlj::Geom g{};
