@@ -380,10 +380,12 @@ int atlj_sim_run_baoab_mg(atlj_sim *s, double dt, double o_decay, double o_noise
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     if ((rc = baoab_move(s, dt, o_decay, o_noise, nullptr, seed, (unsigned)(s->step_count + k)))) return rc;
+    s->defer_fin = true;  // the half kick below finishes the force totals in an extra CTA (FinTail)
     if ((rc = mg_assign_exchange_force(s, rec, k == 0))) return rc;
     if ((rc = launch_kick_sums(s->st, 3 * mg_own_cap(s), s->v[s->cur], s->f, dt / 2, s->vf_partials, rec + 4,
-                               s->cb.err + 4, mg_n_dev(s))))
+                               s->cb.err + 4, mg_n_dev(s), nullptr, s->fin.nb > 0 ? &s->fin : nullptr)))
       return rc;
+    s->fin = FinTail();
   }
   if (nsteps > 0 && (rc = mg_allreduce(s, s->rec_dev, (size_t)nsteps * ATLJ_NREC))) return rc;
   s->step_count += nsteps;
@@ -414,10 +416,12 @@ int atlj_sim_run_nhc_mg(atlj_sim *s, double dt, double temperature, double g, in
   for (int k = 0; k < nsteps; k++) {
     double *rec = s->rec_dev + (size_t)k * ATLJ_NREC;
     if ((rc = nhc_move(s, dt, temperature, g, m, k == 0 ? ksq : nullptr))) return rc;
+    s->defer_fin = true;
     if ((rc = mg_assign_exchange_force(s, rec, k == 0))) return rc;
     if ((rc = launch_kick_sums(s->st, 3 * mg_own_cap(s), s->v[s->cur], s->f, 0.5 * dt, s->vf_partials, rec + 4,
-                               s->cb.err + 4, mg_n_dev(s))))
+                               s->cb.err + 4, mg_n_dev(s), nullptr, s->fin.nb > 0 ? &s->fin : nullptr)))
       return rc;
+    s->fin = FinTail();
     // the chain needs the GLOBAL sum v^2: the whole record of the step is summed over the ranks here
     if ((rc = mg_allreduce(s, rec, ATLJ_NREC)) || (rc = nhc_close(s, dt, temperature, g, m, rec))) return rc;
   }
@@ -522,9 +526,13 @@ int atlj_sim_run_nhc(atlj_sim *s, double dt, double temperature, double g, int m
     set_scalar_kernel<<<1, 1, 0, s->st>>>(st + 1, 1.0);
     ATLJ_LAUNCHED();
     Timer::end(s);
+    s->defer_fin = true;  // the half kick below finishes the force totals in an extra CTA (FinTail)
     if ((rc = sim_force(s, 0.0, false, rec, false))) return rc;
     Timer::begin(s, 2);
-    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->partials, rec + 4, s->cb.err + 4))) return rc;
+    if ((rc = launch_kick_sums(s->st, n3, s->v[s->cur], s->f, half_dt, s->vf_partials, rec + 4, s->cb.err + 4, nullptr,
+                               nullptr, s->fin.nb > 0 ? &s->fin : nullptr)))
+      return rc;
+    s->fin = FinTail();
     nhc_chain_kernel<<<1, 32, 0, s->st>>>(st, m, dt, temperature, g, rec + 4, rec);
     ATLJ_LAUNCHED();
     Timer::end(s);

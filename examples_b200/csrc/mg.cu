@@ -462,6 +462,13 @@ int mg_assign_exchange_force(atlj_sim *s, double *rec, bool first) {
   if ((rc = phase1(s, s->st, 0.0, false, nullptr, 0, false, !first, true)) || (rc = phase2(s, s->st, nullptr, rec, false)))
     return rc;
   if ((nb = phase3(s, s->st, false)) < 0) return nb;
+  s->fin = FinTail();
+  if (s->defer_fin) {  // the caller's half kick finishes the totals in an extra CTA (FinTail, pair_math.cuh)
+    s->defer_fin = false;
+    s->fin.partials = s->partials, s->fin.nb = nb, s->fin.model = s->p.model, s->fin.rec = rec;
+    s->fin.reset_counter = s->cb.err + 2, s->fin.rows_dev = tile2_rows(s);
+    return ATLJ_OK;
+  }
   return launch_finalize(s->st, s->partials, nb, s->p.model, false, rec, s->cb.err + 2, nullptr, 0, tile2_rows(s));
 }
 // emulation (ranks of one process in lockstep): phase 1 of a step whose atoms were moved by another integrator
